@@ -1,0 +1,411 @@
+// csrc/friq_device.cuh -- device functions of the FRIQ-learning hot path (sm_100a).
+//
+// One THREAD owns one agent (its state lives in registers for the whole launch) and walks
+// its private rule base in rule order, so every sum is accumulated in exactly the order
+// the reference uses (sequential over rules i = 0..R-1, left-to-right over dimensions) and
+// the results are bit-identical to the reference's C/AVX2 code - no tree reductions.
+// The 32 agents of a warp form a rule-base tile laid out [slot][lane], so the warp's loads
+// of slot i are one coalesced 128 B (packed antecedents) + 256 B (consequents) transaction.
+// All FP64 arithmetic uses the _rn intrinsics: no FMA contraction (the reference is built
+// without -mfma; its AVX2 blocks use vmulpd + vaddpd).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "friq_devprob.h"
+#include "friq_math.cuh"
+#include "friq_trig.h"
+
+#define FRIQ_PI 3.14159265358979323846264338327
+
+// ---------------------------------------------------------------------------------------
+// TMA staging of the problem block: one cp.async.bulk (UBLKCP) per CTA, completion on an
+// mbarrier.  Called by every thread of the CTA; returns when the bytes have landed.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void friq_stage_problem(const friq_devprob *gprob, void *smem_dst, uint64_t *mbar)
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FRIQ_DEVPROB_SMEM_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(gprob), "r"(FRIQ_DEVPROB_SMEM_BYTES), "r"(bar) : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// nearest universe index, src/inl/min.inl:71-92 (ties -> lower index).  `len` is U except
+// for the action VE values of frirl_init.c:157, which pass U-1.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int friq_nearest_index(const friq_devprob &pb, int k, double x, int len)
+{
+    const double *u = pb.u + (size_t)k * pb.U;
+    const int low = (int)__ddiv_rn(__dsub_rn(x, pb.u0[k]), pb.udiv[k]);
+    if (low < 0) return 0;
+    if (low >= len) return len - 1;
+    if (low + 1 >= pb.U) return low;
+    const double d1 = fabs(__dsub_rn(__ldg(u + low), x)), d2 = fabs(__dsub_rn(__ldg(u + low + 1), x));
+    return d1 <= d2 ? low : low + 1;
+}
+__device__ __forceinline__ double friq_obs_ve(const friq_devprob &pb, int k, double x)
+{
+    return __ldg(pb.ve + (size_t)k * pb.U + friq_nearest_index(pb, k, x, pb.U));
+}
+
+// squared scaled distance over the first N dimensions of the rule packed in w from the point
+// with per-dimension VE values vo[] (five_rule_distance.c:82-100 + :160-212, A1/A2)
+template <int N>
+__device__ __forceinline__ double friq_dist2(const friq_devprob &pb, uint32_t w, const double *vo)
+{
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const double v = pb.dict_ve[k][(w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+        const double d = __dsub_rn(vo[k], v);
+        const double d2 = __dmul_rn(d, d);
+        s = (k == 0) ? d2 : __dadd_rn(s, d2);
+    }
+    return s;
+}
+
+template <int P>
+__device__ __forceinline__ double friq_shepard_weight(double s)
+{
+    const double d = __dsqrt_rn(s);                       // vsqrtpd, five_rule_distance.c:205
+    return __drcp_rn(friq_pow_x87<P>(d));                 // 1.0 / fast_pow(|d|, p)
+}
+
+// first rule whose distance from vo[] (all K dims) is exactly 0, else -1
+// (five_rule_distance.c:206-262 early exit + FIVEVagConcl.c:96-105 rescan)
+template <int K>
+__device__ __forceinline__ int friq_first_hit(const friq_devprob &pb, const uint32_t *rbw, int R, const double *vo)
+{
+    for (int i = 0; i < R; i++)
+        if (friq_dist2<K>(pb, rbw[(size_t)i * FRIQ_TILE], vo) == 0.0) return i;
+    return -1;
+}
+
+// sequential Shepard sums over all rules (FIVEVagConcl.c:224-235, FIVEVagConclWeight.c:125-136);
+// optionally keeps wi in sw[] for the weighted update.
+template <int K, int P>
+__device__ __forceinline__ void friq_shepard(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
+                                             const double *vo, double &vagc, double &ws)
+{
+    vagc = 0.0; ws = 0.0;
+    for (int i = 0; i < R; i++) {
+        const double s = friq_dist2<K>(pb, rbw[(size_t)i * FRIQ_TILE], vo);
+        const double wi = friq_shepard_weight<P>(s);
+        if (sw) sw[(size_t)i * FRIQ_TILE] = wi;
+        vagc = __dadd_rn(vagc, __dmul_rn(wi, rbq[(size_t)i * FRIQ_TILE]));
+        ws = __dadd_rn(ws, wi);
+    }
+}
+
+// FIVE_vag_concl (FIVEVagConcl.c:64-351): returns hit index or -1, conclusion in conc
+template <int K, int P>
+__device__ __forceinline__ int friq_vag_concl(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
+                                              const double *vo, double &conc, double &ws)
+{
+    const int hit = friq_first_hit<K>(pb, rbw, R, vo);
+    if (hit >= 0) { conc = rbq[(size_t)hit * FRIQ_TILE]; ws = 0.0; return hit; }
+    double vagc;
+    friq_shepard<K, P>(pb, rbw, rbq, sw, R, vo, vagc, ws);
+    conc = __ddiv_rn(vagc, ws);
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------
+// frirl_get_best_action (frirl_get_best_action.c:31-341) + FIVEVagConcl_FRIRL_BestAct
+// (:56-301), all A actions in one pass over the rule base (ACH actions per pass when A is
+// large).  With PIGGY the same pass also finds the first rule at distance 0 from the
+// previous step's antecedents vo_q[] (the exact-hit test of Q(s,a) in frirl_update_sarsa):
+// it re-uses the dictionary loads of the pass and costs ~3(S+1) FP64 ops per rule instead
+// of a second sweep.
+// ---------------------------------------------------------------------------------------
+template <int S, int P, int A, int ACH, bool PIGGY>
+__device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, int R,
+                                                      const double *vo_obs, double *actconc, const double *vo_q, int &hitq)
+{
+    static_assert(A % ACH == 0, "action chunking");
+    hitq = -1;
+#pragma unroll 1
+    for (int c0 = 0; c0 < A; c0 += ACH) {
+        double vagc[ACH], ws[ACH], hq[ACH], ave[ACH];
+        unsigned hitmask = 0;
+#pragma unroll
+        for (int a = 0; a < ACH; a++) { vagc[a] = 0.0; ws[a] = 0.0; hq[a] = 0.0; ave[a] = pb.act_ve[c0 + a]; }
+        uint32_t w = 0; double q = 0.0;
+        if (R > 0) { w = rbw[0]; q = rbq[0]; }
+#pragma unroll 1
+        for (int i = 0; i < R; i++) {
+            uint32_t wn = 0; double qn = 0.0;
+            if (i + 1 < R) { wn = rbw[(size_t)(i + 1) * FRIQ_TILE]; qn = rbq[(size_t)(i + 1) * FRIQ_TILE]; }   // prefetch
+            double ssum = 0.0, sq = 0.0;
+#pragma unroll
+            for (int k = 0; k < S; k++) {
+                const double v = pb.dict_ve[k][(w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+                const double d = __dsub_rn(vo_obs[k], v);
+                const double d2 = __dmul_rn(d, d);
+                ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                                  // A3/A4
+                if (PIGGY) {
+                    const double e = __dsub_rn(vo_q[k], v);
+                    const double e2 = __dmul_rn(e, e);
+                    sq = (k == 0) ? e2 : __dadd_rn(sq, e2);
+                }
+            }
+            const double va = pb.dict_ve[S][(w >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)];
+            if (PIGGY) {
+                if (c0 == 0) {
+                    const double e = __dsub_rn(vo_q[S], va);
+                    sq = __dadd_rn(sq, __dmul_rn(e, e));
+                    if (sq == 0.0 && hitq < 0) hitq = i;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < ACH; a++) {
+                const double da = __dsub_rn(ave[a], va);
+                const double s = __dadd_rn(__dmul_rn(da, da), ssum);                         // A5
+                const bool z = (s == 0.0);
+                if (z && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q; }           // BestAct.c:89-93
+                const double wi = friq_shepard_weight<P>(z ? 1.0 : s);
+                vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wi, q));                               // BestAct.c:216
+                ws[a] = __dadd_rn(ws[a], wi);                                                 // :217
+            }
+            w = wn; q = qn;
+        }
+#pragma unroll
+        for (int a = 0; a < ACH; a++)
+            actconc[c0 + a] = ((hitmask >> a) & 1u) ? hq[a] : __ddiv_rn(vagc[a], ws[a]);      // :265
+    }
+}
+
+// first index of the maximum (src/inl/max.inl:16-28, strict <)
+template <int A>
+__device__ __forceinline__ int friq_argmax(const double *v)
+{
+    int best = 0; double bv = v[0];
+#pragma unroll
+    for (int i = 1; i < A; i++) if (bv < v[i]) { bv = v[i]; best = i; }
+    return best;
+}
+template <int A>
+__device__ __forceinline__ double friq_pick(const double *v, int idx)
+{
+    double r = v[0];
+#pragma unroll
+    for (int i = 1; i < A; i++) if (i == idx) r = v[i];
+    return r;
+}
+
+// frirl_e_greedy_selection.c:21-37 with the Philox stream (explore when u1 <= epsilon; the
+// random action is min(A-1, floor(u2*A)) - the reference's round(u*A) can return A).
+template <int A>
+__device__ __forceinline__ int friq_select_action(const friq_devprob &pb, const double *actconc, double epsilon,
+                                                  unsigned long long seed, uint32_t episode, uint32_t step)
+{
+    int best = friq_argmax<A>(actconc);
+    if (pb.no_random == 1 || epsilon == 0.0) return best;
+    uint32_t r[4];
+    friq_philox4x32_10(episode, step, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u1 = (double)((((uint64_t)r[1] << 32) | r[0]) >> 11) * 0x1p-53;
+    const double u2 = (double)((((uint64_t)r[3] << 32) | r[2]) >> 11) * 0x1p-53;
+    if (u1 > epsilon) return best;
+    const int ra = (int)floor(__dmul_rn(u2, (double)A));
+    return ra > A - 1 ? A - 1 : ra;
+}
+
+// frirl_check_possible_states.c:53-122: index of the grid value the observation snaps to
+// (ties -> upper).  The grid-refinement branch (:68) cannot fire when epsilon equals the
+// grid step; the host layer rejects problems where it could.
+__device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, double x)
+{
+    const double *g = pb.dict_val[k];
+    const int n = pb.grid_len[k];
+    int i;
+    for (i = 0; i < n; i++) if (x < g[i]) break;
+    if (i == n) return n - 1;
+    if (i == 0) return 0;
+    i--;
+    return (__dsub_rn(x, g[i]) < __dsub_rn(g[i + 1], x)) ? i : i + 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// frirl_update_sarsa (frirl_update_sarsa.c:348-385) + update_rules (:22-143), given
+//   qp            Q(s',a')                                  (:355)
+//   hitq / qnow   exact-hit rule and value of Q(s,a)        (:356); when hitq < 0, sw[] holds
+//                 the wi of that evaluation and ws their sequential sum (re-used by
+//                 FIVE_vag_concl_weight, FIVEVagConclWeight.c:125-175, same point, same RB)
+//   qs[] / vo_q[] the antecedents (s,a) and their VE values.
+// ---------------------------------------------------------------------------------------
+template <int S, int P>
+__device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
+                                                 const double *qs, double reward, double qp, int hitq, double qnow, double ws,
+                                                 double alpha, double gamma)
+{
+    constexpr int K = S + 1;
+    const double qdiff = __dmul_rn(alpha, __dsub_rn(__dadd_rn(reward, __dmul_rn(gamma, qp)), qnow));   // :358
+    if (qdiff > pb.qdiff_pos || qdiff < pb.qdiff_neg) {
+        int gi[K]; bool same = true; uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            gi[k] = friq_snap_index(pb, k, qs[k]);                                               // :146-170
+            same = same && (pb.dict_val[k][gi[k]] == qs[k]);
+            packed |= (uint32_t)gi[k] << (FRIQ_IDX_BITS * k);
+        }
+        int hitg = hitq; double qg = qnow;
+        if (!same) {                                   // snapped point differs: evaluate Q there (:370)
+            double vg[K], wsg;
+#pragma unroll
+            for (int k = 0; k < K; k++) vg[k] = pb.dict_ve[k][gi[k]];
+            hitg = friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vg, qg, wsg);
+        }
+        if (hitg < 0) {                                // no rule there: append (five_add_rule.c:47-95)
+            flags |= FRIQ_F_INSERTED;
+            if (R < cap) { rbw[(size_t)R * FRIQ_TILE] = packed; rbq[(size_t)R * FRIQ_TILE] = __dadd_rn(qg, qdiff); R++; }
+            else flags |= FRIQ_F_OVERFLOW;
+            return;
+        }
+        flags &= ~FRIQ_F_INSERTED;                     // :378
+    }
+    int rules = R - ((flags & FRIQ_F_INSERTED) ? 1 : 0);
+    if (hitq >= 0) {
+        if (pb.skip_rules == 0 || hitq < rules) rbq[(size_t)hitq * FRIQ_TILE] = __dadd_rn(qnow, qdiff);   // :55
+        return;                                                                                          // :61-63
+    }
+    if (pb.skip_rules == 0) { rules = R; flags &= ~FRIQ_F_INSERTED; }
+    const double pre = __dmul_rn(0.04, ws);            // cheap superset of (wi/ws > wsig >= 0.05)
+    const bool filter = pb.wsig >= 0.05;
+    for (int i = 0; i < rules; i++) {
+        const double wi = sw[(size_t)i * FRIQ_TILE];
+        if (filter && !(wi > pre)) continue;
+        const double wgt = __ddiv_rn(wi, ws);                                                            // A6
+        if (wgt > pb.wsig) rbq[(size_t)i * FRIQ_TILE] = __dadd_rn(qnow, __dmul_rn(qdiff, wgt));          // A7
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Environments (the example drivers' callbacks).  Expressions keep the reference's
+// operation order; constant sub-expressions fold exactly as gcc folds them.
+// ---------------------------------------------------------------------------------------
+template <int ENV> __device__ __forceinline__ void friq_env_step(double action, const double *s, double *n);
+template <int ENV> __device__ __forceinline__ void friq_env_reward(const double *s, double &reward, int &done);
+
+template <> __device__ __forceinline__ void friq_env_step<FRIQ_ENV_MOUNTAINCAR>(double action, const double *s, double *n)
+{   // mountaincar.c:37-74
+    double v = __dmul_rn(__dadd_rn(__dadd_rn(s[1], __dmul_rn(0.001, action)), __dmul_rn(-0.0025, friq_cos(__dmul_rn(3.0, s[0])))), 0.999);
+    if (v < -0.07) v = -0.07;
+    if (v > 0.07) v = 0.07;
+    double x = __dadd_rn(s[0], v);
+    if (x <= -1.5) { x = -1.5; v = 0.0; }
+    n[0] = x; n[1] = v;
+}
+template <> __device__ __forceinline__ void friq_env_reward<FRIQ_ENV_MOUNTAINCAR>(const double *s, double &reward, int &done)
+{   // mountaincar.c:77-95
+    if (s[0] >= 0.45) { reward = 1000.0; done = 1; } else { reward = -10.0; done = 0; }
+}
+
+template <> __device__ __forceinline__ void friq_env_step<FRIQ_ENV_ACROBOT>(double action, const double *s, double *n)
+{   // acrobot.c:31-130 (accelerations once, then four Euler sub-steps - "Adam White's loop")
+    const double max1 = 4 * FRIQ_PI, max2 = 9 * FRIQ_PI, g = 9.8, dt = 0.05;
+    double t1 = s[0], t2 = s[1], w1 = s[2], w2 = s[3];
+    double s2, c2;
+    friq_sincos(t2, &s2, &c2);
+    const double d1 = __dadd_rn(__dadd_rn(__dadd_rn(0.25, __dadd_rn(1.25, c2)), 1.0), 1.0);
+    const double d2 = __dadd_rn(__dadd_rn(0.25, __dmul_rn(0.5, c2)), 1.0);
+    const double phi2 = __dmul_rn(0.5 * g, friq_cos(__dsub_rn(__dadd_rn(t1, t2), FRIQ_PI / 2)));
+    const double phi1 = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(-0.5, w2), s2), __dsub_rn(w2, __dmul_rn(2.0, w1))),
+                                            __dmul_rn((1.0 * 0.5 + 1.0 * 1.0) * g, friq_cos(__dsub_rn(t1, FRIQ_PI / 2)))), phi2);
+    double acc2 = __dsub_rn(__dsub_rn(__dadd_rn(action, __dmul_rn(phi1, __ddiv_rn(d2, d1))),
+                                      __dmul_rn(__dmul_rn(__dmul_rn(0.5, w1), w1), s2)), phi2);
+    acc2 = __ddiv_rn(acc2, __dsub_rn(1.25, __ddiv_rn(__dmul_rn(d2, d2), d1)));
+    const double acc1 = __ddiv_rn(-__dadd_rn(__dmul_rn(d2, acc2), phi1), d1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        w1 = __dadd_rn(w1, __dmul_rn(acc1, dt));
+        if (w1 < -max1) w1 = -max1;
+        if (w1 > max1) w1 = max1;
+        t1 = __dadd_rn(t1, __dmul_rn(w1, dt));
+        w2 = __dadd_rn(w2, __dmul_rn(acc2, dt));
+        if (w2 < -max2) w2 = -max2;
+        if (w2 > max2) w2 = max2;
+        t2 = __dadd_rn(t2, __dmul_rn(w2, dt));
+    }
+    if (t1 < -FRIQ_PI) t1 = -FRIQ_PI;
+    if (t1 > FRIQ_PI) t1 = FRIQ_PI;
+    if (t2 < -FRIQ_PI) t2 = -FRIQ_PI;
+    if (t2 > FRIQ_PI) t2 = FRIQ_PI;
+    n[0] = t1; n[1] = t2; n[2] = w1; n[3] = w2;
+}
+template <> __device__ __forceinline__ void friq_env_reward<FRIQ_ENV_ACROBOT>(const double *s, double &reward, int &done)
+{   // acrobot.c:133-162
+    const double y1 = __dsub_rn(0.0, friq_cos(s[0]));
+    const double y2 = __dsub_rn(y1, friq_cos(s[1]));
+    if (y2 >= 1.0) { reward = 1000.0; done = 1; } else { reward = -10.0; done = 0; }
+}
+
+template <> __device__ __forceinline__ void friq_env_step<FRIQ_ENV_CARTPOLE>(double action, const double *s, double *n)
+{   // cartpole.c:35-77 (Euler, tau = 0.02)
+    const double g = 9.8, total_mass = 1.0 + 0.1, pml = 0.1 * 0.5, tau = 0.02, fourthirds = 4.0 / 3.0;
+    const double x = s[0], xd = s[1], th = s[2], thd = s[3];
+    double sn, cs;
+    friq_sincos(th, &sn, &cs);
+    const double force = __dmul_rn(action, 10.0);
+    const double temp = __ddiv_rn(__dadd_rn(force, __dmul_rn(__dmul_rn(__dmul_rn(pml, thd), thd), sn)), total_mass);
+    const double thacc = __ddiv_rn(__dsub_rn(__dmul_rn(g, sn), __dmul_rn(cs, temp)),
+                                   __dmul_rn(0.5, __dsub_rn(fourthirds, __ddiv_rn(__dmul_rn(__dmul_rn(0.1, cs), cs), total_mass))));
+    const double xacc = __dsub_rn(temp, __ddiv_rn(__dmul_rn(__dmul_rn(pml, thacc), cs), total_mass));
+    n[0] = __dadd_rn(x, __dmul_rn(tau, xd));
+    n[1] = __dadd_rn(xd, __dmul_rn(tau, xacc));
+    n[2] = __dadd_rn(th, __dmul_rn(tau, thd));
+    n[3] = __dadd_rn(thd, __dmul_rn(tau, thacc));
+}
+template <> __device__ __forceinline__ void friq_env_reward<FRIQ_ENV_CARTPOLE>(const double *s, double &reward, int &done)
+{   // cartpole.c:79-112 ("success" is the failure-termination flag here)
+    const double deg45 = FRIQ_PI / 4;
+    const double x = s[0], th = s[2], thd = s[3];
+    if (x < -4.0 || x > 4.0 || th < (-1 * deg45) || th > deg45) {
+        reward = __dsub_rn(__dsub_rn(-10000.0, __dmul_rn(50.0, fabs(x))), __dmul_rn(100.0, fabs(th)));
+        done = 1;
+    } else {
+        reward = __dsub_rn(__dsub_rn(__dsub_rn(10.0, __dmul_rn(__dmul_rn(1000.0, th), th)), __dmul_rn(5.0, fabs(x))), __dmul_rn(10.0, thd));
+        done = 0;
+    }
+}
+
+// quantise_observations: writes the quantised state q[] and its VE values vo[]
+template <int ENV, int S>
+__device__ __forceinline__ void friq_env_quantize(const friq_devprob &pb, const double *s, double *q, double *vo)
+{
+    if (ENV == FRIQ_ENV_CARTPOLE) {                      // cartpole.c:114-168
+        const double deg12 = FRIQ_PI / 15, deg3 = FRIQ_PI / 60;
+        double x0 = s[0], x1 = round(s[1]), x2 = __dmul_rn(floor(__ddiv_rn(s[2], deg3)), deg3), x3 = s[3];
+        if (x0 < 0) x0 = -1;
+        if (x0 > 0) x0 = 1;
+        if (x1 < -1) x1 = -1;
+        if (x1 > 1) x1 = 1;
+        if (x2 > deg12) x2 = deg12;
+        if (x2 < (-1 * deg12)) x2 = -1 * deg12;
+        if (x3 < 0) x3 = -1;
+        if (x3 > 0) x3 = 1;
+        q[0] = x0; q[1] = x1; q[2] = x2; q[3] = x3;
+#pragma unroll
+        for (int k = 0; k < S; k++) vo[k] = friq_obs_ve(pb, k, q[k]);
+    } else {                                             // mountaincar.c:98-125, acrobot.c:165-192
+#pragma unroll
+        for (int k = 0; k < S; k++) {
+            int where = (int)round(__ddiv_rn(__dadd_rn(s[k], pb.q_abs0[k]), pb.q_div[k]));
+            if (where < 0) where = 0; else if (where > pb.grid_len[k] - 1) where = pb.grid_len[k] - 1;
+            q[k] = pb.dict_val[k][where];
+            vo[k] = pb.dict_ve[k][where];                // = VE_k[nearest_index(values[where])]
+        }
+    }
+}

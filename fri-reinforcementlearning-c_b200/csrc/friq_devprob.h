@@ -1,0 +1,115 @@
+/* csrc/friq_devprob.h -- layouts shared by the ANSI-C host layer (friq_host.c) and
+ * the CUDA layer (friq_engine.cu).  Plain C, no CUDA types.
+ *
+ * friq_devprob is the read-only "problem block": everything the fused step kernel
+ * needs about the FRIQ problem (what struct FIVERB + struct frirl_desc hold on the
+ * host in the reference: FIVE.h:24-76, frirl_types.h:62-169), reduced to what the
+ * path touches.  It is ~9.7 KB and is staged into shared memory with one TMA bulk
+ * copy (cp.async.bulk + mbarrier) per CTA.
+ *
+ * Rule storage.  A rule's antecedent in dimension k is stored as a 6-bit index
+ * into a per-dimension *value dictionary* dict_val[k][] (the grid values of
+ * frirl_init.c:55-102 first - every rule the learner inserts is grid-snapped,
+ * frirl_update_sarsa.c:367-375 - then any extra value met in a loaded rule base).
+ * dict_ve[k][j] = VE_k[nearest_index(dict_val[k][j])] is exactly what
+ * five_add_rule.c:71-84 caches in rseqant_veval.  K*6 <= 32 bits => one u32 per
+ * rule; the consequent is one f64.
+ */
+#ifndef FRIQ_DEVPROB_H
+#define FRIQ_DEVPROB_H
+#include <stddef.h>
+
+#define FRIQ_MAXK 8          /* FIVE_MAX_NUM_OF_UNIVERSES, FIVE.h:19 */
+#define FRIQ_MAXDICT 64
+#define FRIQ_IDX_BITS 6
+#define FRIQ_MAXA 32
+#define FRIQ_TILE 32         /* agents per rule-base tile (= one warp) */
+
+#define FRIQ_ENV_NONE (-1)
+#ifndef FRIQ_ENV_MOUNTAINCAR            /* same values as include/friq_b200.h */
+#define FRIQ_ENV_MOUNTAINCAR 0
+#define FRIQ_ENV_ACROBOT 1
+#define FRIQ_ENV_CARTPOLE 2
+#endif
+
+/* per-agent flag bits */
+enum { FRIQ_F_NEED_RESET = 1, FRIQ_F_INSERTED = 2, FRIQ_F_CONVERGED = 4, FRIQ_F_OVERFLOW = 8 };
+/* run mode bits */
+enum { FRIQ_M_LEARN = 1, FRIQ_M_TRACK = 2, FRIQ_M_STOP_ON_CONVERGE = 4, FRIQ_M_STOP_AT_EPISODE_END = 8 };
+
+typedef struct friq_devprob {
+    int S, K, A, U, p, env, skip_rules, no_random;
+    int max_steps, max_episodes, qp_reuse, ncorner;
+    int grid_len[FRIQ_MAXK];
+    int dict_len[FRIQ_MAXK];
+    int act_dict[FRIQ_MAXA];                  /* dictionary index (dimension S) of action a */
+    double qdiff_pos, qdiff_neg, wsig, qdiff_final_tol, reward_good_above, pad0;
+    double u0[FRIQ_MAXK], udiv[FRIQ_MAXK];
+    double values_def[FRIQ_MAXK], ve_def[FRIQ_MAXK];
+    double q_abs0[FRIQ_MAXK], q_div[FRIQ_MAXK];   /* quantiser of mountaincar.c:98-125 / acrobot.c:165-192 */
+    double act_val[FRIQ_MAXA];
+    double act_ve[FRIQ_MAXA];                 /* possible_actions->vevalues (frirl_init.c:156-158, len = U-1) */
+    double act_ve_eval[FRIQ_MAXA];            /* VE_act[nearest_index(act_val)] as five_rule_distance sees it */
+    double dict_val[FRIQ_MAXK][FRIQ_MAXDICT];
+    double dict_ve[FRIQ_MAXK][FRIQ_MAXDICT];
+    const double *u, *ve;                     /* device pointers, [K][U] row-major */
+    /* ---- everything above is staged to shared memory; the tail stays in global ---- */
+    unsigned int corner[256];                 /* packed 2^K corner rules, frirl_init_rb.c:99-126 */
+} friq_devprob;
+
+/* bytes staged to shared memory (multiple of 16) */
+#define FRIQ_DEVPROB_SMEM_BYTES ((unsigned)((offsetof(friq_devprob, corner) + 15ul) & ~15ul))
+
+/* per-agent state, structure of arrays in device memory; n = agents padded to a tile */
+typedef struct friq_devstate {
+    long n, n_pad;
+    int cap;
+    unsigned int *rbw;          /* [tiles][cap][32] packed antecedent indices */
+    double *rbq;                /* [tiles][cap][32] consequents */
+    double *sw;                 /* [tiles][cap][32] scratch: Shepard weights wi of the last Q(s,a) */
+    double *prevq;              /* [tiles][cap][32] consequents at episode start (convergence test) */
+    double *s;                  /* [FRIQ_MAXK][n_pad] raw state */
+    double *qs;                 /* [FRIQ_MAXK][n_pad] quantised antecedents of the previous step (q_ant) */
+    double *vo;                 /* [FRIQ_MAXK][n_pad] their VE values */
+    int *aidx, *flags, *R, *step_in_ep, *last_steps, *last_rules, *prev_steps, *prev_numru;
+    unsigned int *ep_num;
+    double *ep_return, *last_return, *prev_reward;
+    unsigned long long *total_steps, *sum_rules, *seed;
+    double *alpha, *gamma, *epsilon;
+} friq_devstate;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* CUDA layer entry points (friq_engine.cu); return 0 or a cudaError_t value */
+int friqd_set_device(int device);
+int friqd_malloc(void **p, unsigned long bytes);
+int friqd_free(void *p);
+int friqd_memset(void *p, int v, unsigned long bytes);
+int friqd_h2d(void *dst, const void *src, unsigned long bytes);
+int friqd_d2h(void *dst, const void *src, unsigned long bytes);
+int friqd_d2d_async(void *dst, const void *src, unsigned long bytes, void *stream);
+int friqd_h2d_2d(void *dst, unsigned long dpitch, const void *src, unsigned long spitch, unsigned long width, unsigned long height);
+int friqd_d2h_2d(void *dst, unsigned long dpitch, const void *src, unsigned long spitch, unsigned long width, unsigned long height);
+int friqd_h2d_async(void *dst, const void *src, unsigned long bytes, void *stream);
+int friqd_d2h_async(void *dst, const void *src, unsigned long bytes, void *stream);
+int friqd_device_count(int *count);
+int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const double *d_q, int R, void *stream);
+int friqd_sync(void *stream);
+const char *friqd_error_string(int err);
+int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long long seed0, long first_agent,
+                      double alpha, double gamma, double epsilon, void *stream);
+int friqd_run_steps(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, void *stream);
+int friqd_vag_concl(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_conc, int *d_hit,
+                    double *d_weights, void *stream);
+int friqd_best_action(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_states, double *d_actconc,
+                      int *d_best, void *stream);
+int friqd_update_sarsa(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_qant, const double *d_reward,
+                       const double *d_curqant, void *stream);
+int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream);
+int friqd_pow_x87(const double *d_x, double *d_out, long n, int p, int force_exact, void *stream);
+int friqd_fp64_peak(double *out_ginstr_per_s, int iters);
+#ifdef __cplusplus
+}
+#endif
+#endif

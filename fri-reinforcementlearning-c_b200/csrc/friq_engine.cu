@@ -1,0 +1,378 @@
+// csrc/friq_engine.cu -- CUDA layer of the B200-native FRIQ-learning engine (sm_100a).
+//
+// Kernels
+//   k_run_steps      the fused persistent step kernel: for every agent, n env steps of
+//                    frirl_episode.c:86-186 (dynamics, reward, quantiser, best action over all
+//                    actions, epsilon-greedy, SARSA update / rule insertion), agent state in
+//                    registers, problem block staged to shared memory by TMA.
+//   k_vag_concl / k_best_action / k_update_sarsa
+//                    one call of FIVE_vag_concl(_weight) / frirl_get_best_action /
+//                    frirl_update_sarsa per agent: the per-call boundary of the reference API
+//                    (and the per-call parity tests); same device functions as the fused kernel.
+//   k_init_agents    corner-rule bases + episode bookkeeping (frirl_init_rb.c, frirl_init.c).
+// The extern "C" friqd_* functions are the thin C-ABI the ANSI-C host layer calls.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "friq_device.cuh"
+
+#define FRIQ_BLOCK 64
+
+struct __align__(16) friq_smem_t {
+    unsigned char prob[FRIQ_DEVPROB_SMEM_BYTES];
+    uint64_t mbar;
+};
+
+#define FRIQ_SMEM_PROLOGUE()                                                      \
+    __shared__ friq_smem_t sm;                                                    \
+    friq_stage_problem(gprob, sm.prob, &sm.mbar);                                 \
+    const friq_devprob &pb = *reinterpret_cast<const friq_devprob *>(sm.prob);    \
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;                  \
+    if (ag >= st.n) return;                                                       \
+    const size_t tile_off = (size_t)(ag >> 5) * st.cap * FRIQ_TILE + (ag & 31);   \
+    uint32_t *rbw = st.rbw + tile_off;                                            \
+    double *rbq = st.rbq + tile_off;                                              \
+    double *sw = st.sw + tile_off;
+
+// ---------------------------------------------------------------------------------------
+template <int S, int P, int A, int ACH, int ENV>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
+{
+    constexpr int K = S + 1;
+    FRIQ_SMEM_PROLOGUE();
+    double *prevq = st.prevq ? st.prevq + tile_off : nullptr;
+
+    // ---- agent state -> registers
+    double s[S], qs[K], vo[K];
+#pragma unroll
+    for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ag];
+#pragma unroll
+    for (int k = 0; k < K; k++) { qs[k] = st.qs[(size_t)k * st.n_pad + ag]; vo[k] = st.vo[(size_t)k * st.n_pad + ag]; }
+    int aidx = st.aidx[ag], flags = st.flags[ag], R = st.R[ag], step_in_ep = st.step_in_ep[ag];
+    uint32_t ep_num = st.ep_num[ag];
+    double ep_return = st.ep_return[ag];
+    double prev_reward = st.prev_reward[ag]; int prev_steps = st.prev_steps[ag], prev_numru = st.prev_numru[ag];
+    double last_return = st.last_return[ag]; int last_steps = st.last_steps[ag], last_rules = st.last_rules[ag];
+    unsigned long long total_steps = st.total_steps[ag], sum_rules = st.sum_rules[ag];
+    const unsigned long long seed = st.seed[ag];
+    const double alpha = st.alpha[ag], gamma = st.gamma[ag], epsilon = st.epsilon[ag];
+    const bool learn = mode & FRIQ_M_LEARN, track = (mode & FRIQ_M_TRACK) && prevq;
+
+    long done_steps = 0;
+    while (done_steps < n_steps) {
+        if ((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED)) break;
+        const bool initial = flags & FRIQ_F_NEED_RESET;
+        double cur[S], cq[S], vc[S], reward = 0.0; int done = 0;
+        if (initial) {                                   // frirl_episode.c:46-82
+#pragma unroll
+            for (int k = 0; k < S; k++) { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; cur[k] = cq[k] = s[k]; }
+            ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
+            prev_numru = R;
+            if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
+        } else {                                         // frirl_episode.c:97-112
+            friq_env_step<ENV>(pb.act_val[aidx], s, cur);
+            friq_env_reward<ENV>(cur, reward, done);
+            ep_return = __dadd_rn(ep_return, reward);
+            friq_env_quantize<ENV, S>(pb, cur, cq, vc);
+            step_in_ep++;
+        }
+        // best action at the new observation (+ exact-hit scan of Q(s,a) for the update)
+        double actconc[A]; int hitq;
+        friq_best_action_pass<S, P, A, ACH, true>(pb, rbw, rbq, R, vc, actconc, vo, hitq);
+        const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
+        if (initial) {
+            aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
+            continue;
+        }
+        sum_rules += (unsigned long long)R;
+        if (learn) {                                     // frirl_update_sarsa.c:348-385
+            double qp, qnow, ws = 0.0;
+            if (pb.qp_reuse) qp = friq_pick<A>(actconc, a2);      // Q(s',a') == actconc[a'] bit for bit
+            else {
+                double vq[K], wsd;
+#pragma unroll
+                for (int k = 0; k < S; k++) vq[k] = vc[k];
+                vq[S] = pb.act_ve_eval[a2];
+                friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vq, qp, wsd);
+            }
+            if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
+            else { double vagc; friq_shepard<K, P>(pb, rbw, rbq, sw, R, vo, vagc, ws); qnow = __ddiv_rn(vagc, ws); }
+            friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward, qp, hitq, qnow, ws, alpha, gamma);
+        }
+        // frirl_episode.c:163-185
+#pragma unroll
+        for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; }
+        aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
+        total_steps++; done_steps++;
+        if (done || step_in_ep >= pb.max_steps) {
+            // "RB complete" predicate, frirl_sequential_run.c:83-150
+            if (learn && track && prev_numru == R && prev_steps == step_in_ep && ep_return > pb.reward_good_above && prev_reward == ep_return) {
+                bool ok = true;
+                for (int i = 0; i < R && ok; i++)
+                    if (fabs(__dsub_rn(rbq[(size_t)i * FRIQ_TILE], prevq[(size_t)i * FRIQ_TILE])) >= pb.qdiff_final_tol) ok = false;
+                if (ok) flags |= FRIQ_F_CONVERGED;
+            }
+            last_return = ep_return; last_steps = step_in_ep; last_rules = R;
+            prev_reward = ep_return; prev_steps = step_in_ep;
+            ep_num++;
+            flags |= FRIQ_F_NEED_RESET;
+            if (mode & FRIQ_M_STOP_AT_EPISODE_END) break;
+        }
+    }
+
+    // ---- registers -> agent state
+#pragma unroll
+    for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
+#pragma unroll
+    for (int k = 0; k < K; k++) { st.qs[(size_t)k * st.n_pad + ag] = qs[k]; st.vo[(size_t)k * st.n_pad + ag] = vo[k]; }
+    st.aidx[ag] = aidx; st.flags[ag] = flags; st.R[ag] = R; st.step_in_ep[ag] = step_in_ep;
+    st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
+    st.prev_reward[ag] = prev_reward; st.prev_steps[ag] = prev_steps; st.prev_numru[ag] = prev_numru;
+    st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
+    st.total_steps[ag] = total_steps; st.sum_rules[ag] = sum_rules;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-call kernels
+// ---------------------------------------------------------------------------------------
+template <int S, int P>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+k_vag_concl(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ ant, double *conc, int *hit, double *weights)
+{
+    constexpr int K = S + 1;
+    FRIQ_SMEM_PROLOGUE();
+    double vo[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) vo[k] = friq_obs_ve(pb, k, ant[(size_t)ag * K + k]);       // five_rule_distance.c:75
+    const int R = st.R[ag];
+    double c, ws;
+    const int h = friq_vag_concl<K, P>(pb, rbw, rbq, sw, R, vo, c, ws);
+    if (conc) conc[ag] = c;
+    hit[ag] = h;
+    if (weights && h < 0)                                                                   // FIVEVagConclWeight.c:153-175
+        for (int i = 0; i < R; i++) weights[(size_t)ag * st.cap + i] = __ddiv_rn(sw[(size_t)i * FRIQ_TILE], ws);
+}
+
+template <int S, int P, int A, int ACH>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+k_best_action(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ states, double *actconc_out, int *best)
+{
+    FRIQ_SMEM_PROLOGUE();
+    (void)sw;
+    double vo[S], actconc[A];
+#pragma unroll
+    for (int k = 0; k < S; k++) vo[k] = friq_obs_ve(pb, k, states[(size_t)ag * S + k]);    // get_best_action.c:60-63
+    int hq;
+    friq_best_action_pass<S, P, A, ACH, false>(pb, rbw, rbq, st.R[ag], vo, actconc, nullptr, hq);
+#pragma unroll
+    for (int a = 0; a < A; a++) actconc_out[(size_t)ag * A + a] = actconc[a];
+    best[ag] = friq_argmax<A>(actconc);
+}
+
+template <int S, int P>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+k_update_sarsa(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ qant, const double *__restrict__ reward,
+               const double *__restrict__ curqant)
+{
+    constexpr int K = S + 1;
+    FRIQ_SMEM_PROLOGUE();
+    double qs[K], vq[K], vc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        qs[k] = qant[(size_t)ag * K + k];
+        vq[k] = friq_obs_ve(pb, k, qs[k]);
+        vc[k] = friq_obs_ve(pb, k, curqant[(size_t)ag * K + k]);
+    }
+    int R = st.R[ag], flags = st.flags[ag];
+    double qp, qnow, wsp, ws;
+    friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vc, qp, wsp);                 // :355
+    const int hitq = friq_vag_concl<K, P>(pb, rbw, rbq, sw, R, vq, qnow, ws);    // :356
+    friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward[ag], qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
+    st.R[ag] = R; st.flags[ag] = flags;
+}
+
+__global__ void k_init_agents(const friq_devprob *__restrict__ gprob, friq_devstate st, unsigned long long seed0, long first_agent,
+                              double alpha, double gamma, double epsilon)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n) return;
+    const size_t tile_off = (size_t)(ag >> 5) * st.cap * FRIQ_TILE + (ag & 31);
+    const int n = gprob->ncorner;
+    for (int i = 0; i < n; i++) { st.rbw[tile_off + (size_t)i * FRIQ_TILE] = gprob->corner[i]; st.rbq[tile_off + (size_t)i * FRIQ_TILE] = 0.0; }
+    for (int k = 0; k < FRIQ_MAXK; k++) { st.s[(size_t)k * st.n_pad + ag] = 0.0; st.qs[(size_t)k * st.n_pad + ag] = 0.0; st.vo[(size_t)k * st.n_pad + ag] = 0.0; }
+    st.R[ag] = n; st.aidx[ag] = 0; st.flags[ag] = FRIQ_F_NEED_RESET; st.step_in_ep[ag] = 0; st.ep_num[ag] = 1u;
+    st.ep_return[ag] = -1.0; st.prev_reward[ag] = -1.0; st.prev_steps[ag] = -1; st.prev_numru[ag] = n;     // frirl_init.c:144-145
+    st.last_return[ag] = 0.0; st.last_steps[ag] = 0; st.last_rules[ag] = n;
+    st.total_steps[ag] = 0ull; st.sum_rules[ag] = 0ull;
+    st.seed[ag] = seed0 + (unsigned long long)(first_agent + ag);
+    st.alpha[ag] = alpha; st.gamma[ag] = gamma; st.epsilon[ag] = epsilon;
+}
+
+__global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict__ words, const double *__restrict__ q, int R)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n) return;
+    const size_t tile_off = (size_t)(ag >> 5) * st.cap * FRIQ_TILE + (ag & 31);
+    for (int i = 0; i < R; i++) { st.rbw[tile_off + (size_t)i * FRIQ_TILE] = words[i]; st.rbq[tile_off + (size_t)i * FRIQ_TILE] = q[i]; }
+    st.R[ag] = R;
+}
+
+__global__ void k_trig(const double *x, double *s, double *c, long n)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) friq_sincos(x[i], &s[i], &c[i]);
+}
+__global__ void k_pow(const double *x, double *out, long n, int p, int force_exact)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = force_exact ? friq_pow_x87_exact(x[i], p) : friq_pow_x87_rt(x[i], p);
+}
+
+// FP64 issue-rate micro-benchmark: 8 independent DADD/DMUL chains per thread (no FMA, like the path)
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+    const double m = 1.0000000001, c = 1e-12;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { a[j] = __dmul_rn(a[j], m); a[j] = __dadd_rn(a[j], c); }
+    }
+    double r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r += a[j];
+    if (r == 123.456) out[0] = r;
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+static inline dim3 grid_for(long n) { return dim3((unsigned)((n + FRIQ_BLOCK - 1) / FRIQ_BLOCK)); }
+
+// supported problem shapes (S, p, A): the three example drivers.  ENV_NONE problems of the same
+// shape use the per-call kernels only.
+#define FRIQ_SHAPE_MC(pb) ((pb)->S == 2 && (pb)->p == 3 && (pb)->A == 3)
+#define FRIQ_SHAPE_AC(pb) ((pb)->S == 4 && (pb)->p == 5 && (pb)->A == 3)
+#define FRIQ_SHAPE_CP(pb) ((pb)->S == 4 && (pb)->p == 5 && (pb)->A == 21)
+#define FRIQ_ERR_SHAPE 9001
+
+extern "C" {
+
+int friqd_set_device(int device) { CK(cudaSetDevice(device)); return 0; }
+int friqd_malloc(void **p, unsigned long bytes) { CK(cudaMalloc(p, bytes)); return 0; }
+int friqd_free(void *p) { CK(cudaFree(p)); return 0; }
+int friqd_memset(void *p, int v, unsigned long bytes) { CK(cudaMemset(p, v, bytes)); return 0; }
+int friqd_h2d(void *dst, const void *src, unsigned long bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+int friqd_d2h(void *dst, const void *src, unsigned long bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
+int friqd_d2d_async(void *dst, const void *src, unsigned long bytes, void *stream)
+{ CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0; }
+int friqd_h2d_2d(void *dst, unsigned long dpitch, const void *src, unsigned long spitch, unsigned long width, unsigned long height)
+{ CK(cudaMemcpy2D(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice)); return 0; }
+int friqd_d2h_2d(void *dst, unsigned long dpitch, const void *src, unsigned long spitch, unsigned long width, unsigned long height)
+{ CK(cudaMemcpy2D(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost)); return 0; }
+int friqd_h2d_async(void *dst, const void *src, unsigned long bytes, void *stream)
+{ CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)); return 0; }
+int friqd_d2h_async(void *dst, const void *src, unsigned long bytes, void *stream)
+{ CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream)); return 0; }
+int friqd_device_count(int *count) { CK(cudaGetDeviceCount(count)); return 0; }
+int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const double *d_q, int R, void *stream)
+{
+    k_broadcast_rb<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(st, d_words, d_q, R);
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_sync(void *stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+const char *friqd_error_string(int err)
+{
+    if (err == FRIQ_ERR_SHAPE) return "unsupported problem shape (S, p, A): supported are (2,3,3), (4,5,3), (4,5,21)";
+    return cudaGetErrorString((cudaError_t)err);
+}
+
+int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long long seed0, long first_agent,
+                      double alpha, double gamma, double epsilon, void *stream)
+{
+    k_init_agents<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(dprob, st, seed0, first_agent, alpha, gamma, epsilon);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) k_run_steps<4, 5, 21, 7, FRIQ_ENV_CARTPOLE><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_vag_concl(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_conc, int *d_hit,
+                    double *d_weights, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (hp->S == 2 && hp->p == 3) k_vag_concl<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
+    else if (hp->S == 4 && hp->p == 5) k_vag_concl<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_best_action(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_states, double *d_actconc,
+                      int *d_best, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (FRIQ_SHAPE_MC(hp)) k_best_action<2, 3, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (FRIQ_SHAPE_AC(hp)) k_best_action<4, 5, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (FRIQ_SHAPE_CP(hp)) k_best_action<4, 5, 21, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_update_sarsa(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_qant, const double *d_reward,
+                       const double *d_curqant, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (hp->S == 2 && hp->p == 3) k_update_sarsa<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
+    else if (hp->S == 4 && hp->p == 5) k_update_sarsa<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream)
+{
+    k_trig<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_sin, d_cos, n);
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_pow_x87(const double *d_x, double *d_out, long n, int p, int force_exact, void *stream)
+{
+    k_pow<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n, p, force_exact);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// measured FP64 DADD/DMUL issue rate of this GPU, in G lane-instructions per second
+int friqd_fp64_peak(double *out_ginstr_per_s, int iters)
+{
+    double *d; CK(cudaMalloc(&d, 8));
+    int dev, sms; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    k_fp64_peak<<<blocks, threads>>>(d, iters / 8);
+    CK(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(d, iters);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    *out_ginstr_per_s = (double)blocks * threads * iters * 16.0 / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,574 @@
+/* csrc/friq_host.c -- ANSI-C host layer of the B200-native FRIQ-learning engine.
+ *
+ * Implements include/friq_b200.h on top of the thin CUDA C-ABI (friqd_*, friq_engine.cu):
+ *   - init-time tables, bit-identical to the reference's (plain sequential FP64; compile with
+ *     -ffp-contract=off): universes, scaling functions, vague environments, corner rule base,
+ *     action VE values (frirl_init.c, frirl_init_ve.c, frirl_init_rb.c, FIVEGScFunc.c,
+ *     FIVEGVagEnv.c, FIVEInit.c, frirl_app_helpers.c:32-44);
+ *   - the per-dimension value dictionaries the device rule bases index into;
+ *   - batch bookkeeping, host <-> device marshalling, rule-base file formats.
+ * No FIVE evaluation or SARSA arithmetic happens here: that is device-only.
+ */
+#include "../../include/friq_b200.h"
+#include "friq_devprob.h"
+
+#include <fcntl.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+static __thread char g_err[512] = "";
+const char *friq_last_error(void) { return g_err; }
+#define FAIL(code, ...) do { snprintf(g_err, sizeof g_err, __VA_ARGS__); return (code); } while (0)
+#define DEV(call) do { int e_ = (call); if (e_) FAIL(e_, "%s failed: %s", #call, friqd_error_string(e_)); } while (0)
+
+struct friq_problem {
+    friq_devprob hp;          /* host copy (hp.u / hp.ve hold DEVICE pointers once uploaded) */
+    friq_devprob *dp;         /* device copy */
+    double *u, *ve;           /* host tables [K][U] */
+    double *d_u, *d_ve;
+    int device;               /* device the tables live on, -1 = not uploaded yet */
+    double alpha, gamma, epsilon;
+};
+
+struct friq_batch {
+    friq_problem *P;
+    friq_devstate st;
+    int device;
+    uint64_t seed0; long first_agent;
+    void *slab;               /* per-agent scalar arrays */
+    double *d_in0, *d_in1, *d_in2, *d_out0; int *d_iout; size_t cap_in, cap_out, cap_w; double *d_w;
+};
+
+/* ------------------------------------------------------------------ built-in problem blocks */
+static const double MC_X[10] = {-1.5, -1.295, -1.09, -0.885, -0.68, -0.475, -0.27, -0.065, 0.14, 0.345};
+static const double MC_V[6] = {-0.07, -0.042, -0.014, 0.014, 0.042, 0.07};
+static const double AC_T[5] = {-1.570796326794897, -0.785398163397448, 0, 0.785398163397448, 1.570796326794897};
+static const double CP_T[9] = {-0.2094, -0.1571, -0.1047, -0.0524, 0.0, 0.0524, 0.1047, 0.1571, 0.2094};
+static const double CP_A[21] = {-1.0, -0.9, -0.8, -0.7, -0.6, -0.5, -0.3999999999999999, -0.29999999999999992,
+                                -0.19999999999999995, -0.09999999999999998, 0.0, +0.09999999999999998, +0.19999999999999995,
+                                +0.29999999999999992, +0.3999999999999999, +0.5, +0.6, +0.7, +0.8, +0.9, +1.0};
+static const friq_dim_desc MC_DIMS[2] = {   /* mountaincar.c:244-266 */
+    {10, MC_X, 0.205, 1.0, -0.5, 41, NULL, 0.1}, {6, MC_V, 0.028, 1.0, 0.0, 41, NULL, 0.005}};
+static const friq_dim_desc AC_DIMS[4] = {   /* acrobot.c:261-310 */
+    {5, AC_T, 0.785398163397448, 1.0, 0.0, 41, NULL, 0.1}, {5, AC_T, 0.785398163397448, 1.0, 0.0, 41, NULL, 0.1},
+    {3, NULL, 0.785398163397448, 1.0, 0.0, 41, NULL, 0.05}, {3, NULL, 0.785398163397448, 1.0, 0.0, 41, NULL, 0.05}};
+static const friq_dim_desc CP_DIMS[4] = {   /* cartpole.c:272-384 */
+    {2, NULL, 2.0, 1.0, 1.0, 1001, NULL, 0.016}, {3, NULL, 1.0, 1.0, 0.0, 1001, NULL, 0.032},
+    {9, CP_T, 0.0524, 21.485917317405871, 0.0, 1001, NULL, 0.0031415926535897933}, {2, NULL, 2.0, 1.0, 0.0, 1001, NULL, 0.016}};
+
+int friq_problem_desc_builtin(int env, friq_problem_desc *d)
+{
+    memset(d, 0, sizeof *d);
+    d->env = env;
+    d->gamma = 1.0; d->qdiff_pos_boundary = 1.0; d->rule_weight_considered_significant_for_update = 0.05;   /* frirl_types_def.h:22-77 */
+    d->skip_rules = 1; d->no_random = 1; d->max_episodes = 1000; d->max_steps = 1000;
+    switch (env) {
+    case FRIQ_ENV_MOUNTAINCAR:             /* mountaincar.c:220-279 */
+        d->statedims_len = 2; d->statedims = MC_DIMS;
+        d->actiondim = (friq_dim_desc){3, NULL, 1.0, 0.0, 0.0, 41, NULL, 0.1};
+        d->alpha = 0.5; d->epsilon = 0.01; d->qdiff_neg_boundary = -4.0; d->qdiff_final_tolerance = 500.0; d->reward_good_above = -5000.0;
+        return 0;
+    case FRIQ_ENV_ACROBOT:                 /* acrobot.c:242-324 */
+        d->statedims_len = 4; d->statedims = AC_DIMS;
+        d->actiondim = (friq_dim_desc){3, NULL, 1.0, 0.0, 0.0, 41, NULL, 0.1};
+        d->alpha = 0.5; d->epsilon = 0.001; d->qdiff_neg_boundary = -200.0; d->qdiff_final_tolerance = 50.0; d->reward_good_above = 0.0;
+        return 0;
+    case FRIQ_ENV_CARTPOLE:                /* cartpole.c:252-402 */
+        d->statedims_len = 4; d->statedims = CP_DIMS;
+        d->actiondim = (friq_dim_desc){21, CP_A, 0.1, 0.0, 0.0, 1001, NULL, 0.008};
+        d->alpha = 0.3; d->epsilon = 0.001; d->qdiff_neg_boundary = -200.0; d->qdiff_final_tolerance = 250.0; d->reward_good_above = 0.0;
+        return 0;
+    }
+    FAIL(1, "friq_problem_desc_builtin: unknown environment %d", env);
+}
+
+/* ------------------------------------------------------------------------ table generation */
+/* symmetric fixed-resolution array, frirl_gen_fixres_arr (frirl_app_helpers.c:32-44) */
+static void fixres_fill(double *dst, int n, double step)
+{
+    const double first = -((n - 1) * step) / 2;
+    int i = 0;
+    while (i < n / 2 + 1) { dst[i] = first + step * i; i++; }
+    while (i < n) { dst[i] = dst[n - 1 - i] * -1; i++; }
+}
+
+/* nearest universe index, get_vag_abs_min_i_fixres (min.inl:71-92) */
+static int nearest_index(const double *u, int U, int len, double div, double x)
+{
+    int low = (int)((x - u[0]) / div);
+    if (low < 0) return 0;
+    if (low >= len) return len - 1;
+    if (low + 1 >= U) return low;
+    return (fabs(u[low] - x) <= fabs(u[low + 1] - x)) ? low : low + 1;
+}
+
+/* One row of the vague environment.  pts[] are (position, S_left, S_right) scaling points;
+ * the scaling function between two points is constant when S_right(p) == S_left(p+1), else linear
+ * (FIVEGScFunc.c:100-146 with nls = NAN); VE is its trapezoid primitive integral (FIVEGVagEnv.c:81-94). */
+static void vague_env_row(const double *u, int U, const double *pts, int npts, double *ve)
+{
+    double *sc = (double *)malloc(sizeof(double) * U);
+    const double *last = pts + 3 * (npts - 1);
+    for (int j = 0; j < U; j++) {
+        const double x = u[j];
+        double v = 0.0;
+        if (x < pts[0]) v = pts[1];
+        for (const double *p = pts; p != last; p += 3)
+            if (x >= p[0] && x < p[3]) v = (p[2] == p[4]) ? p[2] : ((p[4] - p[2]) / (p[3] - p[0])) * (x - p[0]) + p[2];
+        if (x >= last[0]) v = (j == U - 1 && x == last[0]) ? last[1] : last[2];
+        sc[j] = v;
+    }
+    ve[0] = 0;
+    for (int j = 1; j < U; j++) ve[j] = ve[j - 1] + (u[j] - u[j - 1]) * (sc[j - 1] + sc[j]) * 0.5;
+    free(sc);
+}
+
+static int dict_find_or_add(friq_problem *P, int k, double v)
+{
+    friq_devprob *hp = &P->hp;
+    for (int j = 0; j < hp->dict_len[k]; j++)
+        if (memcmp(&hp->dict_val[k][j], &v, sizeof v) == 0) return j;
+    if (hp->dict_len[k] >= FRIQ_MAXDICT) return -1;
+    const int j = hp->dict_len[k]++;
+    hp->dict_val[k][j] = v;
+    hp->dict_ve[k][j] = P->ve[(size_t)k * hp->U + nearest_index(P->u + (size_t)k * hp->U, hp->U, hp->U, hp->udiv[k], v)];   /* five_add_rule.c:71-84 */
+    return j;
+}
+
+int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
+{
+    const int S = d->statedims_len, K = S + 1, A = d->actiondim.values_len, U = d->actiondim.universe_len;
+    if (S < 1 || K * FRIQ_IDX_BITS > 32) FAIL(2, "friq_problem_create: %d state dimensions unsupported (packed rule word holds %d)", S, 32 / FRIQ_IDX_BITS - 1);
+    if (A < 2 || A > FRIQ_MAXA) FAIL(2, "friq_problem_create: %d actions unsupported (max %d)", A, FRIQ_MAXA);
+    for (int k = 0; k < S; k++) {
+        if (d->statedims[k].universe_len != U) FAIL(2, "friq_problem_create: all universes must have the same length (frirl_init.c:37)");
+        if (d->statedims[k].values_len < 2 || d->statedims[k].values_len > FRIQ_MAXDICT) FAIL(2, "friq_problem_create: state dim %d has %d values (2..%d supported)", k, d->statedims[k].values_len, FRIQ_MAXDICT);
+    }
+    friq_problem *P = (friq_problem *)calloc(1, sizeof *P);
+    friq_devprob *hp = &P->hp;
+    P->device = -1;
+    P->u = (double *)malloc(sizeof(double) * K * U); P->ve = (double *)malloc(sizeof(double) * K * U);
+    hp->S = S; hp->K = K; hp->A = A; hp->U = U; hp->p = K;                       /* FIVEInit.c:89-93 called with p = 0 */
+    hp->env = d->env; hp->skip_rules = d->skip_rules; hp->no_random = d->no_random;
+    hp->max_steps = d->max_steps; hp->max_episodes = d->max_episodes;
+    hp->qdiff_pos = d->qdiff_pos_boundary; hp->qdiff_neg = d->qdiff_neg_boundary;
+    hp->wsig = d->rule_weight_considered_significant_for_update;
+    hp->qdiff_final_tol = d->qdiff_final_tolerance; hp->reward_good_above = d->reward_good_above;
+    P->alpha = d->alpha; P->gamma = d->gamma; P->epsilon = d->epsilon;
+
+    double pts[3 * FRIQ_MAXDICT];
+    for (int k = 0; k < K; k++) {
+        const friq_dim_desc *dim = (k < S) ? &d->statedims[k] : &d->actiondim;
+        double *u = P->u + (size_t)k * U, *ve = P->ve + (size_t)k * U;
+        if (dim->universe) memcpy(u, dim->universe, sizeof(double) * U); else fixres_fill(u, U, dim->universe_div);
+        if (u[U - 1] - u[0] == 0.0) { friq_problem_destroy(P); FAIL(2, "friq_problem_create: universe %d has zero extent (frirl_init.c:160-168)", k); }
+        hp->grid_len[k] = hp->dict_len[k] = dim->values_len;
+        if (dim->values) memcpy(hp->dict_val[k], dim->values, sizeof(double) * dim->values_len);
+        else fixres_fill(hp->dict_val[k], dim->values_len, dim->values_div);
+        hp->u0[k] = u[0];
+        hp->udiv[k] = (u[U - 1] - u[0]) / (unsigned)(U - 1);                      /* FIVEInit.c:244-248 */
+        if (k < S) {                                                              /* frirl_init_ve.c:36-57 */
+            for (int i = 0; i < dim->values_len; i++) { pts[3 * i] = hp->dict_val[k][i]; pts[3 * i + 1] = pts[3 * i + 2] = dim->values_steep; }
+        } else {                                                                  /* frirl_init_ve.c:82-92: integer steepness (A-1)/2 */
+            const double ratio = 1.0 / (A - 1) * 2.0;
+            for (int i = 0; i < A; i++) { pts[3 * i] = i * ratio - 1.0; pts[3 * i + 1] = pts[3 * i + 2] = (A - 1) / 2; }
+        }
+        vague_env_row(u, U, pts, dim->values_len, ve);
+        for (int j = 0; j < dim->values_len; j++)
+            hp->dict_ve[k][j] = ve[nearest_index(u, U, U, hp->udiv[k], hp->dict_val[k][j])];
+        hp->values_def[k] = dim->values_def;
+        hp->ve_def[k] = ve[nearest_index(u, U, U, hp->udiv[k], dim->values_def)];
+        hp->q_abs0[k] = fabs(hp->dict_val[k][0]); hp->q_div[k] = dim->values_div;
+        /* frirl_check_possible_states.c:68 would refine the grid when epsilon <= step/2; the device keeps grids fixed */
+        for (int j = 1; j < dim->values_len; j++)
+            if (dim->values_div <= fabs(hp->dict_val[k][j] - hp->dict_val[k][j - 1]) / 2) {
+                friq_problem_destroy(P);
+                FAIL(2, "friq_problem_create: dim %d: values_div <= half the grid step would trigger grid refinement (unsupported)", k);
+            }
+    }
+    hp->qp_reuse = 1;
+    for (int a = 0; a < A; a++) {
+        const double *ua = P->u + (size_t)S * U, *vea = P->ve + (size_t)S * U;
+        hp->act_val[a] = hp->dict_val[S][a]; hp->act_dict[a] = a;
+        hp->act_ve[a] = vea[nearest_index(ua, U, U - 1, hp->udiv[S], hp->act_val[a])];          /* frirl_init.c:156-158 */
+        hp->act_ve_eval[a] = vea[nearest_index(ua, U, U, hp->udiv[S], hp->act_val[a])];
+        if (hp->act_ve[a] != hp->act_ve_eval[a]) hp->qp_reuse = 0;
+    }
+    /* corner rules in binary-counter order (frirl_init_rb.c:99-126) */
+    hp->ncorner = 1 << K;
+    for (int r = 0; r < hp->ncorner; r++) {
+        unsigned w = 0;
+        for (int k = 0; k < K; k++) {
+            int lo = 0, hi = 0;
+            for (int j = 1; j < hp->grid_len[k]; j++) { if (hp->dict_val[k][j] < hp->dict_val[k][lo]) lo = j; if (hp->dict_val[k][j] > hp->dict_val[k][hi]) hi = j; }
+            w |= (unsigned)(((r / (hp->ncorner >> (k + 1))) % 2 == 0) ? lo : hi) << (FRIQ_IDX_BITS * k);
+        }
+        hp->corner[r] = w;
+    }
+    *out = P;
+    return 0;
+}
+
+static int problem_upload(friq_problem *P, int device)
+{
+    friq_devprob *hp = &P->hp;
+    const size_t tb = sizeof(double) * hp->K * hp->U;
+    if (P->device != -1 && P->device != device) FAIL(3, "friq: a problem is bound to the first device it is used on (%d)", P->device);
+    DEV(friqd_set_device(device));
+    if (P->device == -1) {
+        DEV(friqd_malloc((void **)&P->d_u, tb)); DEV(friqd_malloc((void **)&P->d_ve, tb)); DEV(friqd_malloc((void **)&P->dp, sizeof(friq_devprob)));
+        DEV(friqd_h2d(P->d_u, P->u, tb)); DEV(friqd_h2d(P->d_ve, P->ve, tb));
+        hp->u = P->d_u; hp->ve = P->d_ve;
+        P->device = device;
+    }
+    DEV(friqd_h2d(P->dp, hp, sizeof(friq_devprob)));
+    return 0;
+}
+
+void friq_problem_destroy(friq_problem *P)
+{
+    if (!P) return;
+    if (P->device != -1) { friqd_set_device(P->device); friqd_free(P->d_u); friqd_free(P->d_ve); friqd_free(P->dp); }
+    free(P->u); free(P->ve); free(P);
+}
+
+int friq_problem_dims(const friq_problem *P, int *dims)
+{
+    dims[0] = P->hp.S; dims[1] = P->hp.K; dims[2] = P->hp.A; dims[3] = P->hp.U; dims[4] = P->hp.p; dims[5] = P->hp.ncorner;
+    return 0;
+}
+int friq_problem_tables(const friq_problem *P, double *u, double *ve, double *udiv, double *act_val, double *act_ve)
+{
+    const size_t n = (size_t)P->hp.K * P->hp.U;
+    if (u) memcpy(u, P->u, sizeof(double) * n);
+    if (ve) memcpy(ve, P->ve, sizeof(double) * n);
+    if (udiv) memcpy(udiv, P->hp.udiv, sizeof(double) * P->hp.K);
+    if (act_val) memcpy(act_val, P->hp.act_val, sizeof(double) * P->hp.A);
+    if (act_ve) memcpy(act_ve, P->hp.act_ve, sizeof(double) * P->hp.A);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------- batches */
+int friq_device_count(int *count) { DEV(friqd_device_count(count)); return 0; }
+
+int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t seed0, long first_agent, friq_batch **out)
+{
+    if (n < 1) FAIL(4, "friq_batch_create: n_agents must be >= 1");
+    if (cap < P->hp.ncorner) FAIL(4, "friq_batch_create: rule_capacity %d < %d initial corner rules", cap, P->hp.ncorner);
+    int rc = problem_upload(P, device); if (rc) return rc;
+    friq_batch *b = (friq_batch *)calloc(1, sizeof *b);
+    b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
+    friq_devstate *st = &b->st;
+    st->n = n; st->n_pad = (n + FRIQ_TILE - 1) / FRIQ_TILE * FRIQ_TILE; st->cap = cap;
+    const size_t slots = (size_t)st->n_pad * cap, np = (size_t)st->n_pad;
+    DEV(friqd_malloc((void **)&st->rbw, slots * 4)); DEV(friqd_malloc((void **)&st->rbq, slots * 8)); DEV(friqd_malloc((void **)&st->sw, slots * 8));
+    DEV(friqd_memset(st->rbw, 0, slots * 4)); DEV(friqd_memset(st->rbq, 0, slots * 8)); DEV(friqd_memset(st->sw, 0, slots * 8));
+    /* one slab for the per-agent scalars: 3*MAXK + 10 f64/u64 rows, 9 i32/u32 rows */
+    const size_t rows8 = 3 * FRIQ_MAXK + 9, rows4 = 10;
+    DEV(friqd_malloc(&b->slab, np * (rows8 * 8 + rows4 * 4)));
+    DEV(friqd_memset(b->slab, 0, np * (rows8 * 8 + rows4 * 4)));
+    double *p8 = (double *)b->slab;
+    st->s = p8; p8 += FRIQ_MAXK * np; st->qs = p8; p8 += FRIQ_MAXK * np; st->vo = p8; p8 += FRIQ_MAXK * np;
+    st->ep_return = p8; p8 += np; st->last_return = p8; p8 += np; st->prev_reward = p8; p8 += np;
+    st->alpha = p8; p8 += np; st->gamma = p8; p8 += np; st->epsilon = p8; p8 += np;
+    st->total_steps = (unsigned long long *)p8; p8 += np; st->sum_rules = (unsigned long long *)p8; p8 += np; st->seed = (unsigned long long *)p8; p8 += np;
+    int *p4 = (int *)p8;
+    st->aidx = p4; p4 += np; st->flags = p4; p4 += np; st->R = p4; p4 += np; st->step_in_ep = p4; p4 += np;
+    st->last_steps = p4; p4 += np; st->last_rules = p4; p4 += np; st->prev_steps = p4; p4 += np; st->prev_numru = p4; p4 += np;
+    st->ep_num = (unsigned int *)p4; p4 += np;
+    *out = b;
+    return friq_batch_reset(b);
+}
+
+int friq_batch_reset(friq_batch *b)
+{
+    DEV(friqd_set_device(b->device));
+    DEV(friqd_init_agents(b->P->dp, b->st, b->seed0, b->first_agent, b->P->alpha, b->P->gamma, b->P->epsilon, NULL));
+    DEV(friqd_sync(NULL));
+    return 0;
+}
+
+void friq_batch_destroy(friq_batch *b)
+{
+    if (!b) return;
+    friqd_set_device(b->device);
+    friqd_free(b->st.rbw); friqd_free(b->st.rbq); friqd_free(b->st.sw); if (b->st.prevq) friqd_free(b->st.prevq);
+    friqd_free(b->slab);
+    void *tmp[6] = { b->d_in0, b->d_in1, b->d_in2, b->d_out0, b->d_iout, b->d_w };
+    for (int i = 0; i < 6; i++) if (tmp[i]) friqd_free(tmp[i]);
+    free(b);
+}
+
+int friq_batch_set_hyper(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon)
+{
+    DEV(friqd_set_device(b->device));
+    const size_t nb = sizeof(double) * b->st.n;
+    if (alpha) DEV(friqd_h2d(b->st.alpha, alpha, nb));
+    if (gamma) DEV(friqd_h2d(b->st.gamma, gamma, nb));
+    if (epsilon) DEV(friqd_h2d(b->st.epsilon, epsilon, nb));
+    return 0;
+}
+
+int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant, const double *rconc)
+{
+    friq_problem *P = b->P; const int K = P->hp.K;
+    if (R < 0 || R > b->st.cap) FAIL(5, "friq_batch_set_rulebase: %d rules exceed the capacity %d", R, b->st.cap);
+    if (agent >= b->st.n) FAIL(5, "friq_batch_set_rulebase: agent %ld out of range", agent);
+    DEV(friqd_set_device(b->device));
+    unsigned int *w = (unsigned int *)malloc(sizeof(unsigned int) * (R + 1));
+    int grew = 0;
+    for (int i = 0; i < R; i++) {
+        unsigned int word = 0;
+        for (int k = 0; k < K; k++) {
+            const int before = P->hp.dict_len[k];
+            const int j = dict_find_or_add(P, k, rant[(size_t)i * K + k]);
+            if (j < 0) { free(w); FAIL(5, "friq_batch_set_rulebase: more than %d distinct antecedent values in dimension %d", FRIQ_MAXDICT, k); }
+            grew |= (P->hp.dict_len[k] != before);
+            word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
+        }
+        w[i] = word;
+    }
+    if (grew) DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob)));
+    if (agent >= 0) {
+        const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE);
+        if (R) {
+            DEV(friqd_h2d_2d(b->st.rbw + off, FRIQ_TILE * 4, w, 4, 4, R));
+            DEV(friqd_h2d_2d(b->st.rbq + off, FRIQ_TILE * 8, rconc, 8, 8, R));
+        }
+        DEV(friqd_h2d(b->st.R + agent, &R, sizeof(int)));
+    } else {
+        unsigned int *dw; double *dq;
+        DEV(friqd_malloc((void **)&dw, 4 * (R + 1))); DEV(friqd_malloc((void **)&dq, 8 * (R + 1)));
+        if (R) { DEV(friqd_h2d(dw, w, 4 * R)); DEV(friqd_h2d(dq, rconc, 8 * R)); }
+        DEV(friqd_broadcast_rb(b->st, dw, dq, R, NULL)); DEV(friqd_sync(NULL));
+        friqd_free(dw); friqd_free(dq);
+    }
+    free(w);
+    return 0;
+}
+
+int friq_batch_get_rulebase(friq_batch *b, long agent, int *R_out, double *rant, double *rconc)
+{
+    const friq_devprob *hp = &b->P->hp; const int K = hp->K;
+    if (agent < 0 || agent >= b->st.n) FAIL(5, "friq_batch_get_rulebase: agent %ld out of range", agent);
+    DEV(friqd_set_device(b->device));
+    int R; DEV(friqd_d2h(&R, b->st.R + agent, sizeof(int)));
+    *R_out = R;
+    if (!R || (!rant && !rconc)) return 0;
+    const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE);
+    if (rconc) DEV(friqd_d2h_2d(rconc, 8, b->st.rbq + off, FRIQ_TILE * 8, 8, R));
+    if (rant) {
+        unsigned int *w = (unsigned int *)malloc(sizeof(unsigned int) * R);
+        int rc = friqd_d2h_2d(w, 4, b->st.rbw + off, FRIQ_TILE * 4, 4, R);
+        if (rc) { free(w); FAIL(rc, "friq_batch_get_rulebase: %s", friqd_error_string(rc)); }
+        for (int i = 0; i < R; i++)
+            for (int k = 0; k < K; k++) rant[(size_t)i * K + k] = hp->dict_val[k][(w[i] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+        free(w);
+    }
+    return 0;
+}
+
+int friq_batch_set_inserted(friq_batch *b, const int *inserted)
+{
+    DEV(friqd_set_device(b->device));
+    int *f = (int *)malloc(sizeof(int) * b->st.n);
+    int rc = friqd_d2h(f, b->st.flags, sizeof(int) * b->st.n);
+    if (!rc) { for (long i = 0; i < b->st.n; i++) f[i] = (f[i] & ~FRIQ_F_INSERTED) | (inserted[i] ? FRIQ_F_INSERTED : 0); rc = friqd_h2d(b->st.flags, f, sizeof(int) * b->st.n); }
+    free(f);
+    if (rc) FAIL(rc, "friq_batch_set_inserted: %s", friqd_error_string(rc));
+    return 0;
+}
+int friq_batch_get_inserted(friq_batch *b, int *inserted)
+{
+    DEV(friqd_set_device(b->device));
+    DEV(friqd_d2h(inserted, b->st.flags, sizeof(int) * b->st.n));
+    for (long i = 0; i < b->st.n; i++) inserted[i] = (inserted[i] & FRIQ_F_INSERTED) ? 1 : 0;
+    return 0;
+}
+
+int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
+{
+    DEV(friqd_set_device(b->device));
+    if (b->P->hp.env == FRIQ_ENV_HOST_CALLBACKS) FAIL(6, "friq_batch_run: the problem has no built-in environment (host callbacks): use the per-call entry points");
+    if ((mode & FRIQ_RUN_TRACK_CONVERGENCE) && !b->st.prevq) {
+        const size_t slots = (size_t)b->st.n_pad * b->st.cap;
+        DEV(friqd_malloc((void **)&b->st.prevq, slots * 8)); DEV(friqd_memset(b->st.prevq, 0, slots * 8));
+    }
+    DEV(friqd_run_steps(&b->P->hp, b->P->dp, b->st, n_steps, mode, stream));
+    return 0;
+}
+int friq_batch_sync(friq_batch *b, void *stream) { DEV(friqd_set_device(b->device)); DEV(friqd_sync(stream)); return 0; }
+
+int friq_batch_gather(friq_batch *b, double *last_return, int *last_steps, int *rules, int *episodes, int *flags,
+                      long long *total_steps, long long *sum_rules)
+{
+    const long n = b->st.n;
+    DEV(friqd_set_device(b->device));
+    if (last_return) DEV(friqd_d2h(last_return, b->st.last_return, 8 * n));
+    if (last_steps) DEV(friqd_d2h(last_steps, b->st.last_steps, 4 * n));
+    if (rules) DEV(friqd_d2h(rules, b->st.R, 4 * n));
+    if (episodes) { DEV(friqd_d2h(episodes, b->st.ep_num, 4 * n)); for (long i = 0; i < n; i++) episodes[i] -= 1; }
+    if (flags) DEV(friqd_d2h(flags, b->st.flags, 4 * n));
+    if (total_steps) DEV(friqd_d2h(total_steps, b->st.total_steps, 8 * n));
+    if (sum_rules) DEV(friqd_d2h(sum_rules, b->st.sum_rules, 8 * n));
+    return 0;
+}
+
+int friq_batch_gather_device(friq_batch *b, void *d_ret, void *d_steps, void *d_rules, void *stream)
+{
+    const long n = b->st.n;
+    DEV(friqd_set_device(b->device));
+    if (d_ret) DEV(friqd_d2d_async(d_ret, b->st.last_return, 8 * n, stream));
+    if (d_steps) DEV(friqd_d2d_async(d_steps, b->st.last_steps, 4 * n, stream));
+    if (d_rules) DEV(friqd_d2d_async(d_rules, b->st.R, 4 * n, stream));
+    return 0;
+}
+
+int friq_batch_run_host(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon, long n_steps, int mode,
+                        double *last_return, int *last_steps, int *rules, void *stream)
+{
+    const long n = b->st.n;
+    DEV(friqd_set_device(b->device));
+    if (alpha) DEV(friqd_h2d_async(b->st.alpha, alpha, 8 * n, stream));
+    if (gamma) DEV(friqd_h2d_async(b->st.gamma, gamma, 8 * n, stream));
+    if (epsilon) DEV(friqd_h2d_async(b->st.epsilon, epsilon, 8 * n, stream));
+    int rc = friq_batch_run(b, n_steps, mode, stream); if (rc) return rc;
+    if (last_return) DEV(friqd_d2h_async(last_return, b->st.last_return, 8 * n, stream));
+    if (last_steps) DEV(friqd_d2h_async(last_steps, b->st.last_steps, 4 * n, stream));
+    if (rules) DEV(friqd_d2h_async(rules, b->st.R, 4 * n, stream));
+    DEV(friqd_sync(stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------- per-call entry points */
+static int ensure(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*p) friqd_free(*p);
+    *cap = 0;
+    int rc = friqd_malloc(p, need); if (rc) return rc;
+    *cap = need;
+    return 0;
+}
+static int percall_buffers(friq_batch *b)
+{
+    const size_t n = (size_t)b->st.n, need_in = n * FRIQ_MAXK * 8, need_out = n * FRIQ_MAXA * 8;
+    if (b->cap_in < need_in) {
+        size_t c0 = b->cap_in, c1 = b->cap_in, c2 = b->cap_in;
+        DEV(ensure((void **)&b->d_in0, &c0, need_in)); DEV(ensure((void **)&b->d_in1, &c1, need_in)); DEV(ensure((void **)&b->d_in2, &c2, need_in));
+        b->cap_in = need_in;
+    }
+    if (b->cap_out < need_out) {
+        size_t c0 = b->cap_out, c1 = b->cap_out;
+        DEV(ensure((void **)&b->d_out0, &c0, need_out)); DEV(ensure((void **)&b->d_iout, &c1, n * 4 > need_out ? n * 4 : need_out));
+        b->cap_out = need_out;
+    }
+    return 0;
+}
+
+int friq_batch_vag_concl(friq_batch *b, const double *ant, double *conc, int *hit)
+{
+    const long n = b->st.n; const int K = b->P->hp.K;
+    DEV(friqd_set_device(b->device));
+    int rc = percall_buffers(b); if (rc) return rc;
+    DEV(friqd_h2d(b->d_in0, ant, 8ul * n * K));
+    DEV(friqd_vag_concl(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_out0, b->d_iout, NULL, NULL));
+    DEV(friqd_d2h(conc, b->d_out0, 8ul * n)); DEV(friqd_d2h(hit, b->d_iout, 4ul * n));
+    return 0;
+}
+
+int friq_batch_vag_concl_weight(friq_batch *b, const double *ant, int *hit, double *weights)
+{
+    const long n = b->st.n; const int K = b->P->hp.K;
+    DEV(friqd_set_device(b->device));
+    int rc = percall_buffers(b); if (rc) return rc;
+    DEV(ensure((void **)&b->d_w, &b->cap_w, 8ul * n * b->st.cap));
+    DEV(friqd_memset(b->d_w, 0, 8ul * n * b->st.cap));
+    DEV(friqd_h2d(b->d_in0, ant, 8ul * n * K));
+    DEV(friqd_vag_concl(&b->P->hp, b->P->dp, b->st, b->d_in0, NULL, b->d_iout, b->d_w, NULL));
+    DEV(friqd_d2h(hit, b->d_iout, 4ul * n)); DEV(friqd_d2h(weights, b->d_w, 8ul * n * b->st.cap));
+    return 0;
+}
+
+int friq_batch_get_best_action(friq_batch *b, const double *states, double *actconc, int *best)
+{
+    const long n = b->st.n; const int S = b->P->hp.S, A = b->P->hp.A;
+    DEV(friqd_set_device(b->device));
+    int rc = percall_buffers(b); if (rc) return rc;
+    DEV(friqd_h2d(b->d_in0, states, 8ul * n * S));
+    DEV(friqd_best_action(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_out0, b->d_iout, NULL));
+    DEV(friqd_d2h(actconc, b->d_out0, 8ul * n * A)); DEV(friqd_d2h(best, b->d_iout, 4ul * n));
+    return 0;
+}
+
+int friq_batch_update_sarsa(friq_batch *b, const double *q_ant, const double *reward, const double *cur_q_ant)
+{
+    const long n = b->st.n; const int K = b->P->hp.K;
+    DEV(friqd_set_device(b->device));
+    int rc = percall_buffers(b); if (rc) return rc;
+    DEV(friqd_h2d(b->d_in0, q_ant, 8ul * n * K)); DEV(friqd_h2d(b->d_in1, reward, 8ul * n)); DEV(friqd_h2d(b->d_in2, cur_q_ant, 8ul * n * K));
+    DEV(friqd_update_sarsa(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_in1, b->d_in2, NULL));
+    DEV(friqd_sync(NULL));
+    return 0;
+}
+
+/* ----------------------------------------------------------------------- rule-base files */
+/* frirl_save_rb_to_text_file (frirl_utils.c:100-146): "%.18f " per antecedent, "%.18f \n" for Q */
+int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double *rant, const double *rconc)
+{
+    FILE *f = fopen(file_name, "w");
+    if (!f) { perror("friq_save_rb_to_text_file: open()"); FAIL(-1, "cannot open %s", file_name); }
+    for (int i = 0; i < R; i++) {
+        for (int k = 0; k < K; k++) fprintf(f, "%.18f ", rant[(size_t)i * K + k]);
+        fprintf(f, "%.18f \n", rconc[i]);
+    }
+    fclose(f);
+    return 0;
+}
+/* frirl_save_rb_to_bin_file (frirl_utils.c:151-203): int32 R, then per rule K doubles + Q, host endian */
+int friq_save_rb_to_bin_file(const char *file_name, int K, int R, const double *rant, const double *rconc)
+{
+    FILE *f = fopen(file_name, "wb");
+    if (!f) { perror("friq_save_rb_to_bin_file: open()"); FAIL(-1, "cannot open %s", file_name); }
+    int32_t n = R;
+    fwrite(&n, sizeof n, 1, f);
+    for (int i = 0; i < R; i++) { fwrite(rant + (size_t)i * K, sizeof(double), K, f); fwrite(rconc + i, sizeof(double), 1, f); }
+    fclose(f);
+    return 0;
+}
+/* frirl_load_rb_from_bin_file (frirl_utils.c:228-281) */
+int friq_load_rb_from_bin_file(const char *file_name, int K, int max_rules, int *R, double *rant, double *rconc)
+{
+    FILE *f = fopen(file_name, "rb");
+    if (!f) { perror("friq_load_rb_from_bin_file: open()"); FAIL(-1, "cannot open %s", file_name); }
+    int32_t n = 0;
+    if (fread(&n, sizeof n, 1, f) != 1 || n < 0 || n > max_rules) { fclose(f); FAIL(-1, "%s: bad rule count %d (max %d)", file_name, n, max_rules); }
+    for (int i = 0; i < n; i++)
+        if (fread(rant + (size_t)i * K, sizeof(double), K, f) != (size_t)K || fread(rconc + i, sizeof(double), 1, f) != 1) { fclose(f); FAIL(-1, "%s: truncated", file_name); }
+    fclose(f);
+    *R = n;
+    return 0;
+}
+
+/* --------------------------------------------------------------------- device self-tests */
+int friq_device_trig(const double *x, double *s, double *c, long n)
+{
+    double *dx, *ds, *dc;
+    DEV(friqd_malloc((void **)&dx, 8ul * n)); DEV(friqd_malloc((void **)&ds, 8ul * n)); DEV(friqd_malloc((void **)&dc, 8ul * n));
+    DEV(friqd_h2d(dx, x, 8ul * n)); DEV(friqd_trig(dx, ds, dc, n, NULL));
+    DEV(friqd_d2h(s, ds, 8ul * n)); DEV(friqd_d2h(c, dc, 8ul * n));
+    friqd_free(dx); friqd_free(ds); friqd_free(dc);
+    return 0;
+}
+int friq_device_pow_x87(const double *x, double *out, long n, int p, int force_exact)
+{
+    double *dx, *dout;
+    DEV(friqd_malloc((void **)&dx, 8ul * n)); DEV(friqd_malloc((void **)&dout, 8ul * n));
+    DEV(friqd_h2d(dx, x, 8ul * n)); DEV(friqd_pow_x87(dx, dout, n, p, force_exact, NULL)); DEV(friqd_d2h(out, dout, 8ul * n));
+    friqd_free(dx); friqd_free(dout);
+    return 0;
+}
+int friq_device_fp64_peak(double *g) { DEV(friqd_fp64_peak(g, 1 << 16)); return 0; }

@@ -1,0 +1,264 @@
+"""ctypes binding of libfriq_b200.so (the C-ABI declared in include/friq_b200.h).
+
+Thin by design: numpy arrays in, numpy arrays out, every call goes straight to the C-ABI,
+which launches the sm_100a kernels.  There is no Python or CPU implementation of the path
+here; if the shared library is missing, importing the engine fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfriq_b200.so")
+
+ENV_MOUNTAINCAR, ENV_ACROBOT, ENV_CARTPOLE = 0, 1, 2
+ENV_ID = {"mountaincar": 0, "acrobot": 1, "cartpole": 2}
+RUN_LEARN, RUN_TRACK, RUN_STOP_ON_CONVERGE, RUN_STOP_AT_EPISODE_END = 1, 2, 4, 8
+F_NEED_RESET, F_INSERTED, F_CONVERGED, F_OVERFLOW = 1, 2, 4, 8
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+llp = C.POINTER(C.c_longlong)
+
+
+class DimDesc(C.Structure):          # friq_dim_desc == struct frirl_dimension_desc (frirl_types.h:34-44)
+    _fields_ = [("values_len", C.c_int), ("values", dp), ("values_div", C.c_double), ("values_steep", C.c_double),
+                ("values_def", C.c_double), ("universe_len", C.c_int), ("universe", dp), ("universe_div", C.c_double)]
+
+
+class ProblemDesc(C.Structure):      # friq_problem_desc
+    _fields_ = [("env", C.c_int), ("statedims_len", C.c_int), ("statedims", C.POINTER(DimDesc)), ("actiondim", DimDesc),
+                ("alpha", C.c_double), ("gamma", C.c_double), ("epsilon", C.c_double),
+                ("qdiff_pos_boundary", C.c_double), ("qdiff_neg_boundary", C.c_double), ("qdiff_final_tolerance", C.c_double),
+                ("reward_good_above", C.c_double), ("rule_weight_considered_significant_for_update", C.c_double),
+                ("skip_rules", C.c_int), ("no_random", C.c_int), ("max_episodes", C.c_int), ("max_steps", C.c_int)]
+
+
+SYMBOLS = {
+    "friq_last_error": (C.c_char_p, []),
+    "friq_device_count": (C.c_int, [ip]),
+    "friq_problem_desc_builtin": (C.c_int, [C.c_int, C.POINTER(ProblemDesc)]),
+    "friq_problem_create": (C.c_int, [C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]),
+    "friq_problem_destroy": (None, [C.c_void_p]),
+    "friq_problem_dims": (C.c_int, [C.c_void_p, ip]),
+    "friq_problem_tables": (C.c_int, [C.c_void_p, dp, dp, dp, dp, dp]),
+    "friq_batch_create": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_uint64, C.c_long, C.POINTER(C.c_void_p)]),
+    "friq_batch_destroy": (None, [C.c_void_p]),
+    "friq_batch_reset": (C.c_int, [C.c_void_p]),
+    "friq_batch_set_hyper": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "friq_batch_set_rulebase": (C.c_int, [C.c_void_p, C.c_long, C.c_int, dp, dp]),
+    "friq_batch_get_rulebase": (C.c_int, [C.c_void_p, C.c_long, ip, dp, dp]),
+    "friq_batch_set_inserted": (C.c_int, [C.c_void_p, ip]),
+    "friq_batch_get_inserted": (C.c_int, [C.c_void_p, ip]),
+    "friq_batch_run": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
+    "friq_batch_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "friq_batch_gather": (C.c_int, [C.c_void_p, dp, ip, ip, ip, ip, llp, llp]),
+    "friq_batch_gather_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "friq_batch_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "friq_batch_vag_concl": (C.c_int, [C.c_void_p, dp, dp, ip]),
+    "friq_batch_vag_concl_weight": (C.c_int, [C.c_void_p, dp, ip, dp]),
+    "friq_batch_get_best_action": (C.c_int, [C.c_void_p, dp, dp, ip]),
+    "friq_batch_update_sarsa": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "friq_save_rb_to_text_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
+    "friq_save_rb_to_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
+    "friq_load_rb_from_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, ip, dp, dp]),
+    "friq_device_trig": (C.c_int, [dp, dp, dp, C.c_long]),
+    "friq_device_pow_x87": (C.c_int, [dp, dp, C.c_long, C.c_int, C.c_int]),
+    "friq_device_fp64_peak": (C.c_int, [dp]),
+}
+
+_lib = None
+
+
+def build():
+    """Compile the extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s", "-C", HERE], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C {HERE}` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class FriqError(RuntimeError):
+    pass
+
+
+def _ck(rc):
+    if rc != 0:
+        raise FriqError(f"[{rc}] {lib().friq_last_error().decode()}")
+
+
+def _p(a, t=dp):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    n = C.c_int(0)
+    _ck(lib().friq_device_count(C.byref(n)))
+    return n.value
+
+
+class Problem:
+    """Host tables of one FRIQ problem (frirl_init equivalent)."""
+
+    def __init__(self, env=None, desc=None, **overrides):
+        L = lib()
+        self.desc = ProblemDesc()
+        if desc is not None:
+            self.desc = desc
+        else:
+            _ck(L.friq_problem_desc_builtin(ENV_ID[env] if isinstance(env, str) else env, C.byref(self.desc)))
+        for k, v in overrides.items():
+            setattr(self.desc, k, v)
+        self.h = C.c_void_p()
+        _ck(L.friq_problem_create(C.byref(self.desc), C.byref(self.h)))
+        d = (C.c_int * 6)()
+        L.friq_problem_dims(self.h, d)
+        self.S, self.K, self.A, self.U, self.p, self.ncorner = list(d)
+
+    def tables(self):
+        u = np.zeros((self.K, self.U)); ve = np.zeros((self.K, self.U)); udiv = np.zeros(self.K)
+        av = np.zeros(self.A); ave = np.zeros(self.A)
+        _ck(lib().friq_problem_tables(self.h, _p(u), _p(ve), _p(udiv), _p(av), _p(ave)))
+        return dict(u=u, ve=ve, udiv=udiv, act_val=av, act_ve=ave)
+
+    def close(self):
+        if self.h:
+            lib().friq_problem_destroy(self.h); self.h = None
+
+
+class Batch:
+    """n independent agents with private rule bases, resident on one GPU."""
+
+    def __init__(self, problem, n_agents, capacity, device=0, seed0=0x5EED0000, first_agent=0):
+        self.P, self.n, self.cap = problem, int(n_agents), int(capacity)
+        self.h = C.c_void_p()
+        _ck(lib().friq_batch_create(problem.h, device, self.n, self.cap, seed0, first_agent, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().friq_batch_destroy(self.h); self.h = None
+
+    def reset(self):
+        _ck(lib().friq_batch_reset(self.h))
+
+    def set_hyper(self, alpha=None, gamma=None, epsilon=None):
+        a, g, e = [None if x is None else _f64(np.broadcast_to(x, (self.n,))) for x in (alpha, gamma, epsilon)]
+        _ck(lib().friq_batch_set_hyper(self.h, _p(a), _p(g), _p(e)))
+
+    def set_rulebase(self, rant, rconc, agent=-1):
+        rant, rconc = _f64(rant), _f64(rconc)
+        _ck(lib().friq_batch_set_rulebase(self.h, agent, len(rconc), _p(rant), _p(rconc)))
+
+    def get_rulebase(self, agent=0):
+        R = C.c_int(0)
+        rant = np.zeros((self.cap, self.P.K)); rconc = np.zeros(self.cap)
+        _ck(lib().friq_batch_get_rulebase(self.h, agent, C.byref(R), _p(rant), _p(rconc)))
+        return R.value, rant[:R.value].copy(), rconc[:R.value].copy()
+
+    def set_inserted(self, v):
+        v = np.ascontiguousarray(np.broadcast_to(v, (self.n,)), dtype=np.int32)
+        _ck(lib().friq_batch_set_inserted(self.h, _p(v, ip)))
+
+    def get_inserted(self):
+        v = np.zeros(self.n, dtype=np.int32)
+        _ck(lib().friq_batch_get_inserted(self.h, _p(v, ip)))
+        return v
+
+    def run(self, n_steps, mode=RUN_LEARN, stream=None, sync=True):
+        _ck(lib().friq_batch_run(self.h, int(n_steps), int(mode), stream))
+        if sync:
+            _ck(lib().friq_batch_sync(self.h, stream))
+
+    def sync(self, stream=None):
+        _ck(lib().friq_batch_sync(self.h, stream))
+
+    def gather(self):
+        n = self.n
+        out = dict(last_return=np.zeros(n), last_steps=np.zeros(n, np.int32), rules=np.zeros(n, np.int32),
+                   episodes=np.zeros(n, np.int32), flags=np.zeros(n, np.int32),
+                   total_steps=np.zeros(n, np.int64), sum_rules=np.zeros(n, np.int64))
+        _ck(lib().friq_batch_gather(self.h, _p(out["last_return"]), _p(out["last_steps"], ip), _p(out["rules"], ip),
+                                    _p(out["episodes"], ip), _p(out["flags"], ip), _p(out["total_steps"], llp),
+                                    _p(out["sum_rules"], llp)))
+        return out
+
+    def gather_device(self, ret_ptr, steps_ptr, rules_ptr, stream=None):
+        _ck(lib().friq_batch_gather_device(self.h, ret_ptr, steps_ptr, rules_ptr, stream))
+
+    def run_host(self, n_steps, mode, alpha_ptr, gamma_ptr, eps_ptr, ret_ptr, steps_ptr, rules_ptr, stream=None):
+        """End-to-end call with HOST pointers (e.g. pinned torch tensors): H2D, run, D2H, sync."""
+        _ck(lib().friq_batch_run_host(self.h, alpha_ptr, gamma_ptr, eps_ptr, int(n_steps), int(mode), ret_ptr, steps_ptr, rules_ptr, stream))
+
+    # ---- per-call entry points
+    def vag_concl(self, ant):
+        ant = _f64(ant).reshape(self.n, self.P.K)
+        conc = np.zeros(self.n); hit = np.zeros(self.n, np.int32)
+        _ck(lib().friq_batch_vag_concl(self.h, _p(ant), _p(conc), _p(hit, ip)))
+        return hit, conc
+
+    def vag_concl_weight(self, ant):
+        ant = _f64(ant).reshape(self.n, self.P.K)
+        hit = np.zeros(self.n, np.int32); w = np.zeros((self.n, self.cap))
+        _ck(lib().friq_batch_vag_concl_weight(self.h, _p(ant), _p(hit, ip), _p(w)))
+        return hit, w
+
+    def best_action(self, states):
+        states = _f64(states).reshape(self.n, self.P.S)
+        ac = np.zeros((self.n, self.P.A)); best = np.zeros(self.n, np.int32)
+        _ck(lib().friq_batch_get_best_action(self.h, _p(states), _p(ac), _p(best, ip)))
+        return best, ac
+
+    def update_sarsa(self, q_ant, reward, cur_q_ant):
+        q_ant = _f64(q_ant).reshape(self.n, self.P.K); cur = _f64(cur_q_ant).reshape(self.n, self.P.K)
+        reward = _f64(np.broadcast_to(reward, (self.n,)))
+        _ck(lib().friq_batch_update_sarsa(self.h, _p(q_ant), _p(reward), _p(cur)))
+
+
+def device_trig(x):
+    x = _f64(x); s = np.zeros_like(x); c = np.zeros_like(x)
+    _ck(lib().friq_device_trig(_p(x), _p(s), _p(c), x.size))
+    return s, c
+
+
+def device_pow_x87(x, p, force_exact=False):
+    x = _f64(x); out = np.zeros_like(x)
+    _ck(lib().friq_device_pow_x87(_p(x), _p(out), x.size, p, int(force_exact)))
+    return out
+
+
+def device_fp64_peak():
+    g = C.c_double(0)
+    _ck(lib().friq_device_fp64_peak(C.byref(g)))
+    return g.value
+
+
+def save_rb_text(path, rant, rconc):
+    rant, rconc = _f64(rant), _f64(rconc)
+    _ck(lib().friq_save_rb_to_text_file(path.encode(), rant.shape[1], len(rconc), _p(rant), _p(rconc)))
+
+
+def save_rb_bin(path, rant, rconc):
+    rant, rconc = _f64(rant), _f64(rconc)
+    _ck(lib().friq_save_rb_to_bin_file(path.encode(), rant.shape[1], len(rconc), _p(rant), _p(rconc)))
+
+
+def load_rb_bin(path, K, max_rules=16384):
+    R = C.c_int(0); rant = np.zeros((max_rules, K)); rconc = np.zeros(max_rules)
+    _ck(lib().friq_load_rb_from_bin_file(path.encode(), K, max_rules, C.byref(R), _p(rant), _p(rconc)))
+    return rant[:R.value].copy(), rconc[:R.value].copy()

@@ -1,0 +1,133 @@
+/* include/friq_b200.h -- C-ABI of the B200-native FRIQ-learning engine.
+ *
+ * Plain C: opaque handles, plain pointers and sizes, no CUDA / torch types.  The
+ * library behind it (libfriq_b200.so) is ANSI-C host code on top of hand-written
+ * sm_100a kernels; there is NO CPU fallback: every function that evaluates or
+ * updates a rule base launches a kernel and fails with a non-zero code when no
+ * CUDA device is usable.
+ *
+ * What it replaces in the reference (szaguldo-kamaz/FRI-ReinforcementLearning-C):
+ * the hot path  frirl_sequential_run -> frirl_episode -> { env callbacks,
+ * frirl_e_greedy_selection -> frirl_get_best_action -> FIVEVagConcl_FRIRL_BestAct,
+ * frirl_update_sarsa -> FIVE_vag_concl / FIVE_vag_concl_weight / FIVE_add_rule ->
+ * five_rule_distance }  (SURVEY.md section 3), for a BATCH of independent agents
+ * instead of one.  Every entry point cites the reference interface it stands in for.
+ *
+ * Return value: 0 on success, non-zero on error; friq_last_error() describes it.
+ */
+#ifndef FRIQ_B200_H
+#define FRIQ_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRIQ_ENV_HOST_CALLBACKS (-1)   /* no built-in environment: per-call API only */
+#define FRIQ_ENV_MOUNTAINCAR 0         /* examples/mountaincar/mountaincar.c:37-125 */
+#define FRIQ_ENV_ACROBOT 1             /* examples/acrobot/acrobot.c:31-192         */
+#define FRIQ_ENV_CARTPOLE 2            /* examples/cartpole/cartpole.c:35-168       */
+
+/* run-mode bits of friq_batch_run() */
+#define FRIQ_RUN_LEARN 1               /* reduction_state == 0 (frirl_episode.c:155-160); 0 = frirl_test_run.c:65-69 */
+#define FRIQ_RUN_TRACK_CONVERGENCE 2   /* evaluate the "RB complete" predicate, frirl_sequential_run.c:83-150 */
+#define FRIQ_RUN_STOP_ON_CONVERGE 4    /* converged agents stop stepping */
+#define FRIQ_RUN_STOP_AT_EPISODE_END 8 /* every agent stops after finishing its current episode (frirl_episode granularity) */
+
+/* One dimension of the problem; field for field struct frirl_dimension_desc
+ * (src/frirl/frirl_types.h:34-44).  values / universe may be NULL, in which case
+ * they are generated like FRIRL_GEN_FIXRES_VALUES / _UNIVERSE do
+ * (frirl_app_helpers.h:25-38, frirl_app_helpers.c:32-44). */
+typedef struct friq_dim_desc {
+    int values_len;
+    const double *values;
+    double values_div, values_steep, values_def;
+    int universe_len;
+    const double *universe;
+    double universe_div;
+} friq_dim_desc;
+
+/* The part of struct frirl_desc (frirl_types.h:62-169) the path reads. */
+typedef struct friq_problem_desc {
+    int env;                               /* FRIQ_ENV_* (stands in for the 3 callbacks, frirl_types.h:103-120) */
+    int statedims_len;
+    const friq_dim_desc *statedims;
+    friq_dim_desc actiondim;
+    double alpha, gamma, epsilon;
+    double qdiff_pos_boundary, qdiff_neg_boundary, qdiff_final_tolerance;
+    double reward_good_above, rule_weight_considered_significant_for_update;
+    int skip_rules, no_random, max_episodes, max_steps;
+} friq_problem_desc;
+
+typedef struct friq_problem friq_problem;
+typedef struct friq_batch friq_batch;
+
+const char *friq_last_error(void);
+int friq_device_count(int *count);
+
+/* ---- problem (host tables: frirl_init.c:29-341, frirl_init_ve.c, FIVEGScFunc.c, FIVEGVagEnv.c, FIVEInit.c) */
+/* parameter block of one of the three example drivers (mountaincar.c:220-279, acrobot.c:242-324,
+ * cartpole.c:252-402); storage is static, valid for the life of the process */
+int friq_problem_desc_builtin(int env, friq_problem_desc *out);
+int friq_problem_create(const friq_problem_desc *desc, friq_problem **out);
+void friq_problem_destroy(friq_problem *p);
+/* dims[0..5] = S, K, A, U, p, 2^K */
+int friq_problem_dims(const friq_problem *p, int *dims);
+/* host copies of the tables: u, ve [K][U]; udiv [K]; act_val, act_ve [A] (any pointer may be NULL) */
+int friq_problem_tables(const friq_problem *p, double *u, double *ve, double *udiv, double *act_val, double *act_ve);
+
+/* ---- batch of independent agents, each with a private rule base (replaces one struct frirl_desc +
+ * struct FIVERB per agent).  Agent i uses the Philox key seed0 + first_agent + i. */
+int friq_batch_create(friq_problem *p, int device, long n_agents, int rule_capacity, uint64_t seed0, long first_agent, friq_batch **out);
+void friq_batch_destroy(friq_batch *b);
+/* back to frirl_init state: corner rules (frirl_init_rb.c:99-126), episode 1 */
+int friq_batch_reset(friq_batch *b);
+/* per-agent hyper-parameters (host arrays of n_agents, NULL keeps the current values) */
+int friq_batch_set_hyper(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon);
+/* rule base of agent `agent` (or of ALL agents when agent < 0): rant [R][K], rconc [R]
+ * (frirl_load_rb_from_bin_file -> five_add_rule, frirl_utils.c:253-276) */
+int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant, const double *rconc);
+int friq_batch_get_rulebase(friq_batch *b, long agent, int *R, double *rant, double *rconc);
+int friq_batch_set_inserted(friq_batch *b, const int *inserted);   /* fus_is_rule_inserted, frirl_types.h:153 */
+int friq_batch_get_inserted(friq_batch *b, int *inserted);
+
+/* ---- the fused hot path: every agent advances n_steps env steps (frirl_episode.c:86-186 per step,
+ * episodes roll over as in frirl_sequential_run.c:57-161).  Asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream). */
+int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream);
+int friq_batch_sync(friq_batch *b, void *stream);
+/* results -> host arrays of n_agents (any pointer may be NULL): last finished episode's total reward /
+ * steps / rule count (the per-episode printf of frirl_sequential_run.c:77-80), episodes finished,
+ * converged / overflow flags, env steps executed, and the sum over steps of the rule-base size */
+int friq_batch_gather(friq_batch *b, double *last_return, int *last_steps, int *rules, int *episodes, int *flags,
+                      long long *total_steps, long long *sum_rules);
+/* same results copied device -> device into caller-owned buffers (e.g. torch tensors fed to NCCL) */
+int friq_batch_gather_device(friq_batch *b, void *d_last_return_f64, void *d_last_steps_i32, void *d_rules_i32, void *stream);
+/* end-to-end convenience: hyper-parameters H2D, run, results D2H, all on `stream` and synchronised */
+int friq_batch_run_host(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon, long n_steps, int mode,
+                        double *last_return, int *last_steps, int *rules, void *stream);
+
+/* ---- per-call entry points: one call of the reference function per agent, host buffers in and out */
+/* FIVE_vag_concl (FIVE.h:102, FIVEVagConcl.c:64): ant [n][K] -> conc [n], hit [n] (rule index or -1) */
+int friq_batch_vag_concl(friq_batch *b, const double *ant, double *conc, int *hit);
+/* FIVE_vag_concl_weight (FIVE.h:101, FIVEVagConclWeight.c:52): weights [n][rule_capacity], filled when hit == -1 */
+int friq_batch_vag_concl_weight(friq_batch *b, const double *ant, int *hit, double *weights);
+/* frirl_get_best_action (frirl.h:54, frirl_get_best_action.c:31): states [n][S] -> actconc [n][A], best [n] */
+int friq_batch_get_best_action(friq_batch *b, const double *states, double *actconc, int *best);
+/* frirl_update_sarsa (frirl.h:64, frirl_update_sarsa.c:348): q_ant [n][K], reward [n], cur_q_ant [n][K] */
+int friq_batch_update_sarsa(friq_batch *b, const double *q_ant, const double *reward, const double *cur_q_ant);
+
+/* ---- rule-base files, byte-compatible with frirl_utils.c:100-281 */
+int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double *rant, const double *rconc);
+int friq_save_rb_to_bin_file(const char *file_name, int K, int R, const double *rant, const double *rconc);
+int friq_load_rb_from_bin_file(const char *file_name, int K, int max_rules, int *R, double *rant, double *rconc);
+
+/* ---- device self-tests / calibration used by tests and bench.py */
+int friq_device_trig(const double *x, double *sin_out, double *cos_out, long n);        /* correctly rounded sin/cos */
+int friq_device_pow_x87(const double *x, double *out, long n, int p, int force_exact);  /* fast_pow.inl:17-27 */
+int friq_device_fp64_peak(double *ginstr_per_s);                                        /* DADD/DMUL lane-instr/s */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,186 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C-ABI,
+against (a) the per-call vectors recorded from the compiled reference, (b) the reference's own
+tests/orig golden rule bases, (c) the oracle port on seeded random-exploration runs.
+Everything is compared bit-exactly (FP64 results as np.array_equal) - tighter than the 1e-12
+relative bound of the north star."""
+import numpy as np
+import pytest
+
+import _golden
+import _oracle
+
+pytestmark = pytest.mark.gpu
+CAP = {"mountaincar": 192, "acrobot": 704, "cartpole": 512}
+
+
+@pytest.fixture(scope="module")
+def fq():
+    import friq_b200
+    friq_b200.lib()
+    assert friq_b200.device_count() >= 1
+    return friq_b200
+
+
+@pytest.fixture(scope="module", params=_golden.ENVS)
+def env(request, fq):
+    name = request.param
+    P = fq.Problem(name)
+    yield name, _golden.load(name), P
+    P.close()
+
+
+def test_device_pow_x87_fast_and_exact_paths(fq):
+    rng = np.random.default_rng(5)
+    L = _oracle.lib()
+    for p in (2, 3, 4, 5, 8):
+        d = np.concatenate([rng.uniform(1e-3, 60.0, 200000), np.sqrt(rng.uniform(1e-6, 2500.0, 200000)),
+                            2.0 ** rng.integers(-8, 8, 64), np.float64([1.0, 2.0, 0.5, 1.0 + 2 ** -52, 1.0 - 2 ** -53])])
+        want = np.array([L.fo_pow_x87(float(x), p) for x in d[:60000]])
+        got = fq.device_pow_x87(d, p)
+        exact = fq.device_pow_x87(d, p, force_exact=True)
+        assert np.array_equal(got, exact)              # fast path + filter == integer emulation, everywhere
+        assert np.array_equal(got[:60000], want)       # == x87 long double chain (fast_pow.inl:17-27)
+
+
+def test_device_trig_is_correctly_rounded(fq):
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-4.5, 1.5, 100000)])
+    s, c = fq.device_trig(x)
+    P = _oracle.Problem(0, trig=1)
+    L = _oracle.lib()
+    idx = rng.integers(0, x.size, 30000)
+    assert all(s[i] == L.fo_sin(P.h, float(x[i])) and c[i] == L.fo_cos(P.h, float(x[i])) for i in idx)
+
+
+def test_get_best_action_vectors(fq, env):
+    name, g, P = env
+    recs = g["gba"]
+    b = fq.Batch(P, len(recs), CAP[name])
+    for i, r in enumerate(recs):
+        b.set_rulebase(r["rant"], r["rconc"], agent=i)
+    best, actconc = b.best_action(np.stack([r["states"] for r in recs]))
+    for i, r in enumerate(recs):
+        assert best[i] == r["best"]
+        assert np.array_equal(actconc[i], r["actconc"])
+    b.close()
+
+
+def test_vag_concl_and_weight_vectors(fq, env):
+    name, g, P = env
+    recs = [r for r in g["sarsa"]]
+    b = fq.Batch(P, len(recs), CAP[name])
+    for i, r in enumerate(recs):
+        b.set_rulebase(r["rant"], r["rconc"], agent=i)
+    for j in range(2):                                  # qp and qnow are evaluated on the unmodified rule base
+        hit, conc = b.vag_concl(np.stack([r["concl"][j]["ant"] for r in recs]))
+        for i, r in enumerate(recs):
+            assert hit[i] == r["concl"][j]["ret"] and conc[i] == r["concl"][j]["conc"]
+    wrecs = [(i, r) for i, r in enumerate(recs) if r["weight"] is not None and r["R_after"] == r["R"]]
+    ant = np.stack([r["weight"]["ant"] if r["weight"] is not None else r["q_ant"] for r in recs])
+    hit, w = b.vag_concl_weight(ant)
+    for i, r in wrecs:
+        assert hit[i] == r["weight"]["ret"]
+        if hit[i] < 0:
+            assert np.array_equal(w[i, :r["R"]], r["weight"]["weights"])
+    b.close()
+
+
+def test_update_sarsa_vectors(fq, env):
+    name, g, P = env
+    recs = g["sarsa"]
+    b = fq.Batch(P, len(recs), CAP[name])
+    for i, r in enumerate(recs):
+        b.set_rulebase(r["rant"], r["rconc"], agent=i)
+    b.set_inserted(np.array([r["inserted_before"] for r in recs]))
+    b.update_sarsa(np.stack([r["q_ant"] for r in recs]), np.array([r["reward"] for r in recs]),
+                   np.stack([r["cur_q_ant"] for r in recs]))
+    ins = b.get_inserted()
+    for i, r in enumerate(recs):
+        R, rant, rconc = b.get_rulebase(i)
+        assert R == r["R_after"], (i, r["cat"])
+        assert np.array_equal(rant, r["rant_after"])
+        assert np.array_equal(rconc, r["rconc_after"]), (i, r["cat"])
+        assert ins[i] == r["inserted_after"]
+    b.close()
+
+
+def _construct(fq, b, max_steps):
+    """frirl_sequential_run's construct loop (frirl_sequential_run.c:57-161), one launch per episode."""
+    log = []
+    for _ in range(999):
+        b.run(max_steps, fq.RUN_LEARN | fq.RUN_TRACK | fq.RUN_STOP_AT_EPISODE_END)
+        o = b.gather()
+        log.append((o["episodes"][0], o["last_steps"][0], o["last_return"][0], o["rules"][0]))
+        if o["flags"][0] & fq.F_CONVERGED:
+            break
+    return np.array(log, dtype=np.float64), o
+
+
+def test_construct_run_reproduces_reference_golden(fq, env):
+    """The fused step kernel, stepping the example's dynamics on the device with no_random = 1, must
+    reproduce the reference's whole learning trajectory: per-episode (steps, reward, rules) and the
+    final rule base, byte-identical to tests/orig (tests/_test.sh:8-17)."""
+    name, g, P = env
+    n = 40                                              # >1 warp: every agent must agree (whole-batch self-check)
+    b = fq.Batch(P, n, CAP[name])
+    log, o = _construct(fq, b, 1000)
+    ref = np.array(g["episodes"], dtype=np.float64)
+    assert log.shape == ref.shape and np.array_equal(log, ref)
+    assert np.all(o["episodes"] == o["episodes"][0]) and np.all(o["rules"] == o["rules"][0])
+    assert not np.any(o["flags"] & fq.F_OVERFLOW)
+    for agent in (0, 17, n - 1):
+        R, rant, rconc = b.get_rulebase(agent)
+        assert _golden.rb_text(rant, rconc) == _golden.golden_text(name)
+    b.close()
+
+
+@pytest.mark.parametrize("name", ["mountaincar", "acrobot"])
+def test_random_exploration_matches_oracle_port(fq, name):
+    """epsilon-greedy with the Philox stream: per-agent seeds, per-agent hyper-parameters, chunked
+    launches (state must survive kernel boundaries); every agent equals the oracle port bit for bit."""
+    P = fq.Problem(name, no_random=0)
+    n, first = 24, 1000
+    rng = np.random.default_rng(3)
+    alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.01, 0.05, 0.2], n)
+    b = fq.Batch(P, n, CAP[name], seed0=0x5EED0000, first_agent=first)
+    b.set_hyper(alpha, gamma, eps)
+    steps = 1500 if name == "mountaincar" else 700
+    for chunk in (1, 7, steps - 8):
+        b.run(chunk, fq.RUN_LEARN)
+    o = b.gather()
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
+    for i in range(n):
+        a = _oracle.Agent(OP, CAP[name], seed=0x5EED0000 + first + i)
+        a.set_hyper(alpha[i], gamma[i], eps[i])
+        a.run_steps(steps)
+        s = a.summary()
+        R, rant, rconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(rant, orant) and np.array_equal(rconc, orconc), i
+        assert (o["episodes"][i], o["last_steps"][i], o["last_return"][i], o["total_steps"][i], o["sum_rules"][i]) == \
+            (s["episode_num"] - 1, s["last_steps"], s["last_return"], s["total_steps"], s["sum_rules"])
+    b.close(); P.close()
+
+
+def test_inference_mode_leaves_rule_base_untouched(fq):
+    """reduction_state = 1 semantics (frirl_test_run.c:65-69): greedy episode, no rule-base writes."""
+    g = _golden.load("mountaincar")
+    P = fq.Problem("mountaincar")
+    b = fq.Batch(P, 33, 192)
+    b.set_rulebase(g["final"][1], g["final"][2])          # all agents get the learned rule base
+    b.run(1000, fq.RUN_STOP_AT_EPISODE_END)               # no RUN_LEARN
+    o = b.gather()
+    last = g["episodes"][-1]
+    assert np.all(o["last_steps"] == last[1]) and np.all(o["last_return"] == last[2])
+    R, rant, rconc = b.get_rulebase(32)
+    assert np.array_equal(rant, g["final"][1]) and np.array_equal(rconc, g["final"][2])
+    b.close(); P.close()
+
+
+def test_capacity_overflow_is_flagged(fq):
+    P = fq.Problem("mountaincar")
+    b = fq.Batch(P, 32, 12)                               # 8 corner rules + room for 4
+    b.run(400, fq.RUN_LEARN)
+    o = b.gather()
+    assert np.all(o["rules"] == 12) and np.all(o["flags"] & fq.F_OVERFLOW)
+    b.close(); P.close()

@@ -1,0 +1,28 @@
+/* tests/trig_host_shim.c -- compiles the PRODUCT's csrc/friq_trig.h for the host
+ * so the exact device algorithm can be checked against binary128 on the CPU. */
+#include "friq_trig.h"
+#include <quadmath.h>
+double shim_sin(double x) { return friq_sin(x); }
+double shim_cos(double x) { return friq_cos(x); }
+/* returns the number of points where the result is not the correctly rounded one */
+long shim_check(const double *x, long n, double *worst_x) {
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        double s, c; friq_sincos(x[i], &s, &c);
+        if (s != (double)sinq((__float128)x[i]) || c != (double)cosq((__float128)x[i])) { bad++; *worst_x = x[i]; }
+    }
+    return bad;
+}
+/* max relative error of the double-double result vs binary128, in units of 2^-90 */
+double shim_dd_err(const double *x, long n) {
+    double worst = 0;
+    for (long i = 0; i < n; i++) {
+        friq_dd s, c; friq_sincos_dd(x[i], &s, &c);
+        __float128 es = sinq((__float128)x[i]), ec = cosq((__float128)x[i]);
+        __float128 ds = ((__float128)s.h + s.l - es) / es, dc = ((__float128)c.h + c.l - ec) / ec;
+        double a = fabs((double)ds) * 0x1p90, b = fabs((double)dc) * 0x1p90;
+        if (a > worst) worst = a;
+        if (b > worst) worst = b;
+    }
+    return worst;
+}
