@@ -1,0 +1,268 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native FRIQ-learning engine.
+
+Metric (BASELINE.json): agent env-steps/sec (FIVE evals/sec reported beside it) for a batch of
+independent mountaincar FRIQ-learning agents, configs[2]: 65,536 agents per GPU, epsilon-greedy
+(Philox), learning from the corner rule base.  One bench "step" = one launch of the fused step
+kernel advancing EVERY agent by --chunk env steps (dynamics + best action over all actions +
+SARSA update / rule insertion).  Weak scaling: agents per GPU fixed.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU)
+  python bench.py --impl reference ...                            the reference's own CPU implementation
+                                                                  (oracle/_ref, unmodified reference build)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "fri-reinforcementlearning-c_b200"))
+
+METRIC = "agent_env_steps_per_sec"
+UNIT = "env-steps/s"
+WORKLOAD = "mountaincar FRIQ-learning, 65536 agents/GPU, eps-greedy 0.01 (Philox), learning from corner rule base"
+# algorithmic work of one learning env step of mountaincar (S=2, K=p=3, A=3) with R rules
+F_ALG_PER_RULE = 82.0          # FP64 ops (sub/mul/add/cmp/sqrt/div = 1 each), reference's op count
+BYTES_ALG_PER_RULE = 19.0      # index-form rule base streamed once per step (K*1 + 8 read, 8 write back)
+BYTES_ALG_PER_STEP = 256.0     # agent state in + out
+EVALS_PER_STEP = 6.5           # FIVE evals per env step = A + 3 .. A + 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--agents", type=int, default=65536, help="agents per GPU")
+    ap.add_argument("--chunk", type=int, default=250, help="env steps per agent per bench step (one kernel launch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def run_reference(steps_per_agent, target_seconds=15.0):
+    """Time the UNMODIFIED reference (oracle/_ref/ref_mountaincar, built by oracle/Makefile from the
+    reference sources with its own flags -O2 -mavx2) on all host cores: one process per core, each
+    stepping independent mountaincar agents (construct mode, no_random=1: the reference's RNG is
+    unseedable) for `steps_per_agent` env steps of frirl_episode() per agent."""
+    exe = os.path.join(REPO, "oracle", "_ref", "ref_mountaincar")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/ref_mountaincar missing: run `make -C oracle ref` where /root/reference exists")
+    cores = os.cpu_count() or 1
+
+    def once(reps):
+        env = dict(os.environ, REF_MODE="bench", REF_PROCS=str(cores), REF_STEPS=str(steps_per_agent), REF_REPS=str(reps))
+        out = subprocess.run([exe], env=env, capture_output=True, text=True, check=True).stdout
+        m = re.search(r"steps=(\d+) busy_s_per_proc=([\d.]+) wall_s=([\d.]+) steps_per_s=([\d.]+)", out)
+        return float(m.group(1)), float(m.group(2)), float(m.group(3)), float(m.group(4))
+
+    _, busy, _, _ = once(4)
+    reps = max(4, min(20000, int(4 * target_seconds / max(busy, 1e-3))))
+    steps, busy, wall, rate = once(reps)
+    return dict(value=rate, unit=UNIT, cores=cores, kind="reference",
+                sample=f"{cores} processes x {reps} independent agents x {steps_per_agent} env steps each "
+                       f"({int(steps)} steps, {busy:.2f} s busy per process, frirl_episode() time only)")
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate(); self.p.wait()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    steps_per_agent = (args.warmup + args.steps) * args.chunk
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = run_reference(steps_per_agent)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "mountaincar FRIQ-learning (reference C/AVX2 build, no_random=1), independent agents on all host cores",
+                       "steps_per_agent": steps_per_agent},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "five_evals_per_sec": cb["value"] * EVALS_PER_STEP}))
+        return
+
+    import torch
+    import friq_b200 as fq
+
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.agents
+    stream = torch.cuda.current_stream()
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+
+    P = fq.Problem("mountaincar", no_random=0)
+    b = fq.Batch(P, n, 192, device=local, seed0=0x5EED0000, first_agent=rank * n)
+    mode = fq.RUN_LEARN | fq.RUN_RETILE      # agents are re-assigned to warps by rule count before every launch
+
+    # device-side result buffers for the NCCL gather of per-agent (return f64, steps i32, rules i32)
+    d_ret = torch.empty(n, dtype=torch.float64, device="cuda"); d_steps = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_rules = torch.empty(n, dtype=torch.int32, device="cuda")
+    if world > 1:
+        g_ret = torch.empty(world * n, dtype=torch.float64, device="cuda"); g_steps = torch.empty(world * n, dtype=torch.int32, device="cuda")
+        g_rules = torch.empty(world * n, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(3, dtype=torch.float64, device="cuda")
+
+    def gather_results():
+        b.gather_device(ctypes.c_void_p(d_ret.data_ptr()), ctypes.c_void_p(d_steps.data_ptr()), ctypes.c_void_p(d_rules.data_ptr()), sptr)
+        if world > 1:       # the path's only exchange: per-agent results + rule-base statistics over NCCL/NVLink
+            dist.all_gather_into_tensor(g_ret, d_ret); dist.all_gather_into_tensor(g_steps, d_steps); dist.all_gather_into_tensor(g_rules, d_rules)
+            stats[0] = d_rules.sum(); stats[1] = d_ret.sum(); stats[2] = d_rules.max()
+            dist.all_reduce(stats[:2]); dist.all_reduce(stats[2:], op=dist.ReduceOp.MAX)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn):
+        b.reset()
+        for _ in range(args.warmup):
+            step_fn()
+        o0 = b.gather()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk = ClockSampler(local) if rank == 0 else None
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_fn()
+        e1.record(stream)
+        barrier()
+        clocks = clk.stop() if clk else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        o1 = b.gather()
+        dsteps = int((o1["total_steps"] - o0["total_steps"]).sum()); drules = int((o1["sum_rules"] - o0["sum_rules"]).sum())
+        tot = torch.tensor([dsteps, drules], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        return float(ms.item()), int(tot[0].item()), int(tot[1].item()), clocks, o1
+
+    # ---- (1) device-resident: inputs already in HBM, one kernel launch per step (+ the result gather)
+    def step_device():
+        b.run(args.chunk, mode, stream=sptr, sync=False)
+        gather_results()
+
+    ms, nsteps, sumR, clocks, o1 = timed(step_device)
+    assert nsteps == world * n * args.chunk * args.steps, "work skipped inside the timed region"
+
+    # ---- (2) end to end through the C-ABI with HOST buffers: H2D hyper-parameters, run, D2H results
+    h_alpha = torch.full((n,), 0.5, dtype=torch.float64).pin_memory(); h_gamma = torch.full((n,), 1.0, dtype=torch.float64).pin_memory()
+    h_eps = torch.full((n,), 0.01, dtype=torch.float64).pin_memory()
+    h_ret = torch.empty(n, dtype=torch.float64).pin_memory(); h_steps = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_rules = torch.empty(n, dtype=torch.int32).pin_memory()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def step_e2e():
+        b.run_host(args.chunk, mode, vp(h_alpha), vp(h_gamma), vp(h_eps), vp(h_ret), vp(h_steps), vp(h_rules), sptr)
+        _ = float(h_ret[0])
+
+    ms_e2e, nsteps_e2e, _, _, _ = timed(step_e2e)
+
+    fp64_peak_g = fq.device_fp64_peak()          # measured DADD/DMUL lane-instr/s of this GPU (G/s)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    t = ms * 1e-3
+    f_alg = F_ALG_PER_RULE * sumR / world           # per GPU
+    bytes_alg = (BYTES_ALG_PER_RULE * sumR + BYTES_ALG_PER_STEP * nsteps) / world
+    ach_tflops = f_alg / t / 1e12
+    ach_gbs = bytes_alg / t / 1e9
+    frac_fp64 = ach_tflops / (fp64_peak_g / 1e3); frac_hbm = ach_gbs / hbm_peak
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = nsteps / t
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "agents_per_gpu": n, "env_steps_per_agent_per_step": args.chunk,
+                   "rule_capacity": 192, "mean_rules_in_timed_region": sumR / max(nsteps, 1),
+                   "l2": "inputs larger than L2: rule bases + scratch = %.0f MB per GPU" % (n * 192 * 20 / 1e6),
+                   "rng": "Philox4x32-10, key = 0x5EED0000 + agent id"},
+        "five_evals_per_sec": value * EVALS_PER_STEP,
+        "e2e": {"value": nsteps_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 16 * n,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": args.steps * 8,   # per step: 4 re-tiling kernels + k_run_steps + 3 result un-permute kernels
+        
+        "clocks": clocks,
+        "roofline": {"bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",
+                     "achieved": ach_tflops if frac_fp64 >= frac_hbm else ach_gbs,
+                     "peak": fp64_peak_g / 1e3 if frac_fp64 >= frac_hbm else hbm_peak,
+                     "unit": "TFLOP/s" if frac_fp64 >= frac_hbm else "GB/s",
+                     "frac": max(frac_fp64, frac_hbm), "traffic": None,
+                     "kernel": "k_run_steps<2,3,3,3,mountaincar>",
+                     "note": "algorithmic FP64 ops of the reference path (SURVEY 8d: 82*R per env step, sqrt and / counted as 1) over the "
+                             "measured non-FMA FP64 issue rate of this GPU (friq_device_fp64_peak, DADD/DMUL lane-ops/s); "
+                             "hbm view: %.1f GB/s algorithmic of %.0f GB/s measured = %.3f" % (ach_gbs, hbm_peak, frac_hbm)},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            out["cpu_baseline"] = run_reference(steps_per_agent)
+        except Exception as e:       # noqa: BLE001 - reported, never silently dropped
+            out["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

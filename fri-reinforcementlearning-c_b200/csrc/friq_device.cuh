@@ -83,6 +83,13 @@ __device__ __forceinline__ double friq_shepard_weight(double s)
     const double d = __dsqrt_rn(s);                       // vsqrtpd, five_rule_distance.c:205
     return __drcp_rn(friq_pow_x87<P>(d));                 // 1.0 / fast_pow(|d|, p)
 }
+// same value, branch-free; bad != 0 => not proven, recompute with friq_shepard_weight
+template <int P>
+__device__ __forceinline__ double friq_shepard_weight_fast(double s, unsigned &bad)
+{
+    const double d = friq_sqrt_fast(s, bad);
+    return friq_rcp_fast(friq_pow_x87_fast<P>(d, bad), bad);
+}
 
 // first rule whose distance from vo[] (all K dims) is exactly 0, else -1
 // (five_rule_distance.c:206-262 early exit + FIVEVagConcl.c:96-105 rescan)
@@ -170,15 +177,23 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
                     if (sq == 0.0 && hitq < 0) hitq = i;
                 }
             }
+            double sa[ACH], wv[ACH];
+            unsigned bad = 0;
 #pragma unroll
             for (int a = 0; a < ACH; a++) {
                 const double da = __dsub_rn(ave[a], va);
-                const double s = __dadd_rn(__dmul_rn(da, da), ssum);                         // A5
-                const bool z = (s == 0.0);
-                if (z && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q; }           // BestAct.c:89-93
-                const double wi = friq_shepard_weight<P>(z ? 1.0 : s);
-                vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wi, q));                               // BestAct.c:216
-                ws[a] = __dadd_rn(ws[a], wi);                                                 // :217
+                sa[a] = __dadd_rn(__dmul_rn(da, da), ssum);                                  // A5
+                wv[a] = friq_shepard_weight_fast<P>(sa[a] == 0.0 ? 1.0 : sa[a], bad);
+            }
+            if (bad) {                                   // rare: operand outside the proven fast paths
+#pragma unroll
+                for (int a = 0; a < ACH; a++) wv[a] = friq_shepard_weight<P>(sa[a] == 0.0 ? 1.0 : sa[a]);
+            }
+#pragma unroll
+            for (int a = 0; a < ACH; a++) {
+                if (sa[a] == 0.0 && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q; }   // BestAct.c:89-93
+                vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[a], q));                            // BestAct.c:216
+                ws[a] = __dadd_rn(ws[a], wv[a]);                                              // :217
             }
             w = wn; q = qn;
         }

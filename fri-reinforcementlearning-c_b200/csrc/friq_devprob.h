@@ -35,7 +35,7 @@
 /* per-agent flag bits */
 enum { FRIQ_F_NEED_RESET = 1, FRIQ_F_INSERTED = 2, FRIQ_F_CONVERGED = 4, FRIQ_F_OVERFLOW = 8 };
 /* run mode bits */
-enum { FRIQ_M_LEARN = 1, FRIQ_M_TRACK = 2, FRIQ_M_STOP_ON_CONVERGE = 4, FRIQ_M_STOP_AT_EPISODE_END = 8 };
+enum { FRIQ_M_LEARN = 1, FRIQ_M_TRACK = 2, FRIQ_M_STOP_ON_CONVERGE = 4, FRIQ_M_STOP_AT_EPISODE_END = 8, FRIQ_M_RETILE = 16 };
 
 typedef struct friq_devprob {
     int S, K, A, U, p, env, skip_rules, no_random;
@@ -76,6 +76,7 @@ typedef struct friq_devstate {
     double *ep_return, *last_return, *prev_reward;
     unsigned long long *total_steps, *sum_rules, *seed;
     double *alpha, *gamma, *epsilon;
+    int *agent_of_slot;         /* [n_pad] which agent lives in slot p (identity unless re-tiled by rule count) */
 } friq_devstate;
 
 #ifdef __cplusplus
@@ -95,6 +96,8 @@ int friqd_h2d_async(void *dst, const void *src, unsigned long bytes, void *strea
 int friqd_d2h_async(void *dst, const void *src, unsigned long bytes, void *stream);
 int friqd_device_count(int *count);
 int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const double *d_q, int R, void *stream);
+int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules, void *stream);
+int friqd_unpermute(friq_devstate st, const void *src, void *dst, int elem_bytes, void *stream);
 int friqd_sync(void *stream);
 const char *friqd_error_string(int err);
 int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long long seed0, long first_agent,

@@ -59,66 +59,77 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     const double alpha = st.alpha[ag], gamma = st.gamma[ag], epsilon = st.epsilon[ag];
     const bool learn = mode & FRIQ_M_LEARN, track = (mode & FRIQ_M_TRACK) && prevq;
 
+    // All lanes of a warp iterate in lockstep (explicit reconvergence at the loop top): a lane that starts
+    // an episode spends one iteration on the initial action selection (frirl_episode.c:78) while its
+    // neighbours step, and a lane that has finished idles until the slowest lane of the warp is done.
+    const unsigned wmask = __activemask();
     long done_steps = 0;
-    while (done_steps < n_steps) {
-        if ((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED)) break;
+    bool running = true;
+    while (__any_sync(wmask, running && done_steps < n_steps)) {
+        const bool act = running && done_steps < n_steps && !((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED));
         const bool initial = flags & FRIQ_F_NEED_RESET;
         double cur[S], cq[S], vc[S], reward = 0.0; int done = 0;
-        if (initial) {                                   // frirl_episode.c:46-82
+        if (act) {
+            if (initial) {                               // frirl_episode.c:46-82
 #pragma unroll
-            for (int k = 0; k < S; k++) { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; cur[k] = cq[k] = s[k]; }
-            ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
-            prev_numru = R;
-            if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
-        } else {                                         // frirl_episode.c:97-112
-            friq_env_step<ENV>(pb.act_val[aidx], s, cur);
-            friq_env_reward<ENV>(cur, reward, done);
-            ep_return = __dadd_rn(ep_return, reward);
-            friq_env_quantize<ENV, S>(pb, cur, cq, vc);
-            step_in_ep++;
+                for (int k = 0; k < S; k++) { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; cur[k] = cq[k] = s[k]; }
+                ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
+                prev_numru = R;
+                if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
+            } else {                                     // frirl_episode.c:97-112
+                friq_env_step<ENV>(pb.act_val[aidx], s, cur);
+                friq_env_reward<ENV>(cur, reward, done);
+                ep_return = __dadd_rn(ep_return, reward);
+                friq_env_quantize<ENV, S>(pb, cur, cq, vc);
+                step_in_ep++;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < S; k++) { cur[k] = s[k]; cq[k] = qs[k]; vc[k] = vo[k]; }
+            running = false;
         }
         // best action at the new observation (+ exact-hit scan of Q(s,a) for the update)
         double actconc[A]; int hitq;
-        friq_best_action_pass<S, P, A, ACH, true>(pb, rbw, rbq, R, vc, actconc, vo, hitq);
+        friq_best_action_pass<S, P, A, ACH, true>(pb, rbw, rbq, act ? R : 0, vc, actconc, vo, hitq);
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
-        if (initial) {
+        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; }
+        if (act && !initial) {
+            sum_rules += (unsigned long long)R;
+            if (learn) {                                 // frirl_update_sarsa.c:348-385
+                double qp, qnow, ws = 0.0;
+                if (pb.qp_reuse) qp = friq_pick<A>(actconc, a2);      // Q(s',a') == actconc[a'] bit for bit
+                else {
+                    double vq[K], wsd;
+#pragma unroll
+                    for (int k = 0; k < S; k++) vq[k] = vc[k];
+                    vq[S] = pb.act_ve_eval[a2];
+                    friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vq, qp, wsd);
+                }
+                if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
+                else { double vagc; friq_shepard<K, P>(pb, rbw, rbq, sw, R, vo, vagc, ws); qnow = __ddiv_rn(vagc, ws); }
+                friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward, qp, hitq, qnow, ws, alpha, gamma);
+            }
+            // frirl_episode.c:163-185
+#pragma unroll
+            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; }
             aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
-            continue;
-        }
-        sum_rules += (unsigned long long)R;
-        if (learn) {                                     // frirl_update_sarsa.c:348-385
-            double qp, qnow, ws = 0.0;
-            if (pb.qp_reuse) qp = friq_pick<A>(actconc, a2);      // Q(s',a') == actconc[a'] bit for bit
-            else {
-                double vq[K], wsd;
-#pragma unroll
-                for (int k = 0; k < S; k++) vq[k] = vc[k];
-                vq[S] = pb.act_ve_eval[a2];
-                friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vq, qp, wsd);
+            total_steps++; done_steps++;
+            if (done || step_in_ep >= pb.max_steps) {
+                // "RB complete" predicate, frirl_sequential_run.c:83-150
+                if (learn && track && prev_numru == R && prev_steps == step_in_ep && ep_return > pb.reward_good_above && prev_reward == ep_return) {
+                    bool ok = true;
+                    for (int i = 0; i < R && ok; i++)
+                        if (fabs(__dsub_rn(rbq[(size_t)i * FRIQ_TILE], prevq[(size_t)i * FRIQ_TILE])) >= pb.qdiff_final_tol) ok = false;
+                    if (ok) flags |= FRIQ_F_CONVERGED;
+                }
+                last_return = ep_return; last_steps = step_in_ep; last_rules = R;
+                prev_reward = ep_return; prev_steps = step_in_ep;
+                ep_num++;
+                flags |= FRIQ_F_NEED_RESET;
+                if (mode & FRIQ_M_STOP_AT_EPISODE_END) running = false;
             }
-            if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
-            else { double vagc; friq_shepard<K, P>(pb, rbw, rbq, sw, R, vo, vagc, ws); qnow = __ddiv_rn(vagc, ws); }
-            friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward, qp, hitq, qnow, ws, alpha, gamma);
         }
-        // frirl_episode.c:163-185
-#pragma unroll
-        for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; }
-        aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
-        total_steps++; done_steps++;
-        if (done || step_in_ep >= pb.max_steps) {
-            // "RB complete" predicate, frirl_sequential_run.c:83-150
-            if (learn && track && prev_numru == R && prev_steps == step_in_ep && ep_return > pb.reward_good_above && prev_reward == ep_return) {
-                bool ok = true;
-                for (int i = 0; i < R && ok; i++)
-                    if (fabs(__dsub_rn(rbq[(size_t)i * FRIQ_TILE], prevq[(size_t)i * FRIQ_TILE])) >= pb.qdiff_final_tol) ok = false;
-                if (ok) flags |= FRIQ_F_CONVERGED;
-            }
-            last_return = ep_return; last_steps = step_in_ep; last_rules = R;
-            prev_reward = ep_return; prev_steps = step_in_ep;
-            ep_num++;
-            flags |= FRIQ_F_NEED_RESET;
-            if (mode & FRIQ_M_STOP_AT_EPISODE_END) break;
-        }
+        __syncwarp(wmask);
     }
 
     // ---- registers -> agent state
@@ -207,6 +218,7 @@ __global__ void k_init_agents(const friq_devprob *__restrict__ gprob, friq_devst
     st.total_steps[ag] = 0ull; st.sum_rules[ag] = 0ull;
     st.seed[ag] = seed0 + (unsigned long long)(first_agent + ag);
     st.alpha[ag] = alpha; st.gamma[ag] = gamma; st.epsilon[ag] = epsilon;
+    st.agent_of_slot[ag] = (int)ag;
 }
 
 __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict__ words, const double *__restrict__ q, int R)
@@ -218,6 +230,63 @@ __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict_
     st.R[ag] = R;
 }
 
+// ---------------------------------------------------------------------------------------
+// Re-tiling: agents are re-assigned to slots in descending order of their rule count so that the
+// 32 lanes of a warp walk rule bases of (nearly) equal length - the rule loop is the hot loop and
+// its trip count is the per-lane rule count.  Placement never changes an agent's results; slot p
+// remembers which agent it holds (agent_of_slot) so results are reported in agent order.
+// work[0..cap] = histogram / running offsets, work[cap+1 ..] = new slot of every old slot.
+// by_rules == 0 restores the identity placement.
+// ---------------------------------------------------------------------------------------
+__global__ void k_retile_hist(friq_devstate st, int *work)
+{
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < st.n) atomicAdd(&work[st.R[p]], 1);
+}
+__global__ void k_retile_scan(int *work, int cap)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int off = 0;
+    for (int r = cap; r >= 0; r--) { const int c = work[r]; work[r] = off; off += c; }
+}
+__global__ void k_retile_assign(friq_devstate st, int *work, int by_rules)
+{
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= st.n) return;
+    work[st.cap + 1 + p] = by_rules ? atomicAdd(&work[st.R[p]], 1) : st.agent_of_slot[p];
+}
+__global__ void k_retile_move(friq_devstate a, friq_devstate b, const int *work)
+{
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n) return;
+    const long q = work[a.cap + 1 + p];
+    for (int k = 0; k < FRIQ_MAXK; k++) {
+        b.s[(size_t)k * b.n_pad + q] = a.s[(size_t)k * a.n_pad + p];
+        b.qs[(size_t)k * b.n_pad + q] = a.qs[(size_t)k * a.n_pad + p];
+        b.vo[(size_t)k * b.n_pad + q] = a.vo[(size_t)k * a.n_pad + p];
+    }
+    b.aidx[q] = a.aidx[p]; b.flags[q] = a.flags[p]; b.R[q] = a.R[p]; b.step_in_ep[q] = a.step_in_ep[p];
+    b.last_steps[q] = a.last_steps[p]; b.last_rules[q] = a.last_rules[p]; b.prev_steps[q] = a.prev_steps[p]; b.prev_numru[q] = a.prev_numru[p];
+    b.ep_num[q] = a.ep_num[p]; b.ep_return[q] = a.ep_return[p]; b.last_return[q] = a.last_return[p]; b.prev_reward[q] = a.prev_reward[p];
+    b.total_steps[q] = a.total_steps[p]; b.sum_rules[q] = a.sum_rules[p]; b.seed[q] = a.seed[p];
+    b.alpha[q] = a.alpha[p]; b.gamma[q] = a.gamma[p]; b.epsilon[q] = a.epsilon[p];
+    b.agent_of_slot[q] = a.agent_of_slot[p];
+    const size_t po = (size_t)(p >> 5) * a.cap * FRIQ_TILE + (p & 31), qo = (size_t)(q >> 5) * b.cap * FRIQ_TILE + (q & 31);
+    const int R = a.R[p];
+    for (int i = 0; i < R; i++) {
+        b.rbw[qo + (size_t)i * FRIQ_TILE] = a.rbw[po + (size_t)i * FRIQ_TILE];
+        b.rbq[qo + (size_t)i * FRIQ_TILE] = a.rbq[po + (size_t)i * FRIQ_TILE];
+    }
+    if (a.prevq && b.prevq)
+        for (int i = 0; i < R; i++) b.prevq[qo + (size_t)i * FRIQ_TILE] = a.prevq[po + (size_t)i * FRIQ_TILE];
+}
+template <typename T>
+__global__ void k_unpermute(friq_devstate st, const T *src, T *dst)
+{
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < st.n) dst[st.agent_of_slot[p]] = src[p];
+}
+
 __global__ void k_trig(const double *x, double *s, double *c, long n)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,7 +295,19 @@ __global__ void k_trig(const double *x, double *s, double *c, long n)
 __global__ void k_pow(const double *x, double *out, long n, int p, int force_exact)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = force_exact ? friq_pow_x87_exact(x[i], p) : friq_pow_x87_rt(x[i], p);
+    if (i >= n) return;
+    if (force_exact == 0) out[i] = friq_pow_x87_rt(x[i], p);
+    else if (force_exact == 1) out[i] = friq_pow_x87_exact(x[i], p);
+    else {                                   // Shepard weight 1/pow(sqrt(s)): 2 = library ops, 3 = branch-free fast paths
+        unsigned bad = 0; double w;
+        if (force_exact == 2) w = __drcp_rn(friq_pow_x87_exact(__dsqrt_rn(x[i]), p));
+        else {
+            w = (p == 3) ? friq_shepard_weight_fast<3>(x[i], bad) : friq_shepard_weight_fast<5>(x[i], bad);
+            if (bad) w = (p == 3) ? friq_shepard_weight<3>(x[i]) : friq_shepard_weight<5>(x[i]);
+            if (force_exact == 4) w = (double)bad;
+        }
+        out[i] = w;
+    }
 }
 
 // FP64 issue-rate micro-benchmark: 8 independent DADD/DMUL chains per thread (no FMA, like the path)
@@ -282,6 +363,28 @@ int friqd_device_count(int *count) { CK(cudaGetDeviceCount(count)); return 0; }
 int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const double *d_q, int R, void *stream)
 {
     k_broadcast_rb<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(st, d_words, d_q, R);
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 g = grid_for(src.n);
+    if (by_rules) {
+        CK(cudaMemsetAsync(d_work, 0, sizeof(int) * (src.cap + 1), s));
+        k_retile_hist<<<g, FRIQ_BLOCK, 0, s>>>(src, d_work);
+        k_retile_scan<<<1, 32, 0, s>>>(d_work, src.cap);
+    }
+    k_retile_assign<<<g, FRIQ_BLOCK, 0, s>>>(src, d_work, by_rules);
+    k_retile_move<<<g, FRIQ_BLOCK, 0, s>>>(src, dst, d_work);
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_unpermute(friq_devstate st, const void *src, void *dst, int elem_bytes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (elem_bytes == 8) k_unpermute<unsigned long long><<<grid_for(st.n), FRIQ_BLOCK, 0, s>>>(st, (const unsigned long long *)src, (unsigned long long *)dst);
+    else k_unpermute<unsigned int><<<grid_for(st.n), FRIQ_BLOCK, 0, s>>>(st, (const unsigned int *)src, (unsigned int *)dst);
     CK(cudaGetLastError());
     return 0;
 }

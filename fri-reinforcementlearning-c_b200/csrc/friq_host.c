@@ -35,10 +35,13 @@ struct friq_problem {
 
 struct friq_batch {
     friq_problem *P;
-    friq_devstate st;
+    friq_devstate st;         /* current placement */
+    friq_devstate st2;        /* alternate buffers used by re-tiling (allocated on first use) */
+    int have_st2, permuted;
+    int *d_work;              /* re-tiling scratch */
+    void *d_tmp8, *d_tmp4a, *d_tmp4b;   /* un-permuted result staging */
     int device;
     uint64_t seed0; long first_agent;
-    void *slab;               /* per-agent scalar arrays */
     double *d_in0, *d_in1, *d_in2, *d_out0; int *d_iout; size_t cap_in, cap_out, cap_w; double *d_w;
 };
 
@@ -254,6 +257,53 @@ int friq_problem_tables(const friq_problem *P, double *u, double *ve, double *ud
 /* ------------------------------------------------------------------------------- batches */
 int friq_device_count(int *count) { DEV(friqd_device_count(count)); return 0; }
 
+/* device buffers of one placement: rule bases + one slab for the per-agent scalars
+ * (3*MAXK + 9 rows of 8 bytes, 11 rows of 4 bytes) */
+static int alloc_state(friq_devstate *st, int clear)
+{
+    const size_t slots = (size_t)st->n_pad * st->cap, np = (size_t)st->n_pad;
+    const size_t rows8 = 3 * FRIQ_MAXK + 9, rows4 = 11;
+    void *slab;
+    DEV(friqd_malloc((void **)&st->rbw, slots * 4)); DEV(friqd_malloc((void **)&st->rbq, slots * 8));
+    DEV(friqd_malloc(&slab, np * (rows8 * 8 + rows4 * 4)));
+    if (clear) { DEV(friqd_memset(st->rbw, 0, slots * 4)); DEV(friqd_memset(st->rbq, 0, slots * 8)); }
+    DEV(friqd_memset(slab, 0, np * (rows8 * 8 + rows4 * 4)));
+    double *p8 = (double *)slab;
+    st->s = p8; p8 += FRIQ_MAXK * np; st->qs = p8; p8 += FRIQ_MAXK * np; st->vo = p8; p8 += FRIQ_MAXK * np;
+    st->ep_return = p8; p8 += np; st->last_return = p8; p8 += np; st->prev_reward = p8; p8 += np;
+    st->alpha = p8; p8 += np; st->gamma = p8; p8 += np; st->epsilon = p8; p8 += np;
+    st->total_steps = (unsigned long long *)p8; p8 += np; st->sum_rules = (unsigned long long *)p8; p8 += np; st->seed = (unsigned long long *)p8; p8 += np;
+    int *p4 = (int *)p8;
+    st->aidx = p4; p4 += np; st->flags = p4; p4 += np; st->R = p4; p4 += np; st->step_in_ep = p4; p4 += np;
+    st->last_steps = p4; p4 += np; st->last_rules = p4; p4 += np; st->prev_steps = p4; p4 += np; st->prev_numru = p4; p4 += np;
+    st->ep_num = (unsigned int *)p4; p4 += np; st->agent_of_slot = p4; p4 += np;
+    return 0;
+}
+static void free_state(friq_devstate *st)
+{
+    friqd_free(st->rbw); friqd_free(st->rbq); if (st->prevq) friqd_free(st->prevq);
+    friqd_free(st->s);        /* slab base */
+}
+
+/* move every agent to a new slot: by_rules = 1 sorts by descending rule count, 0 restores identity */
+static int retile(friq_batch *b, int by_rules, void *stream)
+{
+    if (!by_rules && !b->permuted) return 0;
+    if (!b->have_st2) {
+        b->st2 = b->st; b->st2.prevq = NULL;
+        int rc = alloc_state(&b->st2, 0); if (rc) return rc;
+        DEV(friqd_malloc((void **)&b->d_work, sizeof(int) * (b->st.cap + 2 + (size_t)b->st.n_pad)));
+        b->have_st2 = 1;
+    }
+    if (b->st.prevq && !b->st2.prevq) DEV(friqd_malloc((void **)&b->st2.prevq, (size_t)b->st.n_pad * b->st.cap * 8));
+    b->st2.sw = b->st.sw;
+    DEV(friqd_retile(b->st, b->st2, b->d_work, by_rules, stream));
+    friq_devstate t = b->st; b->st = b->st2; b->st2 = t;
+    b->permuted = by_rules;
+    return 0;
+}
+#define IDENTITY(b) do { int rc_ = retile((b), 0, NULL); if (rc_) return rc_; } while (0)
+
 int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t seed0, long first_agent, friq_batch **out)
 {
     if (n < 1) FAIL(4, "friq_batch_create: n_agents must be >= 1");
@@ -263,22 +313,9 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
     friq_devstate *st = &b->st;
     st->n = n; st->n_pad = (n + FRIQ_TILE - 1) / FRIQ_TILE * FRIQ_TILE; st->cap = cap;
-    const size_t slots = (size_t)st->n_pad * cap, np = (size_t)st->n_pad;
-    DEV(friqd_malloc((void **)&st->rbw, slots * 4)); DEV(friqd_malloc((void **)&st->rbq, slots * 8)); DEV(friqd_malloc((void **)&st->sw, slots * 8));
-    DEV(friqd_memset(st->rbw, 0, slots * 4)); DEV(friqd_memset(st->rbq, 0, slots * 8)); DEV(friqd_memset(st->sw, 0, slots * 8));
-    /* one slab for the per-agent scalars: 3*MAXK + 10 f64/u64 rows, 9 i32/u32 rows */
-    const size_t rows8 = 3 * FRIQ_MAXK + 9, rows4 = 10;
-    DEV(friqd_malloc(&b->slab, np * (rows8 * 8 + rows4 * 4)));
-    DEV(friqd_memset(b->slab, 0, np * (rows8 * 8 + rows4 * 4)));
-    double *p8 = (double *)b->slab;
-    st->s = p8; p8 += FRIQ_MAXK * np; st->qs = p8; p8 += FRIQ_MAXK * np; st->vo = p8; p8 += FRIQ_MAXK * np;
-    st->ep_return = p8; p8 += np; st->last_return = p8; p8 += np; st->prev_reward = p8; p8 += np;
-    st->alpha = p8; p8 += np; st->gamma = p8; p8 += np; st->epsilon = p8; p8 += np;
-    st->total_steps = (unsigned long long *)p8; p8 += np; st->sum_rules = (unsigned long long *)p8; p8 += np; st->seed = (unsigned long long *)p8; p8 += np;
-    int *p4 = (int *)p8;
-    st->aidx = p4; p4 += np; st->flags = p4; p4 += np; st->R = p4; p4 += np; st->step_in_ep = p4; p4 += np;
-    st->last_steps = p4; p4 += np; st->last_rules = p4; p4 += np; st->prev_steps = p4; p4 += np; st->prev_numru = p4; p4 += np;
-    st->ep_num = (unsigned int *)p4; p4 += np;
+    { int rc2 = alloc_state(st, 1); if (rc2) return rc2; }
+    const size_t slots = (size_t)st->n_pad * cap;
+    DEV(friqd_malloc((void **)&st->sw, slots * 8)); DEV(friqd_memset(st->sw, 0, slots * 8));
     *out = b;
     return friq_batch_reset(b);
 }
@@ -286,6 +323,7 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
 int friq_batch_reset(friq_batch *b)
 {
     DEV(friqd_set_device(b->device));
+    b->permuted = 0;
     DEV(friqd_init_agents(b->P->dp, b->st, b->seed0, b->first_agent, b->P->alpha, b->P->gamma, b->P->epsilon, NULL));
     DEV(friqd_sync(NULL));
     return 0;
@@ -295,8 +333,10 @@ void friq_batch_destroy(friq_batch *b)
 {
     if (!b) return;
     friqd_set_device(b->device);
-    friqd_free(b->st.rbw); friqd_free(b->st.rbq); friqd_free(b->st.sw); if (b->st.prevq) friqd_free(b->st.prevq);
-    friqd_free(b->slab);
+    friqd_free(b->st.sw);
+    free_state(&b->st);
+    if (b->have_st2) { free_state(&b->st2); friqd_free(b->d_work); }
+    if (b->d_tmp8) { friqd_free(b->d_tmp8); friqd_free(b->d_tmp4a); friqd_free(b->d_tmp4b); }
     void *tmp[6] = { b->d_in0, b->d_in1, b->d_in2, b->d_out0, b->d_iout, b->d_w };
     for (int i = 0; i < 6; i++) if (tmp[i]) friqd_free(tmp[i]);
     free(b);
@@ -305,6 +345,7 @@ void friq_batch_destroy(friq_batch *b)
 int friq_batch_set_hyper(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon)
 {
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     const size_t nb = sizeof(double) * b->st.n;
     if (alpha) DEV(friqd_h2d(b->st.alpha, alpha, nb));
     if (gamma) DEV(friqd_h2d(b->st.gamma, gamma, nb));
@@ -318,6 +359,7 @@ int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant
     if (R < 0 || R > b->st.cap) FAIL(5, "friq_batch_set_rulebase: %d rules exceed the capacity %d", R, b->st.cap);
     if (agent >= b->st.n) FAIL(5, "friq_batch_set_rulebase: agent %ld out of range", agent);
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     unsigned int *w = (unsigned int *)malloc(sizeof(unsigned int) * (R + 1));
     int grew = 0;
     for (int i = 0; i < R; i++) {
@@ -355,6 +397,7 @@ int friq_batch_get_rulebase(friq_batch *b, long agent, int *R_out, double *rant,
     const friq_devprob *hp = &b->P->hp; const int K = hp->K;
     if (agent < 0 || agent >= b->st.n) FAIL(5, "friq_batch_get_rulebase: agent %ld out of range", agent);
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     int R; DEV(friqd_d2h(&R, b->st.R + agent, sizeof(int)));
     *R_out = R;
     if (!R || (!rant && !rconc)) return 0;
@@ -374,6 +417,7 @@ int friq_batch_get_rulebase(friq_batch *b, long agent, int *R_out, double *rant,
 int friq_batch_set_inserted(friq_batch *b, const int *inserted)
 {
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     int *f = (int *)malloc(sizeof(int) * b->st.n);
     int rc = friqd_d2h(f, b->st.flags, sizeof(int) * b->st.n);
     if (!rc) { for (long i = 0; i < b->st.n; i++) f[i] = (f[i] & ~FRIQ_F_INSERTED) | (inserted[i] ? FRIQ_F_INSERTED : 0); rc = friqd_h2d(b->st.flags, f, sizeof(int) * b->st.n); }
@@ -384,6 +428,7 @@ int friq_batch_set_inserted(friq_batch *b, const int *inserted)
 int friq_batch_get_inserted(friq_batch *b, int *inserted)
 {
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     DEV(friqd_d2h(inserted, b->st.flags, sizeof(int) * b->st.n));
     for (long i = 0; i < b->st.n; i++) inserted[i] = (inserted[i] & FRIQ_F_INSERTED) ? 1 : 0;
     return 0;
@@ -397,6 +442,7 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         const size_t slots = (size_t)b->st.n_pad * b->st.cap;
         DEV(friqd_malloc((void **)&b->st.prevq, slots * 8)); DEV(friqd_memset(b->st.prevq, 0, slots * 8));
     }
+    if (mode & FRIQ_RUN_RETILE) { int rc = retile(b, 1, stream); if (rc) return rc; }
     DEV(friqd_run_steps(&b->P->hp, b->P->dp, b->st, n_steps, mode, stream));
     return 0;
 }
@@ -407,6 +453,8 @@ int friq_batch_gather(friq_batch *b, double *last_return, int *last_steps, int *
 {
     const long n = b->st.n;
     DEV(friqd_set_device(b->device));
+    DEV(friqd_sync(NULL));
+    IDENTITY(b);
     if (last_return) DEV(friqd_d2h(last_return, b->st.last_return, 8 * n));
     if (last_steps) DEV(friqd_d2h(last_steps, b->st.last_steps, 4 * n));
     if (rules) DEV(friqd_d2h(rules, b->st.R, 4 * n));
@@ -421,6 +469,12 @@ int friq_batch_gather_device(friq_batch *b, void *d_ret, void *d_steps, void *d_
 {
     const long n = b->st.n;
     DEV(friqd_set_device(b->device));
+    if (b->permuted) {          /* report in agent order */
+        if (d_ret) DEV(friqd_unpermute(b->st, b->st.last_return, d_ret, 8, stream));
+        if (d_steps) DEV(friqd_unpermute(b->st, b->st.last_steps, d_steps, 4, stream));
+        if (d_rules) DEV(friqd_unpermute(b->st, b->st.R, d_rules, 4, stream));
+        return 0;
+    }
     if (d_ret) DEV(friqd_d2d_async(d_ret, b->st.last_return, 8 * n, stream));
     if (d_steps) DEV(friqd_d2d_async(d_steps, b->st.last_steps, 4 * n, stream));
     if (d_rules) DEV(friqd_d2d_async(d_rules, b->st.R, 4 * n, stream));
@@ -432,13 +486,22 @@ int friq_batch_run_host(friq_batch *b, const double *alpha, const double *gamma,
 {
     const long n = b->st.n;
     DEV(friqd_set_device(b->device));
-    if (alpha) DEV(friqd_h2d_async(b->st.alpha, alpha, 8 * n, stream));
-    if (gamma) DEV(friqd_h2d_async(b->st.gamma, gamma, 8 * n, stream));
-    if (epsilon) DEV(friqd_h2d_async(b->st.epsilon, epsilon, 8 * n, stream));
+    if (alpha || gamma || epsilon) {                     /* host arrays are in agent order */
+        int rc0 = retile(b, 0, stream); if (rc0) return rc0;
+        if (alpha) DEV(friqd_h2d_async(b->st.alpha, alpha, 8 * n, stream));
+        if (gamma) DEV(friqd_h2d_async(b->st.gamma, gamma, 8 * n, stream));
+        if (epsilon) DEV(friqd_h2d_async(b->st.epsilon, epsilon, 8 * n, stream));
+    }
     int rc = friq_batch_run(b, n_steps, mode, stream); if (rc) return rc;
-    if (last_return) DEV(friqd_d2h_async(last_return, b->st.last_return, 8 * n, stream));
-    if (last_steps) DEV(friqd_d2h_async(last_steps, b->st.last_steps, 4 * n, stream));
-    if (rules) DEV(friqd_d2h_async(rules, b->st.R, 4 * n, stream));
+    const void *s_ret = b->st.last_return, *s_steps = b->st.last_steps, *s_rules = b->st.R;
+    if (b->permuted) {
+        if (!b->d_tmp8) { DEV(friqd_malloc(&b->d_tmp8, 8 * b->st.n_pad)); DEV(friqd_malloc(&b->d_tmp4a, 4 * b->st.n_pad)); DEV(friqd_malloc(&b->d_tmp4b, 4 * b->st.n_pad)); }
+        rc = friq_batch_gather_device(b, b->d_tmp8, b->d_tmp4a, b->d_tmp4b, stream); if (rc) return rc;
+        s_ret = b->d_tmp8; s_steps = b->d_tmp4a; s_rules = b->d_tmp4b;
+    }
+    if (last_return) DEV(friqd_d2h_async(last_return, s_ret, 8 * n, stream));
+    if (last_steps) DEV(friqd_d2h_async(last_steps, s_steps, 4 * n, stream));
+    if (rules) DEV(friqd_d2h_async(rules, s_rules, 4 * n, stream));
     DEV(friqd_sync(stream));
     return 0;
 }
@@ -473,6 +536,7 @@ int friq_batch_vag_concl(friq_batch *b, const double *ant, double *conc, int *hi
 {
     const long n = b->st.n; const int K = b->P->hp.K;
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     int rc = percall_buffers(b); if (rc) return rc;
     DEV(friqd_h2d(b->d_in0, ant, 8ul * n * K));
     DEV(friqd_vag_concl(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_out0, b->d_iout, NULL, NULL));
@@ -484,6 +548,7 @@ int friq_batch_vag_concl_weight(friq_batch *b, const double *ant, int *hit, doub
 {
     const long n = b->st.n; const int K = b->P->hp.K;
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     int rc = percall_buffers(b); if (rc) return rc;
     DEV(ensure((void **)&b->d_w, &b->cap_w, 8ul * n * b->st.cap));
     DEV(friqd_memset(b->d_w, 0, 8ul * n * b->st.cap));
@@ -497,6 +562,7 @@ int friq_batch_get_best_action(friq_batch *b, const double *states, double *actc
 {
     const long n = b->st.n; const int S = b->P->hp.S, A = b->P->hp.A;
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     int rc = percall_buffers(b); if (rc) return rc;
     DEV(friqd_h2d(b->d_in0, states, 8ul * n * S));
     DEV(friqd_best_action(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_out0, b->d_iout, NULL));
@@ -508,6 +574,7 @@ int friq_batch_update_sarsa(friq_batch *b, const double *q_ant, const double *re
 {
     const long n = b->st.n; const int K = b->P->hp.K;
     DEV(friqd_set_device(b->device));
+    IDENTITY(b);
     int rc = percall_buffers(b); if (rc) return rc;
     DEV(friqd_h2d(b->d_in0, q_ant, 8ul * n * K)); DEV(friqd_h2d(b->d_in1, reward, 8ul * n)); DEV(friqd_h2d(b->d_in2, cur_q_ant, 8ul * n * K));
     DEV(friqd_update_sarsa(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_in1, b->d_in2, NULL));

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libfriq_b200.so")
 
 ENV_MOUNTAINCAR, ENV_ACROBOT, ENV_CARTPOLE = 0, 1, 2
 ENV_ID = {"mountaincar": 0, "acrobot": 1, "cartpole": 2}
-RUN_LEARN, RUN_TRACK, RUN_STOP_ON_CONVERGE, RUN_STOP_AT_EPISODE_END = 1, 2, 4, 8
+RUN_LEARN, RUN_TRACK, RUN_STOP_ON_CONVERGE, RUN_STOP_AT_EPISODE_END, RUN_RETILE = 1, 2, 4, 8, 16
 F_NEED_RESET, F_INSERTED, F_CONVERGED, F_OVERFLOW = 1, 2, 4, 8
 
 dp = C.POINTER(C.c_double)
@@ -236,7 +236,8 @@ def device_trig(x):
     return s, c
 
 
-def device_pow_x87(x, p, force_exact=False):
+def device_pow_x87(x, p, force_exact=0):
+    """force_exact: 0 filter+fallback pow, 1 integer pow, 2 weight via library ops, 3 weight via fast paths, 4 fallback flags"""
     x = _f64(x); out = np.zeros_like(x)
     _ck(lib().friq_device_pow_x87(_p(x), _p(out), x.size, p, int(force_exact)))
     return out

@@ -33,6 +33,7 @@ extern "C" {
 #define FRIQ_RUN_TRACK_CONVERGENCE 2   /* evaluate the "RB complete" predicate, frirl_sequential_run.c:83-150 */
 #define FRIQ_RUN_STOP_ON_CONVERGE 4    /* converged agents stop stepping */
 #define FRIQ_RUN_STOP_AT_EPISODE_END 8 /* every agent stops after finishing its current episode (frirl_episode granularity) */
+#define FRIQ_RUN_RETILE 16             /* before the launch, re-assign agents to warps by rule count (results unaffected) */
 
 /* One dimension of the problem; field for field struct frirl_dimension_desc
  * (src/frirl/frirl_types.h:34-44).  values / universe may be NULL, in which case

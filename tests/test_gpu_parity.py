@@ -42,6 +42,21 @@ def test_device_pow_x87_fast_and_exact_paths(fq):
         assert np.array_equal(got[:60000], want)       # == x87 long double chain (fast_pow.inl:17-27)
 
 
+def test_branch_free_shepard_weight_equals_library_ops(fq):
+    """1/pow_x87(sqrt(s)) through the branch-free sqrt / pow / rcp fast paths (with their fallback)
+    must equal the composition of __dsqrt_rn, the integer x87 emulation and __drcp_rn, and the
+    fallback must be rare on generic operands."""
+    rng = np.random.default_rng(11)
+    s = np.concatenate([rng.uniform(1e-6, 3000.0, 1500000), 10.0 ** rng.uniform(-12, 8, 500000),
+                        np.float64([1.0, 4.0, 0.25, 2.0, 9.0, 1e-60, 1e60])])
+    for p in (3, 5):
+        lib_w = fq.device_pow_x87(s, p, force_exact=2)
+        fast_w = fq.device_pow_x87(s, p, force_exact=3)
+        assert np.array_equal(lib_w, fast_w)
+        bad = fq.device_pow_x87(s[:2000000], p, force_exact=4)
+        assert (bad != 0).mean() < 0.01
+
+
 def test_device_trig_is_correctly_rounded(fq):
     rng = np.random.default_rng(6)
     x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-4.5, 1.5, 100000)])
@@ -145,8 +160,9 @@ def test_random_exploration_matches_oracle_port(fq, name):
     b = fq.Batch(P, n, CAP[name], seed0=0x5EED0000, first_agent=first)
     b.set_hyper(alpha, gamma, eps)
     steps = 1500 if name == "mountaincar" else 700
-    for chunk in (1, 7, steps - 8):
-        b.run(chunk, fq.RUN_LEARN)
+    for chunk, mode in ((1, fq.RUN_LEARN), (7, fq.RUN_LEARN | fq.RUN_RETILE), (steps - 508, fq.RUN_LEARN),
+                        (250, fq.RUN_LEARN | fq.RUN_RETILE), (250, fq.RUN_LEARN | fq.RUN_RETILE)):
+        b.run(chunk, mode)                              # re-tiling by rule count must not change any agent's results
     o = b.gather()
     OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
     for i in range(n):
@@ -160,6 +176,38 @@ def test_random_exploration_matches_oracle_port(fq, name):
         assert (o["episodes"][i], o["last_steps"][i], o["last_return"][i], o["total_steps"][i], o["sum_rules"][i]) == \
             (s["episode_num"] - 1, s["last_steps"], s["last_return"], s["total_steps"], s["sum_rules"])
     b.close(); P.close()
+
+
+def test_retiled_results_are_reported_in_agent_order(fq):
+    """FRIQ_RUN_RETILE moves agents between warps (sorted by rule count); device-side gathers and the
+    host-buffer end-to-end call must still report per-agent results in agent order."""
+    import ctypes
+    import torch
+    P = fq.Problem("mountaincar", no_random=0)
+    n = 200
+    ref = fq.Batch(P, n, 192); ref.run(1200, fq.RUN_LEARN); want = ref.gather()
+    b = fq.Batch(P, n, 192)
+    for _ in range(4):
+        b.run(300, fq.RUN_LEARN | fq.RUN_RETILE)
+    d_ret = torch.empty(n, dtype=torch.float64, device="cuda"); d_steps = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_rules = torch.empty(n, dtype=torch.int32, device="cuda")
+    b.gather_device(ctypes.c_void_p(d_ret.data_ptr()), ctypes.c_void_p(d_steps.data_ptr()), ctypes.c_void_p(d_rules.data_ptr()))
+    b.sync()
+    assert np.array_equal(d_rules.cpu().numpy(), want["rules"]) and np.array_equal(d_ret.cpu().numpy(), want["last_return"])
+    assert len(set(want["rules"])) > 3                  # the sort key really varies
+    got = b.gather()
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    for agent in (0, 57, n - 1):
+        assert all(np.array_equal(x, y) for x, y in zip(b.get_rulebase(agent), ref.get_rulebase(agent)))
+    # end-to-end call with host buffers after further re-tiled steps
+    ref.run(100, fq.RUN_LEARN); want = ref.gather()
+    h_ret = np.zeros(n); h_steps = np.zeros(n, np.int32); h_rules = np.zeros(n, np.int32)
+    eps = np.full(n, 0.01); alpha = np.full(n, 0.5); gamma = np.ones(n)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    b.run_host(100, fq.RUN_LEARN | fq.RUN_RETILE, vp(alpha), vp(gamma), vp(eps), vp(h_ret), vp(h_steps), vp(h_rules))
+    assert np.array_equal(h_rules, want["rules"]) and np.array_equal(h_ret, want["last_return"]) and np.array_equal(h_steps, want["last_steps"])
+    b.close(); ref.close(); P.close()
 
 
 def test_inference_mode_leaves_rule_base_untouched(fq):
