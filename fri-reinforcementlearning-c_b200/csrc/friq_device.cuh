@@ -138,7 +138,7 @@ __device__ __forceinline__ int friq_vag_concl(const friq_devprob &pb, const uint
 // it re-uses the dictionary loads of the pass and costs ~3(S+1) FP64 ops per rule instead
 // of a second sweep.
 // ---------------------------------------------------------------------------------------
-template <int S, int P, int A, int ACH, bool PIGGY>
+template <int S, int P, int A, int ACH, bool PIGGY, int UNR>
 __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, int R,
                                                       const double *vo_obs, double *actconc, const double *vo_q, int &hitq)
 {
@@ -150,52 +150,69 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
         unsigned hitmask = 0;
 #pragma unroll
         for (int a = 0; a < ACH; a++) { vagc[a] = 0.0; ws[a] = 0.0; hq[a] = 0.0; ave[a] = pb.act_ve[c0 + a]; }
-        uint32_t w = 0; double q = 0.0;
-        if (R > 0) { w = rbw[0]; q = rbq[0]; }
-#pragma unroll 1
-        for (int i = 0; i < R; i++) {
-            uint32_t wn = 0; double qn = 0.0;
-            if (i + 1 < R) { wn = rbw[(size_t)(i + 1) * FRIQ_TILE]; qn = rbq[(size_t)(i + 1) * FRIQ_TILE]; }   // prefetch
-            double ssum = 0.0, sq = 0.0;
+        // UNR rules per trip: UNR * ACH independent sqrt/pow/rcp chains in flight (ILP), accumulated in rule order
+        uint32_t w[UNR]; double q[UNR];
 #pragma unroll
-            for (int k = 0; k < S; k++) {
-                const double v = pb.dict_ve[k][(w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
-                const double d = __dsub_rn(vo_obs[k], v);
-                const double d2 = __dmul_rn(d, d);
-                ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                                  // A3/A4
-                if (PIGGY) {
-                    const double e = __dsub_rn(vo_q[k], v);
-                    const double e2 = __dmul_rn(e, e);
-                    sq = (k == 0) ? e2 : __dadd_rn(sq, e2);
-                }
+        for (int u = 0; u < UNR; u++) { w[u] = 0; q[u] = 0.0; if (u < R) { w[u] = rbw[(size_t)u * FRIQ_TILE]; q[u] = rbq[(size_t)u * FRIQ_TILE]; } }
+#pragma unroll 1
+        for (int i = 0; i < R; i += UNR) {
+            uint32_t wn[UNR]; double qn[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {                                                   // prefetch the next trip
+                wn[u] = 0; qn[u] = 0.0;
+                if (i + UNR + u < R) { wn[u] = rbw[(size_t)(i + UNR + u) * FRIQ_TILE]; qn[u] = rbq[(size_t)(i + UNR + u) * FRIQ_TILE]; }
             }
-            const double va = pb.dict_ve[S][(w >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)];
-            if (PIGGY) {
-                if (c0 == 0) {
-                    const double e = __dsub_rn(vo_q[S], va);
-                    sq = __dadd_rn(sq, __dmul_rn(e, e));
-                    if (sq == 0.0 && hitq < 0) hitq = i;
-                }
-            }
-            double sa[ACH], wv[ACH];
+            double sa[UNR][ACH], wv[UNR][ACH];
             unsigned bad = 0;
 #pragma unroll
-            for (int a = 0; a < ACH; a++) {
-                const double da = __dsub_rn(ave[a], va);
-                sa[a] = __dadd_rn(__dmul_rn(da, da), ssum);                                  // A5
-                wv[a] = friq_shepard_weight_fast<P>(sa[a] == 0.0 ? 1.0 : sa[a], bad);
-            }
-            if (bad) {                                   // rare: operand outside the proven fast paths
+            for (int u = 0; u < UNR; u++) {
+                double ssum = 0.0, sq = 0.0;
 #pragma unroll
-                for (int a = 0; a < ACH; a++) wv[a] = friq_shepard_weight<P>(sa[a] == 0.0 ? 1.0 : sa[a]);
+                for (int k = 0; k < S; k++) {
+                    const double v = pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+                    const double d = __dsub_rn(vo_obs[k], v);
+                    const double d2 = __dmul_rn(d, d);
+                    ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                              // A3/A4
+                    if (PIGGY) {
+                        const double e = __dsub_rn(vo_q[k], v);
+                        const double e2 = __dmul_rn(e, e);
+                        sq = (k == 0) ? e2 : __dadd_rn(sq, e2);
+                    }
+                }
+                const double va = pb.dict_ve[S][(w[u] >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)];
+                if (PIGGY) {
+                    if (c0 == 0) {
+                        const double e = __dsub_rn(vo_q[S], va);
+                        sq = __dadd_rn(sq, __dmul_rn(e, e));
+                        if (sq == 0.0 && hitq < 0 && i + u < R) hitq = i + u;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < ACH; a++) {
+                    const double da = __dsub_rn(ave[a], va);
+                    sa[u][a] = __dadd_rn(__dmul_rn(da, da), ssum);                           // A5
+                    wv[u][a] = friq_shepard_weight_fast<P>(sa[u][a] == 0.0 ? 1.0 : sa[u][a], bad);
+                }
+            }
+            if (bad) {                                   // rare: an operand outside the proven fast paths
+#pragma unroll
+                for (int u = 0; u < UNR; u++)
+#pragma unroll
+                    for (int a = 0; a < ACH; a++) wv[u][a] = friq_shepard_weight<P>(sa[u][a] == 0.0 ? 1.0 : sa[u][a]);
             }
 #pragma unroll
-            for (int a = 0; a < ACH; a++) {
-                if (sa[a] == 0.0 && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q; }   // BestAct.c:89-93
-                vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[a], q));                            // BestAct.c:216
-                ws[a] = __dadd_rn(ws[a], wv[a]);                                              // :217
+            for (int u = 0; u < UNR; u++) {
+                if (u == 0 || i + u < R) {
+#pragma unroll
+                    for (int a = 0; a < ACH; a++) {
+                        if (sa[u][a] == 0.0 && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q[u]; }   // BestAct.c:89-93
+                        vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u][a], q[u]));              // BestAct.c:216
+                        ws[a] = __dadd_rn(ws[a], wv[u][a]);                                   // :217
+                    }
+                }
             }
-            w = wn; q = qn;
+#pragma unroll
+            for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
         }
 #pragma unroll
         for (int a = 0; a < ACH; a++)

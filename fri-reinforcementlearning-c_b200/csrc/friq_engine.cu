@@ -35,8 +35,8 @@ struct __align__(16) friq_smem_t {
     double *sw = st.sw + tile_off;
 
 // ---------------------------------------------------------------------------------------
-template <int S, int P, int A, int ACH, int ENV>
-__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+template <int S, int P, int A, int ACH, int ENV, int UNR>
+__global__ void __launch_bounds__(FRIQ_BLOCK, UNR > 1 ? 4 : 8)
 k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
 {
     constexpr int K = S + 1;
@@ -90,7 +90,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         }
         // best action at the new observation (+ exact-hit scan of Q(s,a) for the update)
         double actconc[A]; int hitq;
-        friq_best_action_pass<S, P, A, ACH, true>(pb, rbw, rbq, act ? R : 0, vc, actconc, vo, hitq);
+        friq_best_action_pass<S, P, A, ACH, true, UNR>(pb, rbw, rbq, act ? R : 0, vc, actconc, vo, hitq);
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; }
         if (act && !initial) {
@@ -175,7 +175,7 @@ k_best_action(const friq_devprob *__restrict__ gprob, friq_devstate st, const do
 #pragma unroll
     for (int k = 0; k < S; k++) vo[k] = friq_obs_ve(pb, k, states[(size_t)ag * S + k]);    // get_best_action.c:60-63
     int hq;
-    friq_best_action_pass<S, P, A, ACH, false>(pb, rbw, rbq, st.R[ag], vo, actconc, nullptr, hq);
+    friq_best_action_pass<S, P, A, ACH, false, 1>(pb, rbw, rbq, st.R[ag], vo, actconc, nullptr, hq);
 #pragma unroll
     for (int a = 0; a < A; a++) actconc_out[(size_t)ag * A + a] = actconc[a];
     best[ag] = friq_argmax<A>(actconc);
@@ -406,9 +406,9 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
 int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, void *stream)
 {
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
-    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) k_run_steps<4, 5, 21, 7, FRIQ_ENV_CARTPOLE><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) k_run_steps<4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -431,7 +431,7 @@ int friqd_best_action(const friq_devprob *hp, const friq_devprob *dprob, friq_de
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
     if (FRIQ_SHAPE_MC(hp)) k_best_action<2, 3, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else if (FRIQ_SHAPE_AC(hp)) k_best_action<4, 5, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
-    else if (FRIQ_SHAPE_CP(hp)) k_best_action<4, 5, 21, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (FRIQ_SHAPE_CP(hp)) k_best_action<4, 5, 21, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
