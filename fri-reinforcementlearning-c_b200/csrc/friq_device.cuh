@@ -132,25 +132,35 @@ __device__ __forceinline__ int friq_vag_concl(const friq_devprob &pb, const uint
 
 // ---------------------------------------------------------------------------------------
 // frirl_get_best_action (frirl_get_best_action.c:31-341) + FIVEVagConcl_FRIRL_BestAct
-// (:56-301), all A actions in one pass over the rule base (ACH actions per pass when A is
-// large).  With PIGGY the same pass also finds the first rule at distance 0 from the
-// previous step's antecedents vo_q[] (the exact-hit test of Q(s,a) in frirl_update_sarsa):
-// it re-uses the dictionary loads of the pass and costs ~3(S+1) FP64 ops per rule instead
-// of a second sweep.
+// (:56-301): all A actions in one pass over the rule base (ACH actions per sweep when A is
+// large), UNR rules per trip, i.e. UNR * ACH independent sqrt / pow / rcp chains in flight;
+// the sums are still accumulated strictly in rule order.
+//   hidx[a]  first rule at distance 0 from (observation, action a), or -1 (BestAct.c:89-93).
+//            Because best action and FIVE_vag_concl see the same VE values (qp_reuse), hidx[a']
+//            is also the exact-hit rule of Q(s',a') - the next step's Q(s,a) - so the step
+//            kernel never needs a separate exact-hit scan.
+//   WITHQ    additionally evaluates the Shepard sums of Q(s,a) at the previous antecedents
+//            vo_q[] (FIVEVagConcl.c:224-235) as one more chain for the lanes with needq set,
+//            keeping the weights wi in sw[] for the weighted update.
 // ---------------------------------------------------------------------------------------
-template <int S, int P, int A, int ACH, bool PIGGY, int UNR>
-__device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, int R,
-                                                      const double *vo_obs, double *actconc, const double *vo_q, int &hitq)
+__device__ __forceinline__ bool friq_is_zero(double x)      // x == 0.0 for x >= +0, on the integer pipe
+{
+    return ((unsigned)__double2hiint(x) | (unsigned)__double2loint(x)) == 0u;
+}
+
+template <int S, int P, int A, int ACH, bool WITHQ, int UNR>
+__device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
+                                                      const double *vo_obs, double *actconc, int *hidx,
+                                                      const double *vo_q, bool needq, double &vagq, double &wsq)
 {
     static_assert(A % ACH == 0, "action chunking");
-    hitq = -1;
+    vagq = 0.0; wsq = 0.0;
 #pragma unroll 1
     for (int c0 = 0; c0 < A; c0 += ACH) {
-        double vagc[ACH], ws[ACH], hq[ACH], ave[ACH];
-        unsigned hitmask = 0;
+        double vagc[ACH], ws[ACH], ave[ACH];
+        int hi[ACH];
 #pragma unroll
-        for (int a = 0; a < ACH; a++) { vagc[a] = 0.0; ws[a] = 0.0; hq[a] = 0.0; ave[a] = pb.act_ve[c0 + a]; }
-        // UNR rules per trip: UNR * ACH independent sqrt/pow/rcp chains in flight (ILP), accumulated in rule order
+        for (int a = 0; a < ACH; a++) { vagc[a] = 0.0; ws[a] = 0.0; hi[a] = -1; ave[a] = pb.act_ve[c0 + a]; }
         uint32_t w[UNR]; double q[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) { w[u] = 0; q[u] = 0.0; if (u < R) { w[u] = rbw[(size_t)u * FRIQ_TILE]; q[u] = rbq[(size_t)u * FRIQ_TILE]; } }
@@ -162,7 +172,8 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
                 wn[u] = 0; qn[u] = 0.0;
                 if (i + UNR + u < R) { wn[u] = rbw[(size_t)(i + UNR + u) * FRIQ_TILE]; qn[u] = rbq[(size_t)(i + UNR + u) * FRIQ_TILE]; }
             }
-            double sa[UNR][ACH], wv[UNR][ACH];
+            double wv[UNR][ACH], wq[UNR];
+            bool z[UNR][ACH];
             unsigned bad = 0;
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
@@ -173,41 +184,71 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
                     const double d = __dsub_rn(vo_obs[k], v);
                     const double d2 = __dmul_rn(d, d);
                     ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                              // A3/A4
-                    if (PIGGY) {
+                    if (WITHQ) {
                         const double e = __dsub_rn(vo_q[k], v);
                         const double e2 = __dmul_rn(e, e);
                         sq = (k == 0) ? e2 : __dadd_rn(sq, e2);
                     }
                 }
                 const double va = pb.dict_ve[S][(w[u] >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)];
-                if (PIGGY) {
-                    if (c0 == 0) {
-                        const double e = __dsub_rn(vo_q[S], va);
-                        sq = __dadd_rn(sq, __dmul_rn(e, e));
-                        if (sq == 0.0 && hitq < 0 && i + u < R) hitq = i + u;
-                    }
-                }
 #pragma unroll
                 for (int a = 0; a < ACH; a++) {
                     const double da = __dsub_rn(ave[a], va);
-                    sa[u][a] = __dadd_rn(__dmul_rn(da, da), ssum);                           // A5
-                    wv[u][a] = friq_shepard_weight_fast<P>(sa[u][a] == 0.0 ? 1.0 : sa[u][a], bad);
+                    const double s = __dadd_rn(__dmul_rn(da, da), ssum);                     // A5
+                    z[u][a] = friq_is_zero(s);
+                    wv[u][a] = friq_shepard_weight_fast<P>(z[u][a] ? 1.0 : s, bad);
+                }
+                if (WITHQ) {
+                    if (c0 == 0) {
+                        const double e = __dsub_rn(vo_q[S], va);
+                        sq = __dadd_rn(sq, __dmul_rn(e, e));
+                        wq[u] = friq_shepard_weight_fast<P>((friq_is_zero(sq) || !needq) ? 1.0 : sq, bad);
+                    }
                 }
             }
-            if (bad) {                                   // rare: an operand outside the proven fast paths
+            if (bad) {                                   // rare: an operand outside the proven fast paths -> library routines
 #pragma unroll
-                for (int u = 0; u < UNR; u++)
+                for (int u = 0; u < UNR; u++) {
+                    double v[S + 1];
 #pragma unroll
-                    for (int a = 0; a < ACH; a++) wv[u][a] = friq_shepard_weight<P>(sa[u][a] == 0.0 ? 1.0 : sa[u][a]);
+                    for (int k = 0; k <= S; k++) v[k] = pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+                    double ssum = 0.0, sq = 0.0;
+#pragma unroll
+                    for (int k = 0; k < S; k++) {
+                        const double d = __dsub_rn(vo_obs[k], v[k]);
+                        ssum = (k == 0) ? __dmul_rn(d, d) : __dadd_rn(ssum, __dmul_rn(d, d));
+                        if (WITHQ) { const double e = __dsub_rn(vo_q[k], v[k]); sq = (k == 0) ? __dmul_rn(e, e) : __dadd_rn(sq, __dmul_rn(e, e)); }
+                    }
+#pragma unroll
+                    for (int a = 0; a < ACH; a++) {
+                        const double da = __dsub_rn(ave[a], v[S]);
+                        const double s = __dadd_rn(__dmul_rn(da, da), ssum);
+                        wv[u][a] = friq_shepard_weight<P>(z[u][a] ? 1.0 : s);
+                    }
+                    if (WITHQ) {
+                        if (c0 == 0) {
+                            const double e = __dsub_rn(vo_q[S], v[S]);
+                            sq = __dadd_rn(sq, __dmul_rn(e, e));
+                            wq[u] = friq_shepard_weight<P>((friq_is_zero(sq) || !needq) ? 1.0 : sq);
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
                 if (u == 0 || i + u < R) {
 #pragma unroll
                     for (int a = 0; a < ACH; a++) {
-                        if (sa[u][a] == 0.0 && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q[u]; }   // BestAct.c:89-93
+                        if (z[u][a] && hi[a] < 0) hi[a] = i + u;                              // BestAct.c:89-93
                         vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u][a], q[u]));              // BestAct.c:216
                         ws[a] = __dadd_rn(ws[a], wv[u][a]);                                   // :217
+                    }
+                    if (WITHQ) {
+                        if (c0 == 0) {
+                            if (needq) sw[(size_t)(i + u) * FRIQ_TILE] = wq[u];
+                            vagq = __dadd_rn(vagq, __dmul_rn(wq[u], q[u]));                   // FIVEVagConcl.c:234
+                            wsq = __dadd_rn(wsq, wq[u]);                                      // :235
+                        }
                     }
                 }
             }
@@ -215,8 +256,10 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
             for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
         }
 #pragma unroll
-        for (int a = 0; a < ACH; a++)
-            actconc[c0 + a] = ((hitmask >> a) & 1u) ? hq[a] : __ddiv_rn(vagc[a], ws[a]);      // :265
+        for (int a = 0; a < ACH; a++) {
+            hidx[c0 + a] = hi[a];
+            actconc[c0 + a] = (hi[a] >= 0) ? rbq[(size_t)hi[a] * FRIQ_TILE] : __ddiv_rn(vagc[a], ws[a]);   // :265
+        }
     }
 }
 
@@ -233,6 +276,15 @@ template <int A>
 __device__ __forceinline__ double friq_pick(const double *v, int idx)
 {
     double r = v[0];
+#pragma unroll
+    for (int i = 1; i < A; i++) if (i == idx) r = v[i];
+    return r;
+}
+
+template <int A>
+__device__ __forceinline__ int friq_pick_int(const int *v, int idx)
+{
+    int r = v[0];
 #pragma unroll
     for (int i = 1; i < A; i++) if (i == idx) r = v[i];
     return r;

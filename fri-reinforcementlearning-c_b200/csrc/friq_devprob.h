@@ -76,6 +76,7 @@ typedef struct friq_devstate {
     double *ep_return, *last_return, *prev_reward;
     unsigned long long *total_steps, *sum_rules, *seed;
     double *alpha, *gamma, *epsilon;
+    int *hitq;                  /* [n_pad] exact-hit rule of Q(s,a) for the pending update, -1 none, -2 unknown */
     int *agent_of_slot;         /* [n_pad] which agent lives in slot p (identity unless re-tiled by rule count) */
 } friq_devstate;
 

@@ -49,7 +49,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ag];
 #pragma unroll
     for (int k = 0; k < K; k++) { qs[k] = st.qs[(size_t)k * st.n_pad + ag]; vo[k] = st.vo[(size_t)k * st.n_pad + ag]; }
-    int aidx = st.aidx[ag], flags = st.flags[ag], R = st.R[ag], step_in_ep = st.step_in_ep[ag];
+    int aidx = st.aidx[ag], flags = st.flags[ag], R = st.R[ag], step_in_ep = st.step_in_ep[ag], hitq = st.hitq[ag];
     uint32_t ep_num = st.ep_num[ag];
     double ep_return = st.ep_return[ag];
     double prev_reward = st.prev_reward[ag]; int prev_steps = st.prev_steps[ag], prev_numru = st.prev_numru[ag];
@@ -88,11 +88,20 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             for (int k = 0; k < S; k++) { cur[k] = s[k]; cq[k] = qs[k]; vc[k] = vo[k]; }
             running = false;
         }
-        // best action at the new observation (+ exact-hit scan of Q(s,a) for the update)
-        double actconc[A]; int hitq;
-        friq_best_action_pass<S, P, A, ACH, true, UNR>(pb, rbw, rbq, act ? R : 0, vc, actconc, vo, hitq);
+        // Q(s,a) of the pending update: its exact-hit rule is known from the previous pass (hitq >= 0), or
+        // there is none (-1) and its Shepard sums ride along in this pass as one more chain.  -2 = unknown
+        // (state set through the per-call API, or act_ve != act_ve_eval): scan for it.
+        const bool upd = act && !initial && learn;
+        if (upd && (hitq == -2 || !pb.qp_reuse)) hitq = friq_first_hit<K>(pb, rbw, R, vo);
+        const bool needq = upd && hitq < 0;
+        double actconc[A], vagq, wsq; int hidx[A];
+        if (__any_sync(wmask, needq))
+            friq_best_action_pass<S, P, A, ACH, true, UNR>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, needq, vagq, wsq);
+        else
+            friq_best_action_pass<S, P, A, ACH, false, UNR>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, false, vagq, wsq);
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
-        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; }
+        const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
+        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; hitq = next_hit; }
         if (act && !initial) {
             sum_rules += (unsigned long long)R;
             if (learn) {                                 // frirl_update_sarsa.c:348-385
@@ -106,9 +115,18 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                     friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vq, qp, wsd);
                 }
                 if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
-                else { double vagc; friq_shepard<K, P>(pb, rbw, rbq, sw, R, vo, vagc, ws); qnow = __ddiv_rn(vagc, ws); }
+                else { ws = wsq; qnow = __ddiv_rn(vagq, wsq); }                               // FIVEVagConcl.c:302
+                const int R0 = R;
                 friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward, qp, hitq, qnow, ws, alpha, gamma);
-            }
+                hitq = next_hit;
+                if (R > R0 && hitq == -1) {              // a rule was appended: is it at the next step's (s,a)?
+                    const uint32_t wnew = rbw[(size_t)R0 * FRIQ_TILE];
+                    bool same = pb.dict_ve[S][(wnew >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)] == pb.act_ve_eval[a2];
+#pragma unroll
+                    for (int k = 0; k < S; k++) same = same && (pb.dict_ve[k][(wnew >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)] == vc[k]);
+                    if (same) hitq = R0;
+                }
+            } else hitq = next_hit;
             // frirl_episode.c:163-185
 #pragma unroll
             for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; }
@@ -137,7 +155,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
 #pragma unroll
     for (int k = 0; k < K; k++) { st.qs[(size_t)k * st.n_pad + ag] = qs[k]; st.vo[(size_t)k * st.n_pad + ag] = vo[k]; }
-    st.aidx[ag] = aidx; st.flags[ag] = flags; st.R[ag] = R; st.step_in_ep[ag] = step_in_ep;
+    st.aidx[ag] = aidx; st.flags[ag] = flags; st.R[ag] = R; st.step_in_ep[ag] = step_in_ep; st.hitq[ag] = hitq;
     st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
     st.prev_reward[ag] = prev_reward; st.prev_steps[ag] = prev_steps; st.prev_numru[ag] = prev_numru;
     st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
@@ -174,8 +192,8 @@ k_best_action(const friq_devprob *__restrict__ gprob, friq_devstate st, const do
     double vo[S], actconc[A];
 #pragma unroll
     for (int k = 0; k < S; k++) vo[k] = friq_obs_ve(pb, k, states[(size_t)ag * S + k]);    // get_best_action.c:60-63
-    int hq;
-    friq_best_action_pass<S, P, A, ACH, false, 1>(pb, rbw, rbq, st.R[ag], vo, actconc, nullptr, hq);
+    int hidx[A]; double vagq, wsq;
+    friq_best_action_pass<S, P, A, ACH, false, 1>(pb, rbw, rbq, nullptr, st.R[ag], vo, actconc, hidx, vo, false, vagq, wsq);
 #pragma unroll
     for (int a = 0; a < A; a++) actconc_out[(size_t)ag * A + a] = actconc[a];
     best[ag] = friq_argmax<A>(actconc);
@@ -200,7 +218,7 @@ k_update_sarsa(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
     friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vc, qp, wsp);                 // :355
     const int hitq = friq_vag_concl<K, P>(pb, rbw, rbq, sw, R, vq, qnow, ws);    // :356
     friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward[ag], qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
-    st.R[ag] = R; st.flags[ag] = flags;
+    st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
 }
 
 __global__ void k_init_agents(const friq_devprob *__restrict__ gprob, friq_devstate st, unsigned long long seed0, long first_agent,
@@ -218,7 +236,7 @@ __global__ void k_init_agents(const friq_devprob *__restrict__ gprob, friq_devst
     st.total_steps[ag] = 0ull; st.sum_rules[ag] = 0ull;
     st.seed[ag] = seed0 + (unsigned long long)(first_agent + ag);
     st.alpha[ag] = alpha; st.gamma[ag] = gamma; st.epsilon[ag] = epsilon;
-    st.agent_of_slot[ag] = (int)ag;
+    st.agent_of_slot[ag] = (int)ag; st.hitq[ag] = -2;
 }
 
 __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict__ words, const double *__restrict__ q, int R)
@@ -227,7 +245,7 @@ __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict_
     if (ag >= st.n) return;
     const size_t tile_off = (size_t)(ag >> 5) * st.cap * FRIQ_TILE + (ag & 31);
     for (int i = 0; i < R; i++) { st.rbw[tile_off + (size_t)i * FRIQ_TILE] = words[i]; st.rbq[tile_off + (size_t)i * FRIQ_TILE] = q[i]; }
-    st.R[ag] = R;
+    st.R[ag] = R; st.hitq[ag] = -2;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -270,7 +288,7 @@ __global__ void k_retile_move(friq_devstate a, friq_devstate b, const int *work)
     b.ep_num[q] = a.ep_num[p]; b.ep_return[q] = a.ep_return[p]; b.last_return[q] = a.last_return[p]; b.prev_reward[q] = a.prev_reward[p];
     b.total_steps[q] = a.total_steps[p]; b.sum_rules[q] = a.sum_rules[p]; b.seed[q] = a.seed[p];
     b.alpha[q] = a.alpha[p]; b.gamma[q] = a.gamma[p]; b.epsilon[q] = a.epsilon[p];
-    b.agent_of_slot[q] = a.agent_of_slot[p];
+    b.agent_of_slot[q] = a.agent_of_slot[p]; b.hitq[q] = a.hitq[p];
     const size_t po = (size_t)(p >> 5) * a.cap * FRIQ_TILE + (p & 31), qo = (size_t)(q >> 5) * b.cap * FRIQ_TILE + (q & 31);
     const int R = a.R[p];
     for (int i = 0; i < R; i++) {

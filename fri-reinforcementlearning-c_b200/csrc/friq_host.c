@@ -258,11 +258,11 @@ int friq_problem_tables(const friq_problem *P, double *u, double *ve, double *ud
 int friq_device_count(int *count) { DEV(friqd_device_count(count)); return 0; }
 
 /* device buffers of one placement: rule bases + one slab for the per-agent scalars
- * (3*MAXK + 9 rows of 8 bytes, 11 rows of 4 bytes) */
+ * (3*MAXK + 9 rows of 8 bytes, 12 rows of 4 bytes) */
 static int alloc_state(friq_devstate *st, int clear)
 {
     const size_t slots = (size_t)st->n_pad * st->cap, np = (size_t)st->n_pad;
-    const size_t rows8 = 3 * FRIQ_MAXK + 9, rows4 = 11;
+    const size_t rows8 = 3 * FRIQ_MAXK + 9, rows4 = 12;
     void *slab;
     DEV(friqd_malloc((void **)&st->rbw, slots * 4)); DEV(friqd_malloc((void **)&st->rbq, slots * 8));
     DEV(friqd_malloc(&slab, np * (rows8 * 8 + rows4 * 4)));
@@ -276,7 +276,7 @@ static int alloc_state(friq_devstate *st, int clear)
     int *p4 = (int *)p8;
     st->aidx = p4; p4 += np; st->flags = p4; p4 += np; st->R = p4; p4 += np; st->step_in_ep = p4; p4 += np;
     st->last_steps = p4; p4 += np; st->last_rules = p4; p4 += np; st->prev_steps = p4; p4 += np; st->prev_numru = p4; p4 += np;
-    st->ep_num = (unsigned int *)p4; p4 += np; st->agent_of_slot = p4; p4 += np;
+    st->ep_num = (unsigned int *)p4; p4 += np; st->agent_of_slot = p4; p4 += np; st->hitq = p4; p4 += np;
     return 0;
 }
 static void free_state(friq_devstate *st)
@@ -381,6 +381,7 @@ int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant
             DEV(friqd_h2d_2d(b->st.rbq + off, FRIQ_TILE * 8, rconc, 8, 8, R));
         }
         DEV(friqd_h2d(b->st.R + agent, &R, sizeof(int)));
+        { const int unknown = -2; DEV(friqd_h2d(b->st.hitq + agent, &unknown, sizeof(int))); }
     } else {
         unsigned int *dw; double *dq;
         DEV(friqd_malloc((void **)&dw, 4 * (R + 1))); DEV(friqd_malloc((void **)&dq, 8 * (R + 1)));
