@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--agents", type=int, default=65536, help="agents per GPU")
     ap.add_argument("--chunk", type=int, default=250, help="env steps per agent per bench step (one kernel launch)")
+    ap.add_argument("--retile", type=int, default=100, help="env steps between re-tilings by rule count inside a step (0 = once per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -144,6 +145,8 @@ def main():
 
     P = fq.Problem("mountaincar", no_random=0)
     b = fq.Batch(P, n, 192, device=local, seed0=0x5EED0000, first_agent=rank * n)
+    b.set_retile_interval(args.retile)
+    launches_per_step = (-(-args.chunk // args.retile) if args.retile > 0 else 1)
     mode = fq.RUN_LEARN | fq.RUN_RETILE      # agents are re-assigned to warps by rule count before every launch
 
     # device-side result buffers for the NCCL gather of per-agent (return f64, steps i32, rules i32)
@@ -235,13 +238,13 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "agents_per_gpu": n, "env_steps_per_agent_per_step": args.chunk,
-                   "rule_capacity": 192, "mean_rules_in_timed_region": sumR / max(nsteps, 1),
+                   "rule_capacity": 192, "retile_interval_steps": args.retile, "mean_rules_in_timed_region": sumR / max(nsteps, 1),
                    "l2": "inputs larger than L2: rule bases + scratch = %.0f MB per GPU" % (n * 192 * 20 / 1e6),
                    "rng": "Philox4x32-10, key = 0x5EED0000 + agent id"},
         "five_evals_per_sec": value * EVALS_PER_STEP,
         "e2e": {"value": nsteps_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 16 * n,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": args.steps * 8,   # per step: 4 re-tiling kernels + k_run_steps + 3 result un-permute kernels
+        "gpu_launches": args.steps * (5 * launches_per_step + 3),   # per launch: 4 re-tiling kernels + k_run_steps; per step: 3 result un-permute kernels
         
         "clocks": clocks,
         "roofline": {"bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",

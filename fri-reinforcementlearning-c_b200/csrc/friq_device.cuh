@@ -84,11 +84,11 @@ __device__ __forceinline__ double friq_shepard_weight(double s)
     return __drcp_rn(friq_pow_x87<P>(d));                 // 1.0 / fast_pow(|d|, p)
 }
 // same value, branch-free; bad != 0 => not proven, recompute with friq_shepard_weight
-template <int P>
-__device__ __forceinline__ double friq_shepard_weight_fast(double s, unsigned &bad)
+template <int P, bool SAFE>
+__device__ __forceinline__ double friq_shepard_weight_fast(double s, unsigned &bad, bool live = true)
 {
-    const double d = friq_sqrt_fast(s, bad);
-    return friq_rcp_fast(friq_pow_x87_fast<P>(d, bad), bad);
+    const double d = friq_sqrt_fast<SAFE>(s, bad, live);
+    return friq_rcp_fast<SAFE>(friq_pow_x87_fast<P>(d, bad, live), bad, live);
 }
 
 // first rule whose distance from vo[] (all K dims) is exactly 0, else -1
@@ -148,7 +148,7 @@ __device__ __forceinline__ bool friq_is_zero(double x)      // x == 0.0 for x >=
     return ((unsigned)__double2hiint(x) | (unsigned)__double2loint(x)) == 0u;
 }
 
-template <int S, int P, int A, int ACH, bool WITHQ, int UNR>
+template <int S, int P, int A, int ACH, bool WITHQ, int UNR, bool SAFE>
 __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
                                                       const double *vo_obs, double *actconc, int *hidx,
                                                       const double *vo_q, bool needq, double &vagq, double &wsq)
@@ -196,13 +196,13 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
                     const double da = __dsub_rn(ave[a], va);
                     const double s = __dadd_rn(__dmul_rn(da, da), ssum);                     // A5
                     z[u][a] = friq_is_zero(s);
-                    wv[u][a] = friq_shepard_weight_fast<P>(z[u][a] ? 1.0 : s, bad);
+                    wv[u][a] = friq_shepard_weight_fast<P, SAFE>(s, bad, !z[u][a]);             // NaN when s == 0: discarded
                 }
                 if (WITHQ) {
                     if (c0 == 0) {
                         const double e = __dsub_rn(vo_q[S], va);
                         sq = __dadd_rn(sq, __dmul_rn(e, e));
-                        wq[u] = friq_shepard_weight_fast<P>((friq_is_zero(sq) || !needq) ? 1.0 : sq, bad);
+                        wq[u] = friq_shepard_weight_fast<P, SAFE>(sq, bad, needq && !friq_is_zero(sq));
                     }
                 }
             }

@@ -40,6 +40,7 @@ enum { FRIQ_M_LEARN = 1, FRIQ_M_TRACK = 2, FRIQ_M_STOP_ON_CONVERGE = 4, FRIQ_M_S
 typedef struct friq_devprob {
     int S, K, A, U, p, env, skip_rules, no_random;
     int max_steps, max_episodes, qp_reuse, ncorner;
+    int safe_range, pad1, pad2, pad3;         /* all squared distances in {0} U [2^-200, 2^200] (host-verified) */
     int grid_len[FRIQ_MAXK];
     int dict_len[FRIQ_MAXK];
     int act_dict[FRIQ_MAXA];                  /* dictionary index (dimension S) of action a */

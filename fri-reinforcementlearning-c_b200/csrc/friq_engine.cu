@@ -16,7 +16,12 @@
 #include <stdio.h>
 #include "friq_device.cuh"
 
-#define FRIQ_BLOCK 64
+#ifndef FRIQ_BLOCK
+#define FRIQ_BLOCK 128
+#endif
+#ifndef FRIQ_MINB
+#define FRIQ_MINB 2
+#endif
 
 struct __align__(16) friq_smem_t {
     unsigned char prob[FRIQ_DEVPROB_SMEM_BYTES];
@@ -35,8 +40,8 @@ struct __align__(16) friq_smem_t {
     double *sw = st.sw + tile_off;
 
 // ---------------------------------------------------------------------------------------
-template <int S, int P, int A, int ACH, int ENV, int UNR>
-__global__ void __launch_bounds__(FRIQ_BLOCK, UNR > 1 ? 4 : 8)
+template <int S, int P, int A, int ACH, int ENV, int UNR, bool SAFE>
+__global__ void __launch_bounds__(FRIQ_BLOCK, UNR > 1 ? FRIQ_MINB : (512 / FRIQ_BLOCK))
 k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
 {
     constexpr int K = S + 1;
@@ -96,9 +101,9 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         const bool needq = upd && hitq < 0;
         double actconc[A], vagq, wsq; int hidx[A];
         if (__any_sync(wmask, needq))
-            friq_best_action_pass<S, P, A, ACH, true, UNR>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, needq, vagq, wsq);
+            friq_best_action_pass<S, P, A, ACH, true, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, needq, vagq, wsq);
         else
-            friq_best_action_pass<S, P, A, ACH, false, UNR>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, false, vagq, wsq);
+            friq_best_action_pass<S, P, A, ACH, false, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, false, vagq, wsq);
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; hitq = next_hit; }
@@ -166,7 +171,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 // per-call kernels
 // ---------------------------------------------------------------------------------------
 template <int S, int P>
-__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
 k_vag_concl(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ ant, double *conc, int *hit, double *weights)
 {
     constexpr int K = S + 1;
@@ -184,7 +189,7 @@ k_vag_concl(const friq_devprob *__restrict__ gprob, friq_devstate st, const doub
 }
 
 template <int S, int P, int A, int ACH>
-__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
 k_best_action(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ states, double *actconc_out, int *best)
 {
     FRIQ_SMEM_PROLOGUE();
@@ -193,14 +198,14 @@ k_best_action(const friq_devprob *__restrict__ gprob, friq_devstate st, const do
 #pragma unroll
     for (int k = 0; k < S; k++) vo[k] = friq_obs_ve(pb, k, states[(size_t)ag * S + k]);    // get_best_action.c:60-63
     int hidx[A]; double vagq, wsq;
-    friq_best_action_pass<S, P, A, ACH, false, 1>(pb, rbw, rbq, nullptr, st.R[ag], vo, actconc, hidx, vo, false, vagq, wsq);
+    friq_best_action_pass<S, P, A, ACH, false, 1, false>(pb, rbw, rbq, nullptr, st.R[ag], vo, actconc, hidx, vo, false, vagq, wsq);
 #pragma unroll
     for (int a = 0; a < A; a++) actconc_out[(size_t)ag * A + a] = actconc[a];
     best[ag] = friq_argmax<A>(actconc);
 }
 
 template <int S, int P>
-__global__ void __launch_bounds__(FRIQ_BLOCK, 8)
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
 k_update_sarsa(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ qant, const double *__restrict__ reward,
                const double *__restrict__ curqant)
 {
@@ -320,7 +325,7 @@ __global__ void k_pow(const double *x, double *out, long n, int p, int force_exa
         unsigned bad = 0; double w;
         if (force_exact == 2) w = __drcp_rn(friq_pow_x87_exact(__dsqrt_rn(x[i]), p));
         else {
-            w = (p == 3) ? friq_shepard_weight_fast<3>(x[i], bad) : friq_shepard_weight_fast<5>(x[i], bad);
+            w = (p == 3) ? friq_shepard_weight_fast<3, false>(x[i], bad) : friq_shepard_weight_fast<5, false>(x[i], bad);
             if (bad) w = (p == 3) ? friq_shepard_weight<3>(x[i]) : friq_shepard_weight<5>(x[i]);
             if (force_exact == 4) w = (double)bad;
         }
@@ -424,9 +429,14 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
 int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, void *stream)
 {
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
-    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) k_run_steps<4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+#define FRIQ_LAUNCH_STEP(S_, P_, A_, ACH_, ENV_, UNR_)                                                                   \
+    do {                                                                                                              \
+        if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
+        else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
+    } while (0)
+    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_STEP(2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 2);
+    else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_STEP(4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2);
+    else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) FRIQ_LAUNCH_STEP(4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;

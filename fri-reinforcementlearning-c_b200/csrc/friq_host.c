@@ -38,6 +38,7 @@ struct friq_batch {
     friq_devstate st;         /* current placement */
     friq_devstate st2;        /* alternate buffers used by re-tiling (allocated on first use) */
     int have_st2, permuted;
+    long retile_interval;     /* env steps between re-tilings inside one friq_batch_run (FRIQ_RUN_RETILE) */
     int *d_work;              /* re-tiling scratch */
     void *d_tmp8, *d_tmp4a, *d_tmp4b;   /* un-permuted result staging */
     int device;
@@ -200,6 +201,24 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
         hp->act_ve_eval[a] = vea[nearest_index(ua, U, U, hp->udiv[S], hp->act_val[a])];
         if (hp->act_ve[a] != hp->act_ve_eval[a]) hp->qp_reuse = 0;
     }
+    /* every squared scaled distance the kernels can meet is a sum over dimensions of (VE_k[i] - VE_k[j])^2 */
+    {
+        double smin = INFINITY, smax = 0.0;
+        for (int k = 0; k < K; k++) {
+            const double *ve = P->ve + (size_t)k * U;
+            double lo = ve[0], hi = ve[0], mind = INFINITY;
+            for (int j = 0; j < U; j++) {
+                if (ve[j] < lo) lo = ve[j];
+                if (ve[j] > hi) hi = ve[j];
+                for (int i = j + 1; i < U && i <= j + 1; i++) { const double d = fabs(ve[i] - ve[j]); if (d > 0 && d < mind) mind = d; }
+            }
+            if (!(ve[U - 1] >= ve[0])) mind = 0;      /* not monotone: give up on the static bound */
+            for (int j = 1; j < U; j++) if (ve[j] < ve[j - 1]) mind = 0;
+            if (mind * mind < smin) smin = mind * mind;
+            smax += (hi - lo) * (hi - lo);
+        }
+        hp->safe_range = (smin >= 0x1p-200 && smax <= 0x1p200 && isfinite(smax)) ? 1 : 0;
+    }
     /* corner rules in binary-counter order (frirl_init_rb.c:99-126) */
     hp->ncorner = 1 << K;
     for (int r = 0; r < hp->ncorner; r++) {
@@ -311,6 +330,7 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     int rc = problem_upload(P, device); if (rc) return rc;
     friq_batch *b = (friq_batch *)calloc(1, sizeof *b);
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
+    b->retile_interval = 100;
     friq_devstate *st = &b->st;
     st->n = n; st->n_pad = (n + FRIQ_TILE - 1) / FRIQ_TILE * FRIQ_TILE; st->cap = cap;
     { int rc2 = alloc_state(st, 1); if (rc2) return rc2; }
@@ -443,10 +463,20 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         const size_t slots = (size_t)b->st.n_pad * b->st.cap;
         DEV(friqd_malloc((void **)&b->st.prevq, slots * 8)); DEV(friqd_memset(b->st.prevq, 0, slots * 8));
     }
+    if ((mode & FRIQ_RUN_RETILE) && !(mode & FRIQ_RUN_STOP_AT_EPISODE_END) && b->retile_interval > 0) {
+        /* rule bases grow in bursts; re-sorting every few dozen steps keeps the lanes of a warp in step */
+        for (long done = 0; done < n_steps; done += b->retile_interval) {
+            const long m = n_steps - done < b->retile_interval ? n_steps - done : b->retile_interval;
+            int rc = retile(b, 1, stream); if (rc) return rc;
+            DEV(friqd_run_steps(&b->P->hp, b->P->dp, b->st, m, mode, stream));
+        }
+        return 0;
+    }
     if (mode & FRIQ_RUN_RETILE) { int rc = retile(b, 1, stream); if (rc) return rc; }
     DEV(friqd_run_steps(&b->P->hp, b->P->dp, b->st, n_steps, mode, stream));
     return 0;
 }
+int friq_batch_set_retile_interval(friq_batch *b, long steps) { b->retile_interval = steps; return 0; }
 int friq_batch_sync(friq_batch *b, void *stream) { DEV(friqd_set_device(b->device)); DEV(friqd_sync(stream)); return 0; }
 
 int friq_batch_gather(friq_batch *b, double *last_return, int *last_steps, int *rules, int *episodes, int *flags,

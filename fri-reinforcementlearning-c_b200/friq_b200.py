@@ -54,6 +54,7 @@ SYMBOLS = {
     "friq_batch_get_inserted": (C.c_int, [C.c_void_p, ip]),
     "friq_batch_run": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
     "friq_batch_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "friq_batch_set_retile_interval": (C.c_int, [C.c_void_p, C.c_long]),
     "friq_batch_gather": (C.c_int, [C.c_void_p, dp, ip, ip, ip, ip, llp, llp]),
     "friq_batch_gather_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "friq_batch_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -184,6 +185,9 @@ class Batch:
         _ck(lib().friq_batch_run(self.h, int(n_steps), int(mode), stream))
         if sync:
             _ck(lib().friq_batch_sync(self.h, stream))
+
+    def set_retile_interval(self, steps):
+        _ck(lib().friq_batch_set_retile_interval(self.h, int(steps)))
 
     def sync(self, stream=None):
         _ck(lib().friq_batch_sync(self.h, stream))
