@@ -100,6 +100,13 @@ int friqd_device_count(int *count);
 int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const double *d_q, int R, void *stream);
 int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules, void *stream);
 int friqd_unpermute(friq_devstate st, const void *src, void *dst, int elem_bytes, void *stream);
+int friqd_stream_create(void **s);
+int friqd_stream_destroy(void *s);
+int friqd_event_create(void **e);
+int friqd_event_destroy(void *e);
+int friqd_event_record(void *e, void *stream);
+int friqd_stream_wait_event(void *stream, void *e);
+int friqd_device_sync(void);
 int friqd_sync(void *stream);
 const char *friqd_error_string(int err);
 int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long long seed0, long first_agent,

@@ -411,6 +411,13 @@ int friqd_unpermute(friq_devstate st, const void *src, void *dst, int elem_bytes
     CK(cudaGetLastError());
     return 0;
 }
+int friqd_stream_create(void **s) { cudaStream_t t; CK(cudaStreamCreate(&t)); *s = (void *)t; return 0; }
+int friqd_stream_destroy(void *s) { CK(cudaStreamDestroy((cudaStream_t)s)); return 0; }
+int friqd_event_create(void **e) { cudaEvent_t t; CK(cudaEventCreateWithFlags(&t, cudaEventDisableTiming)); *e = (void *)t; return 0; }
+int friqd_event_destroy(void *e) { CK(cudaEventDestroy((cudaEvent_t)e)); return 0; }
+int friqd_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream)); return 0; }
+int friqd_stream_wait_event(void *stream, void *e) { CK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)e, 0)); return 0; }
+int friqd_device_sync(void) { CK(cudaDeviceSynchronize()); return 0; }
 int friqd_sync(void *stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
 const char *friqd_error_string(int err)
 {

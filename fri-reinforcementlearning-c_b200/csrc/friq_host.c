@@ -19,6 +19,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#define FRIQ_MAXGROUPS 8
 static __thread char g_err[512] = "";
 const char *friq_last_error(void) { return g_err; }
 #define FAIL(code, ...) do { snprintf(g_err, sizeof g_err, __VA_ARGS__); return (code); } while (0)
@@ -39,6 +40,8 @@ struct friq_batch {
     friq_devstate st2;        /* alternate buffers used by re-tiling (allocated on first use) */
     int have_st2, permuted;
     long retile_interval;     /* env steps between re-tilings inside one friq_batch_run (FRIQ_RUN_RETILE) */
+    int groups;               /* independent agent groups pipelined on their own streams (hides launch tails) */
+    void *gstream[FRIQ_MAXGROUPS], *gdone[FRIQ_MAXGROUPS], *gstart;
     int *d_work;              /* re-tiling scratch */
     void *d_tmp8, *d_tmp4a, *d_tmp4b;   /* un-permuted result staging */
     int device;
@@ -311,7 +314,7 @@ static int retile(friq_batch *b, int by_rules, void *stream)
     if (!b->have_st2) {
         b->st2 = b->st; b->st2.prevq = NULL;
         int rc = alloc_state(&b->st2, 0); if (rc) return rc;
-        DEV(friqd_malloc((void **)&b->d_work, sizeof(int) * (b->st.cap + 2 + (size_t)b->st.n_pad)));
+        DEV(friqd_malloc((void **)&b->d_work, sizeof(int) * (FRIQ_MAXGROUPS * ((size_t)b->st.cap + 2 + FRIQ_TILE) + (size_t)b->st.n_pad)));
         b->have_st2 = 1;
     }
     if (b->st.prevq && !b->st2.prevq) DEV(friqd_malloc((void **)&b->st2.prevq, (size_t)b->st.n_pad * b->st.cap * 8));
@@ -321,7 +324,21 @@ static int retile(friq_batch *b, int by_rules, void *stream)
     b->permuted = by_rules;
     return 0;
 }
-#define IDENTITY(b) do { int rc_ = retile((b), 0, NULL); if (rc_) return rc_; } while (0)
+/* the slots [lo, lo + n) of a placement as a stand-alone state (lo is a multiple of the tile size) */
+static friq_devstate state_view(const friq_devstate *st, long lo, long n)
+{
+    friq_devstate v = *st;
+    const size_t ro = (size_t)(lo / FRIQ_TILE) * st->cap * FRIQ_TILE;
+    v.n = n;
+    v.rbw += ro; v.rbq += ro; v.sw += ro; if (v.prevq) v.prevq += ro;
+    v.s += lo; v.qs += lo; v.vo += lo;
+    v.aidx += lo; v.flags += lo; v.R += lo; v.step_in_ep += lo; v.last_steps += lo; v.last_rules += lo; v.prev_steps += lo; v.prev_numru += lo;
+    v.ep_num += lo; v.ep_return += lo; v.last_return += lo; v.prev_reward += lo;
+    v.total_steps += lo; v.sum_rules += lo; v.seed += lo; v.alpha += lo; v.gamma += lo; v.epsilon += lo;
+    v.agent_of_slot += lo; v.hitq += lo;
+    return v;
+}
+#define IDENTITY(b) do { if ((b)->permuted) { DEV(friqd_device_sync()); int rc_ = retile((b), 0, NULL); if (rc_) return rc_; DEV(friqd_device_sync()); } } while (0)
 
 int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t seed0, long first_agent, friq_batch **out)
 {
@@ -331,6 +348,14 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     friq_batch *b = (friq_batch *)calloc(1, sizeof *b);
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
     b->retile_interval = 100;
+    {   /* groups of >= 8192 agents, tile aligned; FRIQ_GROUPS overrides (experiments) */
+        const char *e = getenv("FRIQ_GROUPS");
+        int g = e ? atoi(e) : (int)(n / 32768);
+        if (g < 1) g = 1;
+        if (g > FRIQ_MAXGROUPS) g = FRIQ_MAXGROUPS;
+        while (g > 1 && (n / g) < 1024) g--;
+        b->groups = g;
+    }
     friq_devstate *st = &b->st;
     st->n = n; st->n_pad = (n + FRIQ_TILE - 1) / FRIQ_TILE * FRIQ_TILE; st->cap = cap;
     { int rc2 = alloc_state(st, 1); if (rc2) return rc2; }
@@ -343,6 +368,7 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
 int friq_batch_reset(friq_batch *b)
 {
     DEV(friqd_set_device(b->device));
+    DEV(friqd_device_sync());
     b->permuted = 0;
     DEV(friqd_init_agents(b->P->dp, b->st, b->seed0, b->first_agent, b->P->alpha, b->P->gamma, b->P->epsilon, NULL));
     DEV(friqd_sync(NULL));
@@ -353,6 +379,8 @@ void friq_batch_destroy(friq_batch *b)
 {
     if (!b) return;
     friqd_set_device(b->device);
+    for (int g = 0; g < FRIQ_MAXGROUPS; g++) { if (b->gstream[g]) friqd_stream_destroy(b->gstream[g]); if (b->gdone[g]) friqd_event_destroy(b->gdone[g]); }
+    if (b->gstart) friqd_event_destroy(b->gstart);
     friqd_free(b->st.sw);
     free_state(&b->st);
     if (b->have_st2) { free_state(&b->st2); friqd_free(b->d_work); }
@@ -464,12 +492,34 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         DEV(friqd_malloc((void **)&b->st.prevq, slots * 8)); DEV(friqd_memset(b->st.prevq, 0, slots * 8));
     }
     if ((mode & FRIQ_RUN_RETILE) && !(mode & FRIQ_RUN_STOP_AT_EPISODE_END) && b->retile_interval > 0) {
-        /* rule bases grow in bursts; re-sorting every few dozen steps keeps the lanes of a warp in step */
+        /* Rule bases grow in bursts: re-sorting every `retile_interval` steps keeps the lanes of a warp in
+         * step.  The batch is cut into independent agent groups, each sorted within its own slot range and
+         * issued on its own stream, so that the tail of one group's launch (a few warps with long rule
+         * bases) overlaps the next group's launch instead of idling the GPU. */
+        const int G = b->groups;
+        if (b->permuted && b->permuted != 1 + G) { int rc = retile(b, 0, stream); if (rc) return rc; }   /* group layout changed */
+        if (!b->have_st2) { int rc = retile(b, 1, stream); if (rc) return rc; rc = retile(b, 0, stream); if (rc) return rc; }  /* allocate buffers */
+        if (b->st.prevq && !b->st2.prevq) DEV(friqd_malloc((void **)&b->st2.prevq, (size_t)b->st.n_pad * b->st.cap * 8));
+        if (!b->gstart) DEV(friqd_event_create(&b->gstart));
+        for (int g = 0; g < G; g++) if (!b->gstream[g]) { DEV(friqd_stream_create(&b->gstream[g])); DEV(friqd_event_create(&b->gdone[g])); }
+        DEV(friqd_event_record(b->gstart, stream));
+        const long tiles = b->st.n_pad / FRIQ_TILE, per = (tiles + G - 1) / G * FRIQ_TILE;
+        const size_t wstride = (size_t)b->st.cap + 2 + per;
+        for (int g = 0; g < G; g++) DEV(friqd_stream_wait_event(b->gstream[g], b->gstart));
         for (long done = 0; done < n_steps; done += b->retile_interval) {
             const long m = n_steps - done < b->retile_interval ? n_steps - done : b->retile_interval;
-            int rc = retile(b, 1, stream); if (rc) return rc;
-            DEV(friqd_run_steps(&b->P->hp, b->P->dp, b->st, m, mode, stream));
+            b->st2.sw = b->st.sw;
+            for (int g = 0; g < G; g++) {
+                const long lo = g * per, cnt = (lo + per <= b->st.n ? per : b->st.n - lo);
+                if (cnt <= 0) continue;
+                friq_devstate src = state_view(&b->st, lo, cnt), dst = state_view(&b->st2, lo, cnt);
+                DEV(friqd_retile(src, dst, b->d_work + g * wstride, 1, b->gstream[g]));
+                DEV(friqd_run_steps(&b->P->hp, b->P->dp, dst, m, mode, b->gstream[g]));
+            }
+            friq_devstate t = b->st; b->st = b->st2; b->st2 = t;
+            b->permuted = 1 + G;
         }
+        for (int g = 0; g < G; g++) { DEV(friqd_event_record(b->gdone[g], b->gstream[g])); DEV(friqd_stream_wait_event(stream, b->gdone[g])); }
         return 0;
     }
     if (mode & FRIQ_RUN_RETILE) { int rc = retile(b, 1, stream); if (rc) return rc; }
@@ -477,14 +527,14 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
     return 0;
 }
 int friq_batch_set_retile_interval(friq_batch *b, long steps) { b->retile_interval = steps; return 0; }
-int friq_batch_sync(friq_batch *b, void *stream) { DEV(friqd_set_device(b->device)); DEV(friqd_sync(stream)); return 0; }
+int friq_batch_sync(friq_batch *b, void *stream) { DEV(friqd_set_device(b->device)); DEV(friqd_sync(stream)); DEV(friqd_device_sync()); return 0; }
 
 int friq_batch_gather(friq_batch *b, double *last_return, int *last_steps, int *rules, int *episodes, int *flags,
                       long long *total_steps, long long *sum_rules)
 {
     const long n = b->st.n;
     DEV(friqd_set_device(b->device));
-    DEV(friqd_sync(NULL));
+    DEV(friqd_device_sync());
     IDENTITY(b);
     if (last_return) DEV(friqd_d2h(last_return, b->st.last_return, 8 * n));
     if (last_steps) DEV(friqd_d2h(last_steps, b->st.last_steps, 4 * n));
