@@ -133,6 +133,7 @@ def main():
 
     import torch
     import friq_b200 as fq
+    import friq_dist
 
     torch.cuda.set_device(local)
     dist = None
@@ -144,7 +145,8 @@ def main():
     sptr = ctypes.c_void_p(stream.cuda_stream)
 
     P = fq.Problem("mountaincar", no_random=0)
-    b = fq.Batch(P, n, 192, device=local, seed0=0x5EED0000, first_agent=rank * n)
+    first_agent, _ = friq_dist.shard(world * n, world, rank)
+    b = fq.Batch(P, n, 192, device=local, seed0=0x5EED0000, first_agent=first_agent)
     b.set_retile_interval(args.retile)
     launches_per_step = (-(-args.chunk // args.retile) if args.retile > 0 else 1)
     mode = fq.RUN_LEARN | fq.RUN_RETILE      # agents are re-assigned to warps by rule count before every launch
@@ -160,9 +162,8 @@ def main():
     def gather_results():
         b.gather_device(ctypes.c_void_p(d_ret.data_ptr()), ctypes.c_void_p(d_steps.data_ptr()), ctypes.c_void_p(d_rules.data_ptr()), sptr)
         if world > 1:       # the path's only exchange: per-agent results + rule-base statistics over NCCL/NVLink
-            dist.all_gather_into_tensor(g_ret, d_ret); dist.all_gather_into_tensor(g_steps, d_steps); dist.all_gather_into_tensor(g_rules, d_rules)
-            stats[0] = d_rules.sum(); stats[1] = d_ret.sum(); stats[2] = d_rules.max()
-            dist.all_reduce(stats[:2]); dist.all_reduce(stats[2:], op=dist.ReduceOp.MAX)
+            friq_dist.gather_agent_results(dist, d_ret, d_steps, d_rules, out=(g_ret, g_steps, g_rules))
+            friq_dist.reduce_stats(dist, d_ret, d_rules, stats)
 
     def barrier():
         if world > 1:
