@@ -19,6 +19,9 @@
 #ifndef FRIQ_BLOCK
 #define FRIQ_BLOCK 128
 #endif
+#ifndef FRIQ_UNR_MC
+#define FRIQ_UNR_MC 3
+#endif
 #ifndef FRIQ_MINB
 #define FRIQ_MINB 2
 #endif
@@ -41,7 +44,7 @@ struct __align__(16) friq_smem_t {
 
 // ---------------------------------------------------------------------------------------
 template <int S, int P, int A, int ACH, int ENV, int UNR, bool SAFE>
-__global__ void __launch_bounds__(FRIQ_BLOCK, UNR > 1 ? FRIQ_MINB : (512 / FRIQ_BLOCK))
+__global__ void __launch_bounds__(FRIQ_BLOCK, FRIQ_MINB)
 k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
 {
     constexpr int K = S + 1;
@@ -441,7 +444,7 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
         if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
         else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
     } while (0)
-    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_STEP(2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 2);
+    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_STEP(2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, FRIQ_UNR_MC);
     else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_STEP(4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2);
     else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) FRIQ_LAUNCH_STEP(4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1);
     else return FRIQ_ERR_SHAPE;
