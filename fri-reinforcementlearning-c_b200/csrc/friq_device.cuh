@@ -332,17 +332,17 @@ __device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, do
 // ---------------------------------------------------------------------------------------
 template <int S, int P>
 __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
-                                                 const double *qs, double reward, double qp, int hitq, double qnow, double ws,
+                                                 const double *qs, const int *qi, double reward, double qp, int hitq, double qnow, double ws,
                                                  double alpha, double gamma)
-{
+{   // qi[k] >= 0: qs[k] is known to BE the grid value dict_val[k][qi[k]] (snapping an on-grid value returns it)
     constexpr int K = S + 1;
     const double qdiff = __dmul_rn(alpha, __dsub_rn(__dadd_rn(reward, __dmul_rn(gamma, qp)), qnow));   // :358
     if (qdiff > pb.qdiff_pos || qdiff < pb.qdiff_neg) {
         int gi[K]; bool same = true; uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            gi[k] = friq_snap_index(pb, k, qs[k]);                                               // :146-170
-            same = same && (pb.dict_val[k][gi[k]] == qs[k]);
+            if (qi[k] >= 0) gi[k] = qi[k];
+            else { gi[k] = friq_snap_index(pb, k, qs[k]); same = same && (pb.dict_val[k][gi[k]] == qs[k]); }   // :146-170
             packed |= (uint32_t)gi[k] << (FRIQ_IDX_BITS * k);
         }
         int hitg = hitq; double qg = qnow;
@@ -467,7 +467,7 @@ template <> __device__ __forceinline__ void friq_env_reward<FRIQ_ENV_CARTPOLE>(c
 
 // quantise_observations: writes the quantised state q[] and its VE values vo[]
 template <int ENV, int S>
-__device__ __forceinline__ void friq_env_quantize(const friq_devprob &pb, const double *s, double *q, double *vo)
+__device__ __forceinline__ void friq_env_quantize(const friq_devprob &pb, const double *s, double *q, double *vo, int *qidx)
 {
     if (ENV == FRIQ_ENV_CARTPOLE) {                      // cartpole.c:114-168
         const double deg12 = FRIQ_PI / 15, deg3 = FRIQ_PI / 60;
@@ -482,7 +482,7 @@ __device__ __forceinline__ void friq_env_quantize(const friq_devprob &pb, const 
         if (x3 > 0) x3 = 1;
         q[0] = x0; q[1] = x1; q[2] = x2; q[3] = x3;
 #pragma unroll
-        for (int k = 0; k < S; k++) vo[k] = friq_obs_ve(pb, k, q[k]);
+        for (int k = 0; k < S; k++) { vo[k] = friq_obs_ve(pb, k, q[k]); qidx[k] = -1; }      // off-grid values
     } else {                                             // mountaincar.c:98-125, acrobot.c:165-192
 #pragma unroll
         for (int k = 0; k < S; k++) {
@@ -490,6 +490,7 @@ __device__ __forceinline__ void friq_env_quantize(const friq_devprob &pb, const 
             if (where < 0) where = 0; else if (where > pb.grid_len[k] - 1) where = pb.grid_len[k] - 1;
             q[k] = pb.dict_val[k][where];
             vo[k] = pb.dict_ve[k][where];                // = VE_k[nearest_index(values[where])]
+            qidx[k] = where;
         }
     }
 }

@@ -66,6 +66,12 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     const unsigned long long seed = st.seed[ag];
     const double alpha = st.alpha[ag], gamma = st.gamma[ag], epsilon = st.epsilon[ag];
     const bool learn = mode & FRIQ_M_LEARN, track = (mode & FRIQ_M_TRACK) && prevq;
+    int qi[K];                                           // grid index of qs[k] when it is a grid value, else -1
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        qi[k] = -1;
+        for (int j = 0; j < pb.grid_len[k]; j++) if (pb.dict_val[k][j] == qs[k]) { qi[k] = j; break; }
+    }
 
     // All lanes of a warp iterate in lockstep (explicit reconvergence at the loop top): a lane that starts
     // an episode spends one iteration on the initial action selection (frirl_episode.c:78) while its
@@ -76,11 +82,11 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     while (__any_sync(wmask, running && done_steps < n_steps)) {
         const bool act = running && done_steps < n_steps && !((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED));
         const bool initial = flags & FRIQ_F_NEED_RESET;
-        double cur[S], cq[S], vc[S], reward = 0.0; int done = 0;
+        double cur[S], cq[S], vc[S], reward = 0.0; int done = 0, ci[S];
         if (act) {
             if (initial) {                               // frirl_episode.c:46-82
 #pragma unroll
-                for (int k = 0; k < S; k++) { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; cur[k] = cq[k] = s[k]; }
+                for (int k = 0; k < S; k++) { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; cur[k] = cq[k] = s[k]; qi[k] = ci[k] = -1; }
                 ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
                 prev_numru = R;
                 if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
@@ -88,12 +94,12 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 friq_env_step<ENV>(pb.act_val[aidx], s, cur);
                 friq_env_reward<ENV>(cur, reward, done);
                 ep_return = __dadd_rn(ep_return, reward);
-                friq_env_quantize<ENV, S>(pb, cur, cq, vc);
+                friq_env_quantize<ENV, S>(pb, cur, cq, vc, ci);
                 step_in_ep++;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < S; k++) { cur[k] = s[k]; cq[k] = qs[k]; vc[k] = vo[k]; }
+            for (int k = 0; k < S; k++) { cur[k] = s[k]; cq[k] = qs[k]; vc[k] = vo[k]; ci[k] = qi[k]; }
             running = false;
         }
         // Q(s,a) of the pending update: its exact-hit rule is known from the previous pass (hitq >= 0), or
@@ -109,7 +115,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             friq_best_action_pass<S, P, A, ACH, false, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, false, vagq, wsq);
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
-        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; hitq = next_hit; }
+        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }
         if (act && !initial) {
             sum_rules += (unsigned long long)R;
             if (learn) {                                 // frirl_update_sarsa.c:348-385
@@ -125,7 +131,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
                 else { ws = wsq; qnow = __ddiv_rn(vagq, wsq); }                               // FIVEVagConcl.c:302
                 const int R0 = R;
-                friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward, qp, hitq, qnow, ws, alpha, gamma);
+                friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma);
                 hitq = next_hit;
                 if (R > R0 && hitq == -1) {              // a rule was appended: is it at the next step's (s,a)?
                     const uint32_t wnew = rbw[(size_t)R0 * FRIQ_TILE];
@@ -137,8 +143,8 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             } else hitq = next_hit;
             // frirl_episode.c:163-185
 #pragma unroll
-            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; }
-            aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
+            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; qi[k] = ci[k]; }
+            aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2;
             total_steps++; done_steps++;
             if (done || step_in_ep >= pb.max_steps) {
                 // "RB complete" predicate, frirl_sequential_run.c:83-150
@@ -225,7 +231,10 @@ k_update_sarsa(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
     double qp, qnow, wsp, ws;
     friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vc, qp, wsp);                 // :355
     const int hitq = friq_vag_concl<K, P>(pb, rbw, rbq, sw, R, vq, qnow, ws);    // :356
-    friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, reward[ag], qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
+    int qi[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) qi[k] = -1;
+    friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward[ag], qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
     st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
 }
 
