@@ -78,6 +78,7 @@ typedef struct friq_devstate {
     unsigned long long *total_steps, *sum_rules, *seed;
     double *alpha, *gamma, *epsilon;
     int *hitq;                  /* [n_pad] exact-hit rule of Q(s,a) for the pending update, -1 none, -2 unknown */
+    double *s0;                 /* [FRIQ_MAXK][n_pad] optional per-agent episode start state (NULL: values_def) */
     int *agent_of_slot;         /* [n_pad] which agent lives in slot p (identity unless re-tiled by rule count) */
 } friq_devstate;
 
@@ -112,6 +113,7 @@ const char *friqd_error_string(int err);
 int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long long seed0, long first_agent,
                       double alpha, double gamma, double epsilon, void *stream);
 int friqd_run_steps(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, void *stream);
+int friqd_run_shared(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, long n_steps, int mode, void *stream);
 int friqd_vag_concl(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_conc, int *d_hit,
                     double *d_weights, void *stream);
 int friqd_best_action(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_states, double *d_actconc,

@@ -86,7 +86,11 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         if (act) {
             if (initial) {                               // frirl_episode.c:46-82
 #pragma unroll
-                for (int k = 0; k < S; k++) { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; cur[k] = cq[k] = s[k]; qi[k] = ci[k] = -1; }
+                for (int k = 0; k < S; k++) {
+                    if (st.s0) { s[k] = qs[k] = st.s0[(size_t)k * st.n_pad + ag]; vo[k] = vc[k] = friq_obs_ve(pb, k, s[k]); }
+                    else { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; }
+                    cur[k] = cq[k] = s[k]; qi[k] = ci[k] = -1;
+                }
                 ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
                 prev_numru = R;
                 if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
@@ -172,6 +176,193 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     st.aidx[ag] = aidx; st.flags[ag] = flags; st.R[ag] = R; st.step_in_ep[ag] = step_in_ep; st.hitq[ag] = hitq;
     st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
     st.prev_reward[ag] = prev_reward; st.prev_steps[ag] = prev_steps; st.prev_numru[ag] = prev_numru;
+    st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
+    st.total_steps[ag] = total_steps; st.sum_rules[ag] = sum_rules;
+}
+
+// ---------------------------------------------------------------------------------------
+// Shared-rule-base inference (BASELINE config 4: many agents, ONE large read-only rule base,
+// reduction_state = 1 semantics of frirl_test_run.c:65-69: greedy stepping, no rule-base writes).
+// The rule base is stored as rows of (VE value of each antecedent, consequent) = (K+1) f64 and streams
+// through shared memory in tiles of FRIQ_SRB_TILE rules: one elected thread issues cp.async.bulk (TMA)
+// into a 2-deep ring, completion on mbarriers; all threads (= agents) of the CTA consume the same tile
+// with broadcast shared-memory reads.  One thread per agent, rules visited in order => bit-identical sums.
+// ---------------------------------------------------------------------------------------
+#define FRIQ_SRB_TILE 256
+
+__device__ __forceinline__ void friq_tma_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar)
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar), dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void friq_mbar_wait(uint64_t *mbar, uint32_t parity)
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int S, int P, int A, int ENV, int UNR, bool SAFE>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 2)
+k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ srb, int Rs, long n_steps, int mode)
+{
+    constexpr int K = S + 1, RW = K + 1;
+    __shared__ friq_smem_t sm;
+    __shared__ __align__(16) double tile[2][FRIQ_SRB_TILE * RW];
+    __shared__ uint64_t full[2];
+    friq_stage_problem(gprob, sm.prob, &sm.mbar);
+    const friq_devprob &pb = *reinterpret_cast<const friq_devprob *>(sm.prob);
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 2; j++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full[j])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = ag < st.n;
+    const long ia = valid ? ag : 0;
+
+    double s[S], qs[K];
+#pragma unroll
+    for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ia];
+#pragma unroll
+    for (int k = 0; k < K; k++) qs[k] = st.qs[(size_t)k * st.n_pad + ia];
+    int aidx = st.aidx[ia], flags = st.flags[ia], step_in_ep = st.step_in_ep[ia];
+    uint32_t ep_num = st.ep_num[ia];
+    double ep_return = st.ep_return[ia], last_return = st.last_return[ia];
+    int last_steps = st.last_steps[ia], last_rules = st.last_rules[ia];
+    unsigned long long total_steps = st.total_steps[ia], sum_rules = st.sum_rules[ia];
+    const unsigned long long seed = st.seed[ia];
+    const double epsilon = st.epsilon[ia];
+    const int ntiles = (Rs + FRIQ_SRB_TILE - 1) / FRIQ_SRB_TILE;
+    uint32_t parity = 0;                                 // bit j = phase of full[j]
+
+    long done_steps = 0;
+    bool running = valid;
+    while (__syncthreads_or(running && done_steps < n_steps)) {
+        const bool act = running && done_steps < n_steps;
+        const bool initial = flags & FRIQ_F_NEED_RESET;
+        double cur[S], cq[S], vc[S], reward = 0.0; int done = 0, ci[S];
+        if (act) {
+            if (initial) {
+#pragma unroll
+                for (int k = 0; k < S; k++) {
+                    s[k] = qs[k] = st.s0 ? st.s0[(size_t)k * st.n_pad + ag] : pb.values_def[k];
+                    vc[k] = st.s0 ? friq_obs_ve(pb, k, s[k]) : pb.ve_def[k];
+                    cur[k] = cq[k] = s[k];
+                }
+                ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
+            } else {
+                friq_env_step<ENV>(pb.act_val[aidx], s, cur);
+                friq_env_reward<ENV>(cur, reward, done);
+                ep_return = __dadd_rn(ep_return, reward);
+                friq_env_quantize<ENV, S>(pb, cur, cq, vc, ci);
+                step_in_ep++;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < S; k++) { cur[k] = s[k]; cq[k] = qs[k]; vc[k] = 0.0; }
+            running = false;
+        }
+        // ---- one pass over the shared rule base: all A actions, UNR rules per trip
+        double vagc[A], ws[A], hq[A], ave[A];
+        unsigned hitmask = 0;
+#pragma unroll
+        for (int a = 0; a < A; a++) { vagc[a] = 0.0; ws[a] = 0.0; hq[a] = 0.0; ave[a] = pb.act_ve[a]; }
+        if (threadIdx.x == 0)
+            for (int t = 0; t < 2 && t < ntiles; t++) {
+                const int cnt = min(FRIQ_SRB_TILE, Rs - t * FRIQ_SRB_TILE);
+                friq_tma_load(tile[t], srb + (size_t)t * FRIQ_SRB_TILE * RW, (uint32_t)(cnt * RW * sizeof(double)), &full[t]);
+            }
+        for (int t = 0; t < ntiles; t++) {
+            const int bsel = t & 1, cnt = min(FRIQ_SRB_TILE, Rs - t * FRIQ_SRB_TILE);
+            friq_mbar_wait(&full[bsel], (parity >> bsel) & 1u);
+            parity ^= 1u << bsel;
+            const double *tb = tile[bsel];
+#pragma unroll 1
+            for (int i = 0; i < cnt; i += UNR) {
+                double wv[UNR][A]; bool z[UNR][A]; double q[UNR];
+                unsigned bad = 0;
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const double *r = tb + (size_t)min(i + u, cnt - 1) * RW;
+                    double ssum = 0.0;
+#pragma unroll
+                    for (int k = 0; k < S; k++) {
+                        const double d = __dsub_rn(vc[k], r[k]);
+                        const double d2 = __dmul_rn(d, d);
+                        ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);
+                    }
+                    q[u] = r[K];
+#pragma unroll
+                    for (int a = 0; a < A; a++) {
+                        const double da = __dsub_rn(ave[a], r[S]);
+                        const double sv = __dadd_rn(__dmul_rn(da, da), ssum);
+                        z[u][a] = friq_is_zero(sv);
+                        wv[u][a] = friq_shepard_weight_fast<P, SAFE>(sv, bad, !z[u][a]);
+                    }
+                }
+                if (bad) {
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        const double *r = tb + (size_t)min(i + u, cnt - 1) * RW;
+                        double ssum = 0.0;
+#pragma unroll
+                        for (int k = 0; k < S; k++) { const double d = __dsub_rn(vc[k], r[k]); ssum = (k == 0) ? __dmul_rn(d, d) : __dadd_rn(ssum, __dmul_rn(d, d)); }
+#pragma unroll
+                        for (int a = 0; a < A; a++) {
+                            const double da = __dsub_rn(ave[a], r[S]);
+                            wv[u][a] = friq_shepard_weight<P>(z[u][a] ? 1.0 : __dadd_rn(__dmul_rn(da, da), ssum));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    if (u == 0 || i + u < cnt) {
+#pragma unroll
+                        for (int a = 0; a < A; a++) {
+                            if (z[u][a] && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q[u]; }
+                            vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u][a], q[u]));
+                            ws[a] = __dadd_rn(ws[a], wv[u][a]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();                             // everyone is done with tile[bsel]
+            if (threadIdx.x == 0 && t + 2 < ntiles) {
+                const int c2 = min(FRIQ_SRB_TILE, Rs - (t + 2) * FRIQ_SRB_TILE);
+                friq_tma_load(tile[bsel], srb + (size_t)(t + 2) * FRIQ_SRB_TILE * RW, (uint32_t)(c2 * RW * sizeof(double)), &full[bsel]);
+            }
+        }
+        double actconc[A];
+#pragma unroll
+        for (int a = 0; a < A; a++) actconc[a] = ((hitmask >> a) & 1u) ? hq[a] : __ddiv_rn(vagc[a], ws[a]);
+        const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
+        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; }
+        if (act && !initial) {
+            sum_rules += (unsigned long long)Rs;
+#pragma unroll
+            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; }
+            aidx = a2; qs[S] = pb.act_val[a2];
+            total_steps++; done_steps++;
+            if (done || step_in_ep >= pb.max_steps) {
+                last_return = ep_return; last_steps = step_in_ep; last_rules = Rs;
+                ep_num++;
+                flags |= FRIQ_F_NEED_RESET;
+                if (mode & FRIQ_M_STOP_AT_EPISODE_END) running = false;
+            }
+        }
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
+#pragma unroll
+    for (int k = 0; k < K; k++) st.qs[(size_t)k * st.n_pad + ag] = qs[k];
+    st.aidx[ag] = aidx; st.flags[ag] = flags; st.step_in_ep[ag] = step_in_ep; st.hitq[ag] = -2;
+    st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
     st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
     st.total_steps[ag] = total_steps; st.sum_rules[ag] = sum_rules;
 }
@@ -306,6 +497,7 @@ __global__ void k_retile_move(friq_devstate a, friq_devstate b, const int *work)
     b.total_steps[q] = a.total_steps[p]; b.sum_rules[q] = a.sum_rules[p]; b.seed[q] = a.seed[p];
     b.alpha[q] = a.alpha[p]; b.gamma[q] = a.gamma[p]; b.epsilon[q] = a.epsilon[p];
     b.agent_of_slot[q] = a.agent_of_slot[p]; b.hitq[q] = a.hitq[p];
+    if (a.s0 && b.s0) for (int k = 0; k < FRIQ_MAXK; k++) b.s0[(size_t)k * b.n_pad + q] = a.s0[(size_t)k * a.n_pad + p];
     const size_t po = (size_t)(p >> 5) * a.cap * FRIQ_TILE + (p & 31), qo = (size_t)(q >> 5) * b.cap * FRIQ_TILE + (q & 31);
     const int R = a.R[p];
     for (int i = 0; i < R; i++) {
@@ -456,6 +648,21 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_STEP(2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, FRIQ_UNR_MC);
     else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_STEP(4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2);
     else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) FRIQ_LAUNCH_STEP(4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_run_shared(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, long n_steps, int mode, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+#define FRIQ_LAUNCH_SHARED(S_, P_, A_, ENV_, UNR_)                                                                     \
+    do {                                                                                                              \
+        if (hp->safe_range) k_infer_shared<S_, P_, A_, ENV_, UNR_, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, n_steps, mode); \
+        else k_infer_shared<S_, P_, A_, ENV_, UNR_, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, n_steps, mode);               \
+    } while (0)
+    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_SHARED(2, 3, 3, FRIQ_ENV_MOUNTAINCAR, 3);
+    else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_SHARED(4, 5, 3, FRIQ_ENV_ACROBOT, 2);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;

@@ -40,6 +40,7 @@ struct friq_batch {
     friq_devstate st2;        /* alternate buffers used by re-tiling (allocated on first use) */
     int have_st2, permuted;
     long retile_interval;     /* env steps between re-tilings inside one friq_batch_run (FRIQ_RUN_RETILE) */
+    double *d_srb; int shared_R;   /* shared read-only rule base: rows of (K VE values, consequent) */
     int groups;               /* independent agent groups pipelined on their own streams (hides launch tails) */
     void *gstream[FRIQ_MAXGROUPS], *gdone[FRIQ_MAXGROUPS], *gstart;
     int *d_work;              /* re-tiling scratch */
@@ -312,8 +313,9 @@ static int retile(friq_batch *b, int by_rules, void *stream)
 {
     if (!by_rules && !b->permuted) return 0;
     if (!b->have_st2) {
-        b->st2 = b->st; b->st2.prevq = NULL;
+        b->st2 = b->st; b->st2.prevq = NULL; b->st2.s0 = NULL;
         int rc = alloc_state(&b->st2, 0); if (rc) return rc;
+        if (b->st.s0) DEV(friqd_malloc((void **)&b->st2.s0, 8 * FRIQ_MAXK * (size_t)b->st.n_pad));
         DEV(friqd_malloc((void **)&b->d_work, sizeof(int) * (FRIQ_MAXGROUPS * ((size_t)b->st.cap + 2 + FRIQ_TILE) + (size_t)b->st.n_pad)));
         b->have_st2 = 1;
     }
@@ -335,7 +337,7 @@ static friq_devstate state_view(const friq_devstate *st, long lo, long n)
     v.aidx += lo; v.flags += lo; v.R += lo; v.step_in_ep += lo; v.last_steps += lo; v.last_rules += lo; v.prev_steps += lo; v.prev_numru += lo;
     v.ep_num += lo; v.ep_return += lo; v.last_return += lo; v.prev_reward += lo;
     v.total_steps += lo; v.sum_rules += lo; v.seed += lo; v.alpha += lo; v.gamma += lo; v.epsilon += lo;
-    v.agent_of_slot += lo; v.hitq += lo;
+    v.agent_of_slot += lo; v.hitq += lo; if (v.s0) v.s0 += lo;
     return v;
 }
 #define IDENTITY(b) do { if ((b)->permuted) { DEV(friqd_device_sync()); int rc_ = retile((b), 0, NULL); if (rc_) return rc_; DEV(friqd_device_sync()); } } while (0)
@@ -382,6 +384,9 @@ void friq_batch_destroy(friq_batch *b)
     for (int g = 0; g < FRIQ_MAXGROUPS; g++) { if (b->gstream[g]) friqd_stream_destroy(b->gstream[g]); if (b->gdone[g]) friqd_event_destroy(b->gdone[g]); }
     if (b->gstart) friqd_event_destroy(b->gstart);
     friqd_free(b->st.sw);
+    if (b->d_srb) friqd_free(b->d_srb);
+    if (b->st.s0) friqd_free(b->st.s0);
+    if (b->have_st2 && b->st2.s0) friqd_free(b->st2.s0);
     free_state(&b->st);
     if (b->have_st2) { free_state(&b->st2); friqd_free(b->d_work); }
     if (b->d_tmp8) { friqd_free(b->d_tmp8); friqd_free(b->d_tmp4a); friqd_free(b->d_tmp4b); }
@@ -441,6 +446,48 @@ int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant
     return 0;
 }
 
+/* ONE read-only rule base for all agents (BASELINE config 4): antecedent values are resolved to VE values here,
+ * exactly as five_add_rule.c:71-84 caches them; R = 0 returns to the private rule bases */
+int friq_batch_set_shared_rulebase(friq_batch *b, int R, const double *rant, const double *rconc)
+{
+    friq_problem *P = b->P; const int K = P->hp.K, U = P->hp.U;
+    DEV(friqd_set_device(b->device));
+    DEV(friqd_device_sync());
+    if (b->d_srb) { friqd_free(b->d_srb); b->d_srb = NULL; }
+    b->shared_R = 0;
+    if (R <= 0) return 0;
+    double *rows = (double *)malloc(sizeof(double) * (size_t)R * (K + 1));
+    for (int i = 0; i < R; i++) {
+        for (int k = 0; k < K; k++)
+            rows[(size_t)i * (K + 1) + k] = P->ve[(size_t)k * U + nearest_index(P->u + (size_t)k * U, U, U, P->hp.udiv[k], rant[(size_t)i * K + k])];
+        rows[(size_t)i * (K + 1) + K] = rconc[i];
+    }
+    int rc = friqd_malloc((void **)&b->d_srb, sizeof(double) * (size_t)R * (K + 1));
+    if (!rc) rc = friqd_h2d(b->d_srb, rows, sizeof(double) * (size_t)R * (K + 1));
+    free(rows);
+    if (rc) FAIL(rc, "friq_batch_set_shared_rulebase: %s", friqd_error_string(rc));
+    b->shared_R = R;
+    return 0;
+}
+
+/* per-agent episode start state s0 [n][S] (host, agent order); NULL restores values_def (frirl_episode.c:46-48) */
+int friq_batch_set_initial_state(friq_batch *b, const double *s0)
+{
+    const long n = b->st.n; const size_t np = (size_t)b->st.n_pad; const int S = b->P->hp.S;
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    if (!s0) { if (b->st.s0) { friqd_free(b->st.s0); b->st.s0 = NULL; } if (b->have_st2 && b->st2.s0) { friqd_free(b->st2.s0); b->st2.s0 = NULL; } return 0; }
+    double *t = (double *)calloc(FRIQ_MAXK * np, sizeof(double));
+    for (long i = 0; i < n; i++) for (int k = 0; k < S; k++) t[(size_t)k * np + i] = s0[(size_t)i * S + k];
+    int rc = 0;
+    if (!b->st.s0) rc = friqd_malloc((void **)&b->st.s0, 8 * FRIQ_MAXK * np);
+    if (!rc && b->have_st2 && !b->st2.s0) rc = friqd_malloc((void **)&b->st2.s0, 8 * FRIQ_MAXK * np);
+    if (!rc) rc = friqd_h2d(b->st.s0, t, 8 * FRIQ_MAXK * np);
+    free(t);
+    if (rc) FAIL(rc, "friq_batch_set_initial_state: %s", friqd_error_string(rc));
+    return 0;
+}
+
 int friq_batch_get_rulebase(friq_batch *b, long agent, int *R_out, double *rant, double *rconc)
 {
     const friq_devprob *hp = &b->P->hp; const int K = hp->K;
@@ -460,6 +507,24 @@ int friq_batch_get_rulebase(friq_batch *b, long agent, int *R_out, double *rant,
             for (int k = 0; k < K; k++) rant[(size_t)i * K + k] = hp->dict_val[k][(w[i] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
         free(w);
     }
+    return 0;
+}
+
+/* current raw environment state s [n][S] and current action index [n] of every agent (fep_ant, frirl_types.h:155) */
+int friq_batch_get_state(friq_batch *b, double *s, int *action_index)
+{
+    const long n = b->st.n; const size_t np = (size_t)b->st.n_pad; const int S = b->P->hp.S;
+    DEV(friqd_set_device(b->device));
+    DEV(friqd_device_sync());
+    IDENTITY(b);
+    if (s) {
+        double *t = (double *)malloc(8 * np * S);
+        int rc = friqd_d2h(t, b->st.s, 8 * np * S);
+        if (!rc) for (long i = 0; i < n; i++) for (int k = 0; k < S; k++) s[(size_t)i * S + k] = t[(size_t)k * np + i];
+        free(t);
+        if (rc) FAIL(rc, "friq_batch_get_state: %s", friqd_error_string(rc));
+    }
+    if (action_index) DEV(friqd_d2h(action_index, b->st.aidx, 4 * n));
     return 0;
 }
 
@@ -487,6 +552,12 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
 {
     DEV(friqd_set_device(b->device));
     if (b->P->hp.env == FRIQ_ENV_HOST_CALLBACKS) FAIL(6, "friq_batch_run: the problem has no built-in environment (host callbacks): use the per-call entry points");
+    if (b->shared_R > 0) {
+        if (mode & FRIQ_RUN_LEARN) FAIL(6, "friq_batch_run: a shared rule base is read-only (clear it or drop FRIQ_RUN_LEARN)");
+        IDENTITY(b);
+        DEV(friqd_run_shared(&b->P->hp, b->P->dp, b->st, b->d_srb, b->shared_R, n_steps, mode, stream));
+        return 0;
+    }
     if ((mode & FRIQ_RUN_TRACK_CONVERGENCE) && !b->st.prevq) {
         const size_t slots = (size_t)b->st.n_pad * b->st.cap;
         DEV(friqd_malloc((void **)&b->st.prevq, slots * 8)); DEV(friqd_memset(b->st.prevq, 0, slots * 8));

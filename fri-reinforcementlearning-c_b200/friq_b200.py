@@ -50,6 +50,9 @@ SYMBOLS = {
     "friq_batch_set_hyper": (C.c_int, [C.c_void_p, dp, dp, dp]),
     "friq_batch_set_rulebase": (C.c_int, [C.c_void_p, C.c_long, C.c_int, dp, dp]),
     "friq_batch_get_rulebase": (C.c_int, [C.c_void_p, C.c_long, ip, dp, dp]),
+    "friq_batch_set_shared_rulebase": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
+    "friq_batch_set_initial_state": (C.c_int, [C.c_void_p, dp]),
+    "friq_batch_get_state": (C.c_int, [C.c_void_p, dp, ip]),
     "friq_batch_set_inserted": (C.c_int, [C.c_void_p, ip]),
     "friq_batch_get_inserted": (C.c_int, [C.c_void_p, ip]),
     "friq_batch_run": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
@@ -166,11 +169,24 @@ class Batch:
         rant, rconc = _f64(rant), _f64(rconc)
         _ck(lib().friq_batch_set_rulebase(self.h, agent, len(rconc), _p(rant), _p(rconc)))
 
+    def set_shared_rulebase(self, rant, rconc):
+        rant, rconc = _f64(rant), _f64(rconc)
+        _ck(lib().friq_batch_set_shared_rulebase(self.h, len(rconc), _p(rant), _p(rconc)))
+
+    def set_initial_state(self, s0):
+        s0 = None if s0 is None else _f64(s0).reshape(self.n, self.P.S)
+        _ck(lib().friq_batch_set_initial_state(self.h, _p(s0)))
+
     def get_rulebase(self, agent=0):
         R = C.c_int(0)
         rant = np.zeros((self.cap, self.P.K)); rconc = np.zeros(self.cap)
         _ck(lib().friq_batch_get_rulebase(self.h, agent, C.byref(R), _p(rant), _p(rconc)))
         return R.value, rant[:R.value].copy(), rconc[:R.value].copy()
+
+    def get_state(self):
+        s = np.zeros((self.n, self.P.S)); a = np.zeros(self.n, np.int32)
+        _ck(lib().friq_batch_get_state(self.h, _p(s), _p(a, ip)))
+        return s, a
 
     def set_inserted(self, v):
         v = np.ascontiguousarray(np.broadcast_to(v, (self.n,)), dtype=np.int32)

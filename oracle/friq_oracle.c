@@ -421,7 +421,7 @@ static void agent_step(fo_agent *a) {
     const fo_problem *P = a->P;
     double actconc[FO_MAXA], cur[FO_MAXK], cur_q[FO_MAXK], reward; int done;
     if (a->need_reset) {
-        for (int i = 0; i < P->S; i++) a->s[i] = a->qant[i] = P->values_def[i];   /* NOT quantised, :46-48 */
+        for (int i = 0; i < P->S; i++) a->s[i] = a->qant[i] = a->has_s0 ? a->s0[i] : P->values_def[i];   /* NOT quantised, :46-48 */
         a->ep_return = 0; a->ep_steps = 0; a->step_in_ep = 0; a->need_reset = 0;
         if (a->learning) memcpy(a->prev_rconc, a->rconc, sizeof(double) * a->R);
         a->prev_numru = a->R;
@@ -498,6 +498,8 @@ int fo_agent_inserted(const fo_agent *a) { return a->inserted; }
 void fo_agent_set_inserted(fo_agent *a, int v) { a->inserted = v; }
 void fo_agent_set_hyper(fo_agent *a, double alpha, double gamma, double epsilon) { a->alpha = alpha; a->gamma = gamma; a->epsilon = epsilon; }
 void fo_agent_set_learning(fo_agent *a, int v) { a->learning = v; }
+/* per-agent episode start state (BASELINE config 4: randomised acrobot starts); NULL restores values_def */
+void fo_agent_set_initial_state(fo_agent *a, const double *s0) { a->has_s0 = s0 != NULL; if (s0) memcpy(a->s0, s0, sizeof(double) * a->P->S); }
 void fo_agent_summary(const fo_agent *a, double *o) {
     o[0] = a->R; o[1] = a->episode_num; o[2] = a->last_return; o[3] = a->last_steps; o[4] = a->last_rules;
     o[5] = a->converged; o[6] = (double)a->total_steps; o[7] = a->sum_rules; o[8] = a->inserted; o[9] = a->overflow;

@@ -59,6 +59,7 @@ typedef struct fo_agent {
     long total_steps; double sum_rules;
     uint64_t seed;   /* Philox key */
     double alpha, gamma, epsilon; /* per-agent hyper-parameters (sweep) */
+    int has_s0; double s0[FO_MAXK];   /* optional per-agent episode start state */
     int learning;    /* 0 = inference (reduction_state=1 semantics, frirl_test_run.c:65-69) */
 } fo_agent;
 

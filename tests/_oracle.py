@@ -32,6 +32,7 @@ def lib():
         L.fo_agent_set_hyper.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         L.fo_agent_set_learning.argtypes = [C.c_void_p, C.c_int]
         L.fo_agent_summary.argtypes = [C.c_void_p, dp]
+        L.fo_agent_set_initial_state.argtypes = [C.c_void_p, dp]
         L.fo_vag_concl.argtypes = [C.c_void_p, dp, dp]
         L.fo_vag_concl_weight.argtypes = [C.c_void_p, dp, dp]
         L.fo_get_best_action.argtypes = [C.c_void_p, dp, dp]
@@ -123,6 +124,10 @@ class Agent:
 
     def set_learning(self, v):
         lib().fo_agent_set_learning(self.h, int(v))
+
+    def set_initial_state(self, s0):
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        lib().fo_agent_set_initial_state(self.h, _p(s0))
 
     def run_steps(self, n, stop_on_converge=0):
         lib().fo_agent_run_steps(self.h, n, stop_on_converge)

@@ -225,6 +225,44 @@ def test_inference_mode_leaves_rule_base_untouched(fq):
     b.close(); P.close()
 
 
+@pytest.mark.parametrize("name,R,n,steps", [("mountaincar", 0, 200, 400), ("acrobot", 700, 150, 120), ("acrobot", 513, 40, 30)])
+def test_shared_rule_base_inference_matches_oracle(fq, name, R, n, steps):
+    """BASELINE config 4 in miniature: many agents, ONE read-only rule base streamed through shared memory by
+    TMA, randomised start states, greedy stepping.  R = 0: the learned golden rule base; else a synthetic
+    rule base of R distinct rules on universe points.  Final raw states, actions and episode
+    results of every agent must equal the oracle port's bit for bit."""
+    rng = np.random.default_rng(1234)
+    P = fq.Problem(name)
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1)
+    g = _golden.load(name)
+    if R == 0:
+        rant, rconc = g["final"][1], g["final"][2]
+    else:
+        u = P.tables()["u"]
+        idx = np.unique(rng.integers(0, P.U, size=(4 * R, P.K)), axis=0)
+        idx = idx[rng.permutation(len(idx))[:R]]
+        rant = np.concatenate([g["header"]["rb0"][1], np.stack([u[k][idx[:, k]] for k in range(P.K)], axis=1)])[:R]
+        rconc = np.concatenate([np.zeros(len(g["header"]["rb0"][2])), rng.uniform(-1000, 1000, R)])[:R]
+    lo = {"mountaincar": [-1.2, -0.05], "acrobot": [-np.pi / 2, -np.pi / 2, 0, 0]}[name]
+    hi = {"mountaincar": [0.3, 0.05], "acrobot": [np.pi / 2, np.pi / 2, 0, 0]}[name]
+    s0 = rng.uniform(lo, hi, size=(n, P.S))
+    b = fq.Batch(P, n, max(len(rconc), P.ncorner))
+    b.set_shared_rulebase(rant, rconc)
+    b.set_initial_state(s0)
+    with pytest.raises(fq.FriqError):
+        b.run(1, fq.RUN_LEARN)                          # a shared rule base is read-only
+    b.run(steps // 3, 0); b.run(steps - steps // 3, 0)
+    o = b.gather(); s, a = b.get_state()
+    for i in range(n):
+        ag = _oracle.Agent(OP, len(rconc) + 8); ag.set_rb(rant, rconc); ag.set_learning(0); ag.set_initial_state(s0[i])
+        ag.run_steps(steps)
+        sm = ag.summary()
+        assert np.array_equal(s[i], sm["s"]), i
+        assert (o["total_steps"][i], o["sum_rules"][i]) == (sm["total_steps"], sm["sum_rules"])
+        assert (o["episodes"][i], o["last_steps"][i], o["last_return"][i]) == (sm["episode_num"] - 1, sm["last_steps"], sm["last_return"])
+    b.close(); P.close()
+
+
 def test_capacity_overflow_is_flagged(fq):
     P = fq.Problem("mountaincar")
     b = fq.Batch(P, 32, 12)                               # 8 corner rules + room for 4
