@@ -120,6 +120,9 @@ int friqd_best_action(const friq_devprob *hprob, const friq_devprob *dprob, friq
                       int *d_best, void *stream);
 int friqd_update_sarsa(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_qant, const double *d_reward,
                        const double *d_curqant, void *stream);
+int friqd_classic_step(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_in, double *d_out, void *stream);
+int friqd_rule_distance(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_dists, int *d_hit, void *stream);
+int friqd_bestact_dists(const friq_devprob *hprob, friq_devstate st, const double *d_dists, double *d_conc, void *stream);
 int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream);
 int friqd_pow_x87(const double *d_x, double *d_out, long n, int p, int force_exact, void *stream);
 int friqd_fp64_peak(double *out_ginstr_per_s, int iters);

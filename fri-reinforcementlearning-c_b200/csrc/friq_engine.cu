@@ -429,6 +429,93 @@ k_update_sarsa(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
     st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
 }
 
+// One step of the classic single-agent API (frirl_episode.c:148-160 with HOST environment callbacks):
+// proposed action for the quantised observation (frirl_e_greedy_selection -> frirl_get_best_action unless
+// the host already drew a random action, forced >= 0), then frirl_update_sarsa(q_ant, reward, cur_q_ant).
+// io per agent: in  [0..K) q_ant, [K] reward, [K+1..K+1+S) cur_q_states, [K+1+S] forced action (-1 = greedy),
+//                   [K+2+S] learn (reduction_state == 0)
+//               out [0] action index, [1] rules, [2] fus_is_rule_inserted, [3] overflow, [4..4+A) actconc
+template <int S, int P, int A, int ACH>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
+k_classic_step(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ in, double *__restrict__ out)
+{
+    constexpr int K = S + 1, NIN = K + S + 3, NOUT = 4 + A;
+    FRIQ_SMEM_PROLOGUE();
+    const double *x = in + (size_t)ag * NIN;
+    double *o = out + (size_t)ag * NOUT;
+    double qs[K], vq[K], vc[K], cq[K], actconc[A];
+#pragma unroll
+    for (int k = 0; k < K; k++) { qs[k] = x[k]; vq[k] = friq_obs_ve(pb, k, qs[k]); }
+#pragma unroll
+    for (int k = 0; k < S; k++) { cq[k] = x[K + 1 + k]; vc[k] = friq_obs_ve(pb, k, cq[k]); }
+    const double reward = x[K];
+    int a2 = (int)x[K + 1 + S];
+    const bool learn = x[K + 2 + S] != 0.0;
+    int R = st.R[ag], flags = st.flags[ag];
+#pragma unroll
+    for (int a = 0; a < A; a++) actconc[a] = 0.0;
+    if (a2 < 0) {                                        // frirl_get_best_action.c:31-341
+        int hidx[A]; double vagq, wsq;
+        friq_best_action_pass<S, P, A, ACH, false, 1, false>(pb, rbw, rbq, nullptr, R, vc, actconc, hidx, vc, false, vagq, wsq);
+        a2 = friq_argmax<A>(actconc);
+    }
+    if (learn) {                                         // frirl_update_sarsa.c:348-385
+        cq[S] = pb.act_val[a2]; vc[S] = friq_obs_ve(pb, S, cq[S]);
+        double qp, qnow, wsp, ws;
+        friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vc, qp, wsp);
+        const int hitq = friq_vag_concl<K, P>(pb, rbw, rbq, sw, R, vq, qnow, ws);
+        int qi[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) qi[k] = -1;
+        friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
+        st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
+    }
+    o[0] = (double)a2; o[1] = (double)R; o[2] = (flags & FRIQ_F_INSERTED) ? 1.0 : 0.0; o[3] = (flags & FRIQ_F_OVERFLOW) ? 1.0 : 0.0;
+#pragma unroll
+    for (int a = 0; a < A; a++) o[4 + a] = actconc[a];
+}
+
+// five_rule_distance (five_rule_distance.c:63-295): every rule's scaled distance from the point, and the first
+// rule at distance 0 (-1: none).  All distances are written (the reference stops at the first exact hit and
+// leaves the rest stale).
+template <int S>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
+k_rule_distance(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ ant, double *__restrict__ dists, int *hit)
+{
+    constexpr int K = S + 1;
+    FRIQ_SMEM_PROLOGUE();
+    (void)sw; (void)rbq;
+    double vo[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) vo[k] = friq_obs_ve(pb, k, ant[(size_t)ag * K + k]);
+    const int R = st.R[ag];
+    int h = -1;
+    for (int i = 0; i < R; i++) {
+        const double d = __dsqrt_rn(friq_dist2<K>(pb, rbw[(size_t)i * FRIQ_TILE], vo));
+        dists[(size_t)ag * st.cap + i] = d;
+        if (d == 0.0 && h < 0) h = i;
+    }
+    hit[ag] = h;
+}
+
+// FIVEVagConcl_FRIRL_BestAct (FIVEVagConcl_FRIRL_BestAct.c:56-301) on caller-supplied rule distances
+__global__ void k_bestact_dists(friq_devstate st, const double *__restrict__ dists, double *__restrict__ conc, int P)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n) return;
+    const double *rbq = st.rbq + (size_t)(ag >> 5) * st.cap * FRIQ_TILE + (ag & 31);
+    const double *d = dists + (size_t)ag * st.cap;
+    const int R = st.R[ag];
+    for (int i = 0; i < R; i++) if (d[i] == 0.0) { conc[ag] = rbq[(size_t)i * FRIQ_TILE]; return; }   // :89-93
+    double vagc = 0.0, ws = 0.0;
+    for (int i = 0; i < R; i++) {                                                                    // :212-217
+        const double wi = __drcp_rn(friq_pow_x87_rt(fabs(d[i]), P));
+        vagc = __dadd_rn(vagc, __dmul_rn(wi, rbq[(size_t)i * FRIQ_TILE]));
+        ws = __dadd_rn(ws, wi);
+    }
+    conc[ag] = __ddiv_rn(vagc, ws);                                                                  // :265
+}
+
 __global__ void k_init_agents(const friq_devprob *__restrict__ gprob, friq_devstate st, unsigned long long seed0, long first_agent,
                               double alpha, double gamma, double epsilon)
 {
@@ -698,6 +785,34 @@ int friqd_update_sarsa(const friq_devprob *hp, const friq_devprob *dprob, friq_d
     if (hp->S == 2 && hp->p == 3) k_update_sarsa<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
     else if (hp->S == 4 && hp->p == 5) k_update_sarsa<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
     else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_classic_step(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_in, double *d_out, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (FRIQ_SHAPE_MC(hp)) k_classic_step<2, 3, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (FRIQ_SHAPE_AC(hp)) k_classic_step<4, 5, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (FRIQ_SHAPE_CP(hp)) k_classic_step<4, 5, 21, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_rule_distance(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_dists, int *d_hit, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (hp->S == 2) k_rule_distance<2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
+    else if (hp->S == 4) k_rule_distance<4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int friqd_bestact_dists(const friq_devprob *hp, friq_devstate st, const double *d_dists, double *d_conc, void *stream)
+{
+    k_bestact_dists<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(st, d_dists, d_conc, hp->p);
     CK(cudaGetLastError());
     return 0;
 }

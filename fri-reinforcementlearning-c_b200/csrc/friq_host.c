@@ -238,6 +238,38 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
     return 0;
 }
 
+/* A problem from caller-supplied universes and vague environments (FIVEInit, FIVEInit.c:55-347): no grids, no
+ * actions, no environment - only the FIVE-level per-call entry points make sense on it. */
+int friq_problem_create_from_tables(int K, int U, int p, const double *u, const double *ve, friq_problem **out)
+{
+    if (K < 2 || K * FRIQ_IDX_BITS > 32) FAIL(2, "friq_problem_create_from_tables: %d antecedent dimensions unsupported (2..%d)", K, 32 / FRIQ_IDX_BITS);
+    friq_problem *P = (friq_problem *)calloc(1, sizeof *P);
+    friq_devprob *hp = &P->hp;
+    P->device = -1;
+    P->u = (double *)malloc(sizeof(double) * K * U); P->ve = (double *)malloc(sizeof(double) * K * U);
+    memcpy(P->u, u, sizeof(double) * K * U); memcpy(P->ve, ve, sizeof(double) * K * U);
+    hp->S = K - 1; hp->K = K; hp->A = 0; hp->U = U; hp->p = p ? p : K;
+    hp->env = FRIQ_ENV_NONE; hp->qp_reuse = 0; hp->safe_range = 0; hp->ncorner = 0;
+    hp->wsig = 0.05; hp->qdiff_pos = INFINITY; hp->qdiff_neg = -INFINITY;
+    for (int k = 0; k < K; k++) {
+        hp->u0[k] = u[(size_t)k * U];
+        hp->udiv[k] = (u[(size_t)k * U + U - 1] - u[(size_t)k * U]) / (unsigned)(U - 1);
+    }
+    P->alpha = 0.5; P->gamma = 1.0;
+    *out = P;
+    return 0;
+}
+
+/* learning parameters a caller may change between calls on the classic API (public fields of struct frirl_desc) */
+int friq_problem_set_learning_params(friq_problem *P, double qdiff_pos, double qdiff_neg, double wsig, int skip_rules)
+{
+    friq_devprob *hp = &P->hp;
+    if (hp->qdiff_pos == qdiff_pos && hp->qdiff_neg == qdiff_neg && hp->wsig == wsig && hp->skip_rules == skip_rules) return 0;
+    hp->qdiff_pos = qdiff_pos; hp->qdiff_neg = qdiff_neg; hp->wsig = wsig; hp->skip_rules = skip_rules;
+    if (P->device != -1) { DEV(friqd_set_device(P->device)); DEV(friqd_device_sync()); DEV(friqd_h2d(P->dp, hp, sizeof(friq_devprob))); }
+    return 0;
+}
+
 static int problem_upload(friq_problem *P, int device)
 {
     friq_devprob *hp = &P->hp;
@@ -670,7 +702,7 @@ static int ensure(void **p, size_t *cap, size_t need)
 }
 static int percall_buffers(friq_batch *b)
 {
-    const size_t n = (size_t)b->st.n, need_in = n * FRIQ_MAXK * 8, need_out = n * FRIQ_MAXA * 8;
+    const size_t n = (size_t)b->st.n, need_in = n * (2 * FRIQ_MAXK + 4) * 8, need_out = n * (FRIQ_MAXA + 4) * 8;   /* classic step: K + S + 3 in, 4 + A out */
     if (b->cap_in < need_in) {
         size_t c0 = b->cap_in, c1 = b->cap_in, c2 = b->cap_in;
         DEV(ensure((void **)&b->d_in0, &c0, need_in)); DEV(ensure((void **)&b->d_in1, &c1, need_in)); DEV(ensure((void **)&b->d_in2, &c2, need_in));
@@ -732,6 +764,119 @@ int friq_batch_update_sarsa(friq_batch *b, const double *q_ant, const double *re
     DEV(friqd_update_sarsa(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_in1, b->d_in2, NULL));
     DEV(friqd_sync(NULL));
     return 0;
+}
+
+/* one step of the classic API for every agent: proposed action for cur_q_states (forced[i] >= 0: the host's own
+ * random draw, frirl_e_greedy_selection.c:28-34), then frirl_update_sarsa when learn != 0 (frirl_episode.c:148-160).
+ * One H2D, one kernel, one D2H. */
+int friq_batch_classic_step(friq_batch *b, const double *q_ant, const double *reward, const double *cur_q_states, const int *forced,
+                            int learn, int *action, double *actconc, int *rules, int *inserted)
+{
+    const long n = b->st.n; const int S = b->P->hp.S, K = S + 1, A = b->P->hp.A, NIN = K + S + 3, NOUT = 4 + A;
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    int rc = percall_buffers(b); if (rc) return rc;
+    double *h = (double *)malloc(sizeof(double) * n * (NIN > NOUT ? NIN : NOUT));
+    for (long i = 0; i < n; i++) {
+        double *x = h + (size_t)i * NIN;
+        memcpy(x, q_ant + (size_t)i * K, sizeof(double) * K);
+        x[K] = reward[i];
+        memcpy(x + K + 1, cur_q_states + (size_t)i * S, sizeof(double) * S);
+        x[K + 1 + S] = forced ? (double)forced[i] : -1.0;
+        x[K + 2 + S] = learn ? 1.0 : 0.0;
+    }
+    rc = friqd_h2d(b->d_in0, h, 8ul * n * NIN);
+    if (!rc) rc = friqd_classic_step(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_out0, NULL);
+    if (!rc) rc = friqd_d2h(h, b->d_out0, 8ul * n * NOUT);
+    if (!rc)
+        for (long i = 0; i < n; i++) {
+            const double *o = h + (size_t)i * NOUT;
+            if (action) action[i] = (int)o[0];
+            if (rules) rules[i] = (int)o[1];
+            if (inserted) inserted[i] = (int)o[2];
+            if (actconc) memcpy(actconc + (size_t)i * A, o + 4, sizeof(double) * A);
+            if (o[3] != 0.0) { snprintf(g_err, sizeof g_err, "friq_batch_classic_step: agent %ld exceeded the rule capacity %d", i, b->st.cap); rc = 7; }
+        }
+    free(h);
+    if (rc && rc != 7) FAIL(rc, "friq_batch_classic_step: %s", friqd_error_string(rc));
+    return rc;
+}
+
+/* five_rule_distance (FIVE.h:95, five_rule_distance.c:63): ant [n][K] -> dists [n][rule_capacity] (first R valid), hit [n] */
+int friq_batch_rule_distance(friq_batch *b, const double *ant, double *dists, int *hit)
+{
+    const long n = b->st.n; const int K = b->P->hp.K;
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    int rc = percall_buffers(b); if (rc) return rc;
+    DEV(ensure((void **)&b->d_w, &b->cap_w, 8ul * n * b->st.cap));
+    DEV(friqd_h2d(b->d_in0, ant, 8ul * n * K));
+    DEV(friqd_rule_distance(&b->P->hp, b->P->dp, b->st, b->d_in0, b->d_w, b->d_iout, NULL));
+    DEV(friqd_d2h(hit, b->d_iout, 4ul * n));
+    if (dists) {
+        if (n == 1) { int R; DEV(friqd_d2h(&R, b->st.R, sizeof(int))); DEV(friqd_d2h(dists, b->d_w, 8ul * R)); }
+        else DEV(friqd_d2h(dists, b->d_w, 8ul * n * b->st.cap));
+    }
+    return 0;
+}
+
+/* FIVEVagConcl_FRIRL_BestAct (FIVE.h:86, FIVEVagConcl_FRIRL_BestAct.c:56): dists [n][rule_capacity] -> conc [n] */
+int friq_batch_bestact_from_dists(friq_batch *b, const double *dists, double *conc)
+{
+    const long n = b->st.n;
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    int rc = percall_buffers(b); if (rc) return rc;
+    DEV(ensure((void **)&b->d_w, &b->cap_w, 8ul * n * b->st.cap));
+    if (n == 1) { int R; DEV(friqd_d2h(&R, b->st.R, sizeof(int))); DEV(friqd_h2d(b->d_w, dists, 8ul * R)); }
+    else DEV(friqd_h2d(b->d_w, dists, 8ul * n * b->st.cap));
+    DEV(friqd_bestact_dists(&b->P->hp, b->st, b->d_w, b->d_out0, NULL));
+    DEV(friqd_d2h(conc, b->d_out0, 8ul * n));
+    return 0;
+}
+
+/* FIVE_add_rule (FIVE.h:100, five_add_rule.c:47-95) for one agent: append (ant[K] -> q) */
+int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double q)
+{
+    friq_problem *P = b->P; const int K = P->hp.K;
+    if (agent < 0 || agent >= b->st.n) FAIL(5, "friq_batch_append_rule: agent %ld out of range", agent);
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    int R; DEV(friqd_d2h(&R, b->st.R + agent, sizeof(int)));
+    if (R >= b->st.cap) FAIL(5, "friq_batch_append_rule: rule capacity %d exhausted", b->st.cap);
+    unsigned int word = 0; int grew = 0;
+    for (int k = 0; k < K; k++) {
+        const int before = P->hp.dict_len[k];
+        const int j = dict_find_or_add(P, k, ant[k]);
+        if (j < 0) FAIL(5, "friq_batch_append_rule: more than %d distinct antecedent values in dimension %d", FRIQ_MAXDICT, k);
+        grew |= (P->hp.dict_len[k] != before);
+        word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
+    }
+    if (grew) DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob)));
+    const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE) + (size_t)R * FRIQ_TILE;
+    DEV(friqd_h2d(b->st.rbw + off, &word, 4)); DEV(friqd_h2d(b->st.rbq + off, &q, 8));
+    R++;
+    DEV(friqd_h2d(b->st.R + agent, &R, sizeof(int)));
+    { const int unknown = -2; DEV(friqd_h2d(b->st.hitq + agent, &unknown, sizeof(int))); }
+    return 0;
+}
+
+/* five_remove_rule (FIVE.h:97, five_remove_rule.c:29-85) for one agent: later rules move down one slot */
+int friq_batch_remove_rule(friq_batch *b, long agent, int rule)
+{
+    const int K = b->P->hp.K;
+    int R = 0;
+    int rc = friq_batch_get_rulebase(b, agent, &R, NULL, NULL); if (rc) return rc;
+    if (rule < 0 || rule >= R) FAIL(5, "friq_batch_remove_rule: rule %d out of range (rules: %d)", rule, R);
+    double *rant = (double *)malloc(sizeof(double) * (size_t)R * K), *rconc = (double *)malloc(sizeof(double) * R);
+    rc = friq_batch_get_rulebase(b, agent, &R, rant, rconc);
+    if (!rc) {
+        memmove(rant + (size_t)rule * K, rant + (size_t)(rule + 1) * K, sizeof(double) * (size_t)(R - 1 - rule) * K);
+        memmove(rconc + rule, rconc + rule + 1, sizeof(double) * (R - 1 - rule));
+        rc = friq_batch_set_rulebase(b, agent, R - 1, rant, rconc);
+    }
+    free(rant); free(rconc);
+    return rc;
 }
 
 /* ----------------------------------------------------------------------- rule-base files */

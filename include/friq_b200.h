@@ -71,6 +71,11 @@ int friq_device_count(int *count);
  * cartpole.c:252-402); storage is static, valid for the life of the process */
 int friq_problem_desc_builtin(int env, friq_problem_desc *out);
 int friq_problem_create(const friq_problem_desc *desc, friq_problem **out);
+/* FIVEInit (FIVE.h:79, FIVEInit.c:55): a problem from caller-supplied tables u, ve [K][U]; p = 0 means p = K.
+ * No grids / actions / environment: only the FIVE-level per-call entry points apply. */
+int friq_problem_create_from_tables(int K, int U, int p, const double *u, const double *ve, friq_problem **out);
+/* public learning fields of struct frirl_desc a caller may change between calls (frirl_types.h:84-92) */
+int friq_problem_set_learning_params(friq_problem *p, double qdiff_pos, double qdiff_neg, double wsig, int skip_rules);
 void friq_problem_destroy(friq_problem *p);
 /* dims[0..5] = S, K, A, U, p, 2^K */
 int friq_problem_dims(const friq_problem *p, int *dims);
@@ -126,6 +131,20 @@ int friq_batch_vag_concl_weight(friq_batch *b, const double *ant, int *hit, doub
 int friq_batch_get_best_action(friq_batch *b, const double *states, double *actconc, int *best);
 /* frirl_update_sarsa (frirl.h:64, frirl_update_sarsa.c:348): q_ant [n][K], reward [n], cur_q_ant [n][K] */
 int friq_batch_update_sarsa(friq_batch *b, const double *q_ant, const double *reward, const double *cur_q_ant);
+
+/* one step of the classic API per agent (frirl_episode.c:148-160 with HOST environment callbacks): proposed action for
+ * cur_q_states [n][S] (forced[i] >= 0 = the host's own random draw, frirl_e_greedy_selection.c:28-34; NULL = all greedy),
+ * then frirl_update_sarsa(q_ant [n][K], reward [n], cur_q_states + action) when learn != 0.  Outputs may be NULL. */
+int friq_batch_classic_step(friq_batch *b, const double *q_ant, const double *reward, const double *cur_q_states, const int *forced,
+                            int learn, int *action, double *actconc, int *rules, int *inserted);
+/* five_rule_distance (FIVE.h:95, five_rule_distance.c:63): ant [n][K] -> dists [n][rule_capacity], hit [n] (-1 none);
+ * for n == 1 only the first R distances are written */
+int friq_batch_rule_distance(friq_batch *b, const double *ant, double *dists, int *hit);
+/* FIVEVagConcl_FRIRL_BestAct (FIVE.h:86, FIVEVagConcl_FRIRL_BestAct.c:56): dists [n][rule_capacity] -> conc [n] */
+int friq_batch_bestact_from_dists(friq_batch *b, const double *dists, double *conc);
+/* FIVE_add_rule (FIVE.h:100, five_add_rule.c:47) / five_remove_rule (FIVE.h:97, five_remove_rule.c:29) of one agent */
+int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double q);
+int friq_batch_remove_rule(friq_batch *b, long agent, int rule);
 
 /* ---- rule-base files, byte-compatible with frirl_utils.c:100-281 */
 int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double *rant, const double *rconc);

@@ -11,6 +11,8 @@ not exist):
                                    own tests/orig/frirl_example_<env>.frirlrb.txt
                                    (tests/_test.sh:8-17 diffs exactly these).
   tests/golden/<env>.frirlrb.bin   the binary dump (frirl_utils.c:151-203).
+  tests/golden/mountaincar_reduced.frirlrb.txt, mountaincar_reduction.log
+                                   the shipped mountaincar run: reduction of the golden rule base.
   tests/golden/<env>_calls.npz     per-call known-answer vectors recorded by
                                    oracle/ref_harness.c (record stream, see there)
                                    + the md5 of the text golden.
@@ -46,6 +48,18 @@ def main():
                                 md5=np.array(hashlib.md5(txt).hexdigest()))
             print(f"{env}: byte-identical to tests/orig (md5 {hashlib.md5(txt).hexdigest()}), "
                   f"{stream.size} doubles recorded")
+    # mountaincar exactly as shipped (construct_rb = 0, reduce_rb = 1, mountaincar.c:240-242): rule-base REDUCTION
+    # (frirl_sequential_run.c:170-350) of the constructed golden rule base, 110 -> 28 rules
+    exe = os.path.join(HERE, "_ref", "ref_mountaincar_crtrig")
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe], cwd=tmp, check=True, capture_output=True, text=True,
+                           env=dict(os.environ, REF_MODE="shipped", REF_VERBOSE="1",
+                                    REF_RBFILE=os.path.join(out, "mountaincar.frirlrb.bin")))
+        shutil.copy(os.path.join(tmp, "mountaincar.frirlrb.txt"), os.path.join(out, "mountaincar_reduced.frirlrb.txt"))
+        keep = [l for l in r.stdout.splitlines() if l.startswith(("Reduction Episode", "Smallest", "Loaded"))]
+        keep = [l.split(" rules from")[0] if l.startswith("Loaded") else l for l in keep]
+        open(os.path.join(out, "mountaincar_reduction.log"), "w").write("\n".join(keep) + "\n")
+        print(f"mountaincar reduction: {len(open(os.path.join(out, 'mountaincar_reduced.frirlrb.txt')).readlines())} rules, {len(keep)} log lines")
 
 
 if __name__ == "__main__":
