@@ -263,6 +263,93 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-per-action variant of the pass (k_run_steps_w3): the A = 3 actions of a 32-agent tile are
+// evaluated by three warps (lane = agent, warp = action), so an agent's critical path is one chain
+// per rule instead of A.  Each warp walks the whole rule base in rule order for its own action -
+// the sums are accumulated exactly as in friq_best_action_pass - with UNR rules (= UNR independent
+// sqrt / pow / rcp chains) per trip.
+//   conc   Shepard conclusion of this action, or the consequent of the first rule at distance 0
+//   hidx   that rule's index, -1 if none (FIVEVagConcl_FRIRL_BestAct.c:89-93)
+// ---------------------------------------------------------------------------------------
+template <int S, int P, int UNR, bool SAFE>
+__device__ __forceinline__ void friq_action_pass(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, int R,
+                                                 const double *vo_obs, double ave, double &conc, int &hidx)
+{
+    double vagc = 0.0, ws = 0.0;
+    unsigned hi = 0xffffffffu;
+    uint32_t w[UNR]; double q[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) { w[u] = 0; q[u] = 0.0; if (u < R) { w[u] = rbw[(size_t)u * FRIQ_TILE]; q[u] = rbq[(size_t)u * FRIQ_TILE]; } }
+#pragma unroll 1
+    for (int i = 0; i < R; i += UNR) {
+        uint32_t wn[UNR]; double qn[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {                                                       // prefetch the next trip
+            wn[u] = 0; qn[u] = 0.0;
+            if (i + UNR + u < R) { wn[u] = rbw[(size_t)(i + UNR + u) * FRIQ_TILE]; qn[u] = rbq[(size_t)(i + UNR + u) * FRIQ_TILE]; }
+        }
+        double wv[UNR], sv[UNR]; bool z[UNR];
+        unsigned bad = 0;
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            double ssum = 0.0;
+#pragma unroll
+            for (int k = 0; k < S; k++) {
+                const double d = __dsub_rn(vo_obs[k], pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)]);
+                const double d2 = __dmul_rn(d, d);
+                ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                                  // A3/A4
+            }
+            const double da = __dsub_rn(ave, pb.dict_ve[S][(w[u] >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)]);
+            sv[u] = __dadd_rn(__dmul_rn(da, da), ssum);                                      // A5
+            z[u] = friq_is_zero(sv[u]);
+            wv[u] = friq_shepard_weight_fast<P, SAFE>(sv[u], bad, !z[u]);                    // NaN when s == 0: discarded
+        }
+        if (bad) {                                       // rare: an operand outside the proven fast paths -> library routines
+#pragma unroll
+            for (int u = 0; u < UNR; u++) wv[u] = friq_shepard_weight<P>(z[u] ? 1.0 : sv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            if (u == 0 || i + u < R) {
+                hi = min(hi, z[u] ? (unsigned)(i + u) : 0xffffffffu);                        // first hit: rules come in increasing order
+                vagc = __dadd_rn(vagc, __dmul_rn(wv[u], q[u]));                              // BestAct.c:216
+                ws = __dadd_rn(ws, wv[u]);                                                   // :217
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
+    }
+    hidx = (int)hi;
+    conc = (hidx >= 0) ? rbq[(size_t)hidx * FRIQ_TILE] : __ddiv_rn(vagc, ws);               // :265
+}
+
+// Shepard weights wi of Q(s,a) at the previous antecedents vo_q[] (FIVEVagConcl.c:224-235) for the rules this warp
+// owns: blocks of UNR consecutive rules, dealt round-robin to the NW warps of the tile.  The weights go to sw[]; the
+// lead warp adds them up in rule order afterwards (and re-uses them for the weighted update).
+template <int K, int P, int UNR, int NW, bool SAFE>
+__device__ __forceinline__ void friq_q_weights(const friq_devprob &pb, const uint32_t *rbw, double *sw, int R, const double *vo_q,
+                                               bool needq, int wid)
+{
+#pragma unroll 1
+    for (int i = wid * UNR; i < R; i += NW * UNR) {
+        double wq[UNR], sq[UNR];
+        unsigned bad = 0;
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const uint32_t w = (i + u < R) ? rbw[(size_t)(i + u) * FRIQ_TILE] : 0u;
+            sq[u] = friq_dist2<K>(pb, w, vo_q);
+            wq[u] = friq_shepard_weight_fast<P, SAFE>(sq[u], bad, needq && i + u < R && !friq_is_zero(sq[u]));
+        }
+        if (bad) {
+#pragma unroll
+            for (int u = 0; u < UNR; u++) wq[u] = friq_shepard_weight<P>((friq_is_zero(sq[u]) || !needq) ? 1.0 : sq[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) if (needq && i + u < R) sw[(size_t)(i + u) * FRIQ_TILE] = wq[u];
+    }
+}
+
 // first index of the maximum (src/inl/max.inl:16-28, strict <)
 template <int A>
 __device__ __forceinline__ int friq_argmax(const double *v)

@@ -112,7 +112,7 @@ int friqd_sync(void *stream);
 const char *friqd_error_string(int err);
 int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long long seed0, long first_agent,
                       double alpha, double gamma, double epsilon, void *stream);
-int friqd_run_steps(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, void *stream);
+int friqd_run_steps(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, int variant, void *stream);
 int friqd_run_shared(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, long n_steps, int mode, void *stream);
 int friqd_vag_concl(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_conc, int *d_hit,
                     double *d_weights, void *stream);

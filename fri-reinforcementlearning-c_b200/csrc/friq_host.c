@@ -43,6 +43,9 @@ struct friq_batch {
     double *d_srb; int shared_R;   /* shared read-only rule base: rows of (K VE values, consequent) */
     int groups;               /* independent agent groups pipelined on their own streams (hides launch tails) */
     void *gstream[FRIQ_MAXGROUPS], *gdone[FRIQ_MAXGROUPS], *gstart;
+    void *hstream[FRIQ_MAXGROUPS], *hfork[FRIQ_MAXGROUPS], *hjoin[FRIQ_MAXGROUPS];   /* side streams: the light tiles of a group */
+    int variant;              /* kernel of the un-tiled path: 0 one thread per agent, 1 three warps per tile (FRIQ_W3) */
+    int heavy_pct;            /* share of a group's tiles (largest rule bases first) stepped with three warps per tile */
     int *d_work;              /* re-tiling scratch */
     void *d_tmp8, *d_tmp4a, *d_tmp4b;   /* un-permuted result staging */
     int device;
@@ -382,6 +385,8 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     friq_batch *b = (friq_batch *)calloc(1, sizeof *b);
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
     b->retile_interval = 100;
+    { const char *e = getenv("FRIQ_HEAVY_PCT"); b->heavy_pct = e ? atoi(e) : 20; if (b->heavy_pct < 0) b->heavy_pct = 0; if (b->heavy_pct > 100) b->heavy_pct = 100; }
+    { const char *e = getenv("FRIQ_W3"); b->variant = (e && atoi(e) && P->hp.A == 3) ? 1 : 0; }
     {   /* groups of >= 8192 agents, tile aligned; FRIQ_GROUPS overrides (experiments) */
         const char *e = getenv("FRIQ_GROUPS");
         int g = e ? atoi(e) : (int)(n / 32768);
@@ -413,7 +418,11 @@ void friq_batch_destroy(friq_batch *b)
 {
     if (!b) return;
     friqd_set_device(b->device);
-    for (int g = 0; g < FRIQ_MAXGROUPS; g++) { if (b->gstream[g]) friqd_stream_destroy(b->gstream[g]); if (b->gdone[g]) friqd_event_destroy(b->gdone[g]); }
+    for (int g = 0; g < FRIQ_MAXGROUPS; g++) {
+        if (b->gstream[g]) friqd_stream_destroy(b->gstream[g]);
+        if (b->gdone[g]) friqd_event_destroy(b->gdone[g]);
+        if (b->hstream[g]) { friqd_stream_destroy(b->hstream[g]); friqd_event_destroy(b->hfork[g]); friqd_event_destroy(b->hjoin[g]); }
+    }
     if (b->gstart) friqd_event_destroy(b->gstart);
     friqd_free(b->st.sw);
     if (b->d_srb) friqd_free(b->d_srb);
@@ -604,7 +613,10 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         if (!b->have_st2) { int rc = retile(b, 1, stream); if (rc) return rc; rc = retile(b, 0, stream); if (rc) return rc; }  /* allocate buffers */
         if (b->st.prevq && !b->st2.prevq) DEV(friqd_malloc((void **)&b->st2.prevq, (size_t)b->st.n_pad * b->st.cap * 8));
         if (!b->gstart) DEV(friqd_event_create(&b->gstart));
-        for (int g = 0; g < G; g++) if (!b->gstream[g]) { DEV(friqd_stream_create(&b->gstream[g])); DEV(friqd_event_create(&b->gdone[g])); }
+        for (int g = 0; g < G; g++) if (!b->gstream[g]) {
+            DEV(friqd_stream_create(&b->gstream[g])); DEV(friqd_event_create(&b->gdone[g]));
+            DEV(friqd_stream_create(&b->hstream[g])); DEV(friqd_event_create(&b->hfork[g])); DEV(friqd_event_create(&b->hjoin[g]));
+        }
         DEV(friqd_event_record(b->gstart, stream));
         const long tiles = b->st.n_pad / FRIQ_TILE, per = (tiles + G - 1) / G * FRIQ_TILE;
         const size_t wstride = (size_t)b->st.cap + 2 + per;
@@ -617,7 +629,22 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
                 if (cnt <= 0) continue;
                 friq_devstate src = state_view(&b->st, lo, cnt), dst = state_view(&b->st2, lo, cnt);
                 DEV(friqd_retile(src, dst, b->d_work + g * wstride, 1, b->gstream[g]));
-                DEV(friqd_run_steps(&b->P->hp, b->P->dp, dst, m, mode, b->gstream[g]));
+                /* The rule-count distribution is heavy-tailed and a launch lasts as long as its slowest warp: the tiles
+                 * with the largest rule bases (they come first after the sort) are stepped with three warps per tile,
+                 * which shortens their critical path ~2x; the bulk keeps the cheaper one-thread-per-agent kernel and
+                 * runs beside them on a side stream. */
+                long heavy = (b->P->hp.A == 3) ? (cnt / FRIQ_TILE * b->heavy_pct + 99) / 100 * FRIQ_TILE : 0;
+                if (heavy > cnt) heavy = cnt;
+                if (heavy > 0 && heavy < cnt) {
+                    friq_devstate hv = state_view(&b->st2, lo, heavy), lt = state_view(&b->st2, lo + heavy, cnt - heavy);
+                    DEV(friqd_event_record(b->hfork[g], b->gstream[g]));
+                    DEV(friqd_stream_wait_event(b->hstream[g], b->hfork[g]));
+                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, hv, m, mode, 1, b->gstream[g]));
+                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, lt, m, mode, 0, b->hstream[g]));
+                    DEV(friqd_event_record(b->hjoin[g], b->hstream[g]));
+                    DEV(friqd_stream_wait_event(b->gstream[g], b->hjoin[g]));
+                } else
+                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, dst, m, mode, heavy > 0, b->gstream[g]));
             }
             friq_devstate t = b->st; b->st = b->st2; b->st2 = t;
             b->permuted = 1 + G;
@@ -626,7 +653,7 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         return 0;
     }
     if (mode & FRIQ_RUN_RETILE) { int rc = retile(b, 1, stream); if (rc) return rc; }
-    DEV(friqd_run_steps(&b->P->hp, b->P->dp, b->st, n_steps, mode, stream));
+    DEV(friqd_run_steps(&b->P->hp, b->P->dp, b->st, n_steps, mode, b->variant, stream));
     return 0;
 }
 int friq_batch_set_retile_interval(friq_batch *b, long steps) { b->retile_interval = steps; return 0; }

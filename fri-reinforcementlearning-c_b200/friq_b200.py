@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfriq_b200.so")
+LIB_PATH = os.environ.get("FRIQ_LIB") or os.path.join(HERE, "libfriq_b200.so")   # FRIQ_LIB: build variants in experiments
 
 ENV_MOUNTAINCAR, ENV_ACROBOT, ENV_CARTPOLE = 0, 1, 2
 ENV_ID = {"mountaincar": 0, "acrobot": 1, "cartpole": 2}
@@ -41,6 +41,8 @@ SYMBOLS = {
     "friq_device_count": (C.c_int, [ip]),
     "friq_problem_desc_builtin": (C.c_int, [C.c_int, C.POINTER(ProblemDesc)]),
     "friq_problem_create": (C.c_int, [C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]),
+    "friq_problem_create_from_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_void_p)]),
+    "friq_problem_set_learning_params": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int]),
     "friq_problem_destroy": (None, [C.c_void_p]),
     "friq_problem_dims": (C.c_int, [C.c_void_p, ip]),
     "friq_problem_tables": (C.c_int, [C.c_void_p, dp, dp, dp, dp, dp]),
@@ -65,6 +67,11 @@ SYMBOLS = {
     "friq_batch_vag_concl_weight": (C.c_int, [C.c_void_p, dp, ip, dp]),
     "friq_batch_get_best_action": (C.c_int, [C.c_void_p, dp, dp, ip]),
     "friq_batch_update_sarsa": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "friq_batch_classic_step": (C.c_int, [C.c_void_p, dp, dp, dp, ip, C.c_int, ip, dp, ip, ip]),
+    "friq_batch_rule_distance": (C.c_int, [C.c_void_p, dp, dp, ip]),
+    "friq_batch_bestact_from_dists": (C.c_int, [C.c_void_p, dp, dp]),
+    "friq_batch_append_rule": (C.c_int, [C.c_void_p, C.c_long, dp, C.c_double]),
+    "friq_batch_remove_rule": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
     "friq_save_rb_to_text_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
     "friq_save_rb_to_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
     "friq_load_rb_from_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, ip, dp, dp]),
