@@ -83,6 +83,13 @@ __device__ __forceinline__ double friq_shepard_weight(double s)
     const double d = __dsqrt_rn(s);                       // vsqrtpd, five_rule_distance.c:205
     return __drcp_rn(friq_pow_x87<P>(d));                 // 1.0 / fast_pow(|d|, p)
 }
+// the same as a real call: the fall-back of the fused kernels' fast paths is rare, and inlining the library sqrt / rcp
+// and the power filter once per chain made those kernels ~100 KB of code (instruction-cache misses in the hot loop)
+template <int P>
+__device__ __noinline__ double friq_shepard_weight_slow(double s)
+{
+    return friq_shepard_weight<P>(s);
+}
 // same value, branch-free; bad != 0 => not proven, recompute with friq_shepard_weight
 template <int P, bool SAFE>
 __device__ __forceinline__ double friq_shepard_weight_fast(double s, unsigned &bad, bool live = true)
@@ -148,6 +155,68 @@ __device__ __forceinline__ bool friq_is_zero(double x)      // x == 0.0 for x >=
     return ((unsigned)__double2hiint(x) | (unsigned)__double2loint(x)) == 0u;
 }
 
+// one trip of the pass: UNR rules x ACH actions (+ UNR chains of Q(s,a) when QCH), all chains evaluated together
+// stage by stage (friq_shepard_weights_n); the sums are then added in rule order
+template <int S, int P, int ACH, bool QCH, int UNR, bool SAFE>
+__device__ __forceinline__ void friq_pass_trip(const friq_devprob &pb, const uint32_t (&w)[UNR], const double (&q)[UNR], int i, int R,
+                                               const double *vo_obs, const double (&ave)[ACH], const double *vo_q, bool needq, double *sw,
+                                               double (&vagc)[ACH], double (&ws)[ACH], unsigned (&hi)[ACH], double &vagq, double &wsq)
+{
+    constexpr int NA = UNR * ACH, NC = NA + (QCH ? UNR : 0);
+    double sv[NC], wv[NC];
+    bool live[NC];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+        double ssum = 0.0, sq = 0.0;
+#pragma unroll
+        for (int k = 0; k < S; k++) {
+            const double v = pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+            const double d = __dsub_rn(vo_obs[k], v);
+            const double d2 = __dmul_rn(d, d);
+            ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                              // A3/A4
+            if (QCH) {
+                const double e = __dsub_rn(vo_q[k], v);
+                const double e2 = __dmul_rn(e, e);
+                sq = (k == 0) ? e2 : __dadd_rn(sq, e2);
+            }
+        }
+        const double va = pb.dict_ve[S][(w[u] >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)];
+#pragma unroll
+        for (int a = 0; a < ACH; a++) {
+            const double da = __dsub_rn(ave[a], va);
+            sv[u * ACH + a] = __dadd_rn(__dmul_rn(da, da), ssum);                    // A5
+            live[u * ACH + a] = !friq_is_zero(sv[u * ACH + a]);                      // s == 0: exact hit, weight discarded (NaN)
+        }
+        if (QCH) {
+            const double e = __dsub_rn(vo_q[S], va);
+            sv[NA + u] = __dadd_rn(sq, __dmul_rn(e, e));
+            live[NA + u] = needq && !friq_is_zero(sv[NA + u]);
+        }
+    }
+    unsigned bad = 0;
+    friq_shepard_weights_n<P, SAFE, NC>(sv, wv, bad, live);
+    if (bad) {                                           // rare: an operand outside the proven fast paths -> library routines
+#pragma unroll
+        for (int n = 0; n < NC; n++) wv[n] = friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+        if (u == 0 || i + u < R) {
+#pragma unroll
+            for (int a = 0; a < ACH; a++) {
+                hi[a] = min(hi[a], live[u * ACH + a] ? 0xffffffffu : (unsigned)(i + u));  // first hit (BestAct.c:89-93): rules come in order
+                vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u * ACH + a], q[u]));       // BestAct.c:216
+                ws[a] = __dadd_rn(ws[a], wv[u * ACH + a]);                            // :217
+            }
+            if (QCH) {
+                if (needq) sw[(size_t)(i + u) * FRIQ_TILE] = wv[NA + u];
+                vagq = __dadd_rn(vagq, __dmul_rn(wv[NA + u], q[u]));                  // FIVEVagConcl.c:234
+                wsq = __dadd_rn(wsq, wv[NA + u]);                                     // :235
+            }
+        }
+    }
+}
+
 template <int S, int P, int A, int ACH, bool WITHQ, int UNR, bool SAFE>
 __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
                                                       const double *vo_obs, double *actconc, int *hidx,
@@ -158,9 +227,9 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
 #pragma unroll 1
     for (int c0 = 0; c0 < A; c0 += ACH) {
         double vagc[ACH], ws[ACH], ave[ACH];
-        int hi[ACH];
+        unsigned hi[ACH];
 #pragma unroll
-        for (int a = 0; a < ACH; a++) { vagc[a] = 0.0; ws[a] = 0.0; hi[a] = -1; ave[a] = pb.act_ve[c0 + a]; }
+        for (int a = 0; a < ACH; a++) { vagc[a] = 0.0; ws[a] = 0.0; hi[a] = 0xffffffffu; ave[a] = pb.act_ve[c0 + a]; }
         uint32_t w[UNR]; double q[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) { w[u] = 0; q[u] = 0.0; if (u < R) { w[u] = rbw[(size_t)u * FRIQ_TILE]; q[u] = rbq[(size_t)u * FRIQ_TILE]; } }
@@ -172,93 +241,17 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
                 wn[u] = 0; qn[u] = 0.0;
                 if (i + UNR + u < R) { wn[u] = rbw[(size_t)(i + UNR + u) * FRIQ_TILE]; qn[u] = rbq[(size_t)(i + UNR + u) * FRIQ_TILE]; }
             }
-            double wv[UNR][ACH], wq[UNR];
-            bool z[UNR][ACH];
-            unsigned bad = 0;
-#pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                double ssum = 0.0, sq = 0.0;
-#pragma unroll
-                for (int k = 0; k < S; k++) {
-                    const double v = pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
-                    const double d = __dsub_rn(vo_obs[k], v);
-                    const double d2 = __dmul_rn(d, d);
-                    ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                              // A3/A4
-                    if (WITHQ) {
-                        const double e = __dsub_rn(vo_q[k], v);
-                        const double e2 = __dmul_rn(e, e);
-                        sq = (k == 0) ? e2 : __dadd_rn(sq, e2);
-                    }
-                }
-                const double va = pb.dict_ve[S][(w[u] >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)];
-#pragma unroll
-                for (int a = 0; a < ACH; a++) {
-                    const double da = __dsub_rn(ave[a], va);
-                    const double s = __dadd_rn(__dmul_rn(da, da), ssum);                     // A5
-                    z[u][a] = friq_is_zero(s);
-                    wv[u][a] = friq_shepard_weight_fast<P, SAFE>(s, bad, !z[u][a]);             // NaN when s == 0: discarded
-                }
-                if (WITHQ) {
-                    if (c0 == 0) {
-                        const double e = __dsub_rn(vo_q[S], va);
-                        sq = __dadd_rn(sq, __dmul_rn(e, e));
-                        wq[u] = friq_shepard_weight_fast<P, SAFE>(sq, bad, needq && !friq_is_zero(sq));
-                    }
-                }
-            }
-            if (bad) {                                   // rare: an operand outside the proven fast paths -> library routines
-#pragma unroll
-                for (int u = 0; u < UNR; u++) {
-                    double v[S + 1];
-#pragma unroll
-                    for (int k = 0; k <= S; k++) v[k] = pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
-                    double ssum = 0.0, sq = 0.0;
-#pragma unroll
-                    for (int k = 0; k < S; k++) {
-                        const double d = __dsub_rn(vo_obs[k], v[k]);
-                        ssum = (k == 0) ? __dmul_rn(d, d) : __dadd_rn(ssum, __dmul_rn(d, d));
-                        if (WITHQ) { const double e = __dsub_rn(vo_q[k], v[k]); sq = (k == 0) ? __dmul_rn(e, e) : __dadd_rn(sq, __dmul_rn(e, e)); }
-                    }
-#pragma unroll
-                    for (int a = 0; a < ACH; a++) {
-                        const double da = __dsub_rn(ave[a], v[S]);
-                        const double s = __dadd_rn(__dmul_rn(da, da), ssum);
-                        wv[u][a] = friq_shepard_weight<P>(z[u][a] ? 1.0 : s);
-                    }
-                    if (WITHQ) {
-                        if (c0 == 0) {
-                            const double e = __dsub_rn(vo_q[S], v[S]);
-                            sq = __dadd_rn(sq, __dmul_rn(e, e));
-                            wq[u] = friq_shepard_weight<P>((friq_is_zero(sq) || !needq) ? 1.0 : sq);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                if (u == 0 || i + u < R) {
-#pragma unroll
-                    for (int a = 0; a < ACH; a++) {
-                        if (z[u][a] && hi[a] < 0) hi[a] = i + u;                              // BestAct.c:89-93
-                        vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u][a], q[u]));              // BestAct.c:216
-                        ws[a] = __dadd_rn(ws[a], wv[u][a]);                                   // :217
-                    }
-                    if (WITHQ) {
-                        if (c0 == 0) {
-                            if (needq) sw[(size_t)(i + u) * FRIQ_TILE] = wq[u];
-                            vagq = __dadd_rn(vagq, __dmul_rn(wq[u], q[u]));                   // FIVEVagConcl.c:234
-                            wsq = __dadd_rn(wsq, wq[u]);                                      // :235
-                        }
-                    }
-                }
-            }
+            if (WITHQ && (A == ACH || c0 == 0))
+                friq_pass_trip<S, P, ACH, true, UNR, SAFE>(pb, w, q, i, R, vo_obs, ave, vo_q, needq, sw, vagc, ws, hi, vagq, wsq);
+            else
+                friq_pass_trip<S, P, ACH, false, UNR, SAFE>(pb, w, q, i, R, vo_obs, ave, vo_q, needq, sw, vagc, ws, hi, vagq, wsq);
 #pragma unroll
             for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
         }
 #pragma unroll
         for (int a = 0; a < ACH; a++) {
-            hidx[c0 + a] = hi[a];
-            actconc[c0 + a] = (hi[a] >= 0) ? rbq[(size_t)hi[a] * FRIQ_TILE] : __ddiv_rn(vagc[a], ws[a]);   // :265
+            hidx[c0 + a] = (int)hi[a];
+            actconc[c0 + a] = ((int)hi[a] >= 0) ? rbq[(size_t)hi[a] * FRIQ_TILE] : __ddiv_rn(vagc[a], ws[a]);   // :265
         }
     }
 }
@@ -307,7 +300,7 @@ __device__ __forceinline__ void friq_action_pass(const friq_devprob &pb, const u
         }
         if (bad) {                                       // rare: an operand outside the proven fast paths -> library routines
 #pragma unroll
-            for (int u = 0; u < UNR; u++) wv[u] = friq_shepard_weight<P>(z[u] ? 1.0 : sv[u]);
+            for (int u = 0; u < UNR; u++) wv[u] = friq_shepard_weight_slow<P>(z[u] ? 1.0 : sv[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
@@ -343,11 +336,53 @@ __device__ __forceinline__ void friq_q_weights(const friq_devprob &pb, const uin
         }
         if (bad) {
 #pragma unroll
-            for (int u = 0; u < UNR; u++) wq[u] = friq_shepard_weight<P>((friq_is_zero(sq[u]) || !needq) ? 1.0 : sq[u]);
+            for (int u = 0; u < UNR; u++) wq[u] = friq_shepard_weight_slow<P>((friq_is_zero(sq[u]) || !needq) ? 1.0 : sq[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) if (needq && i + u < R) sw[(size_t)(i + u) * FRIQ_TILE] = wq[u];
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Cooperative Q(s,a) (FIVEVagConcl.c:224-235) for the FEW lanes of a warp whose pending update has no exact-hit rule.
+// Once learning is under way only 1-2 % of the agent-steps need these Shepard sums, but a third of the warp-steps
+// contain at least one such lane; carrying the Q(s,a) chain inside the pass (WITHQ) then makes all 32 lanes pay a
+// fourth chain per rule for the sake of one.  Here the needy agents are served one after the other: all lanes of the
+// warp compute the weights of THAT agent's rules in parallel (lane r takes rules r, r + n, ...) and write them to
+// sw[]; the owning lane then adds them up in rule order, so the sums are bit-identical to the sequential loop.
+//   wmask  lanes of the warp taking part, qm  lanes that need Q(s,a)
+//   rbw / rbq / sw point at the calling lane's column of the tile ([slot][FRIQ_TILE])
+// ---------------------------------------------------------------------------------------
+template <int K, int P, bool SAFE>
+__device__ __forceinline__ void friq_q_cooperative(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
+                                                   const double *vo_q, unsigned wmask, unsigned qm, double &vagq, double &wsq)
+{
+    const int lane = threadIdx.x & 31;
+    const int nw = __popc(wmask), rank = __popc(wmask & ((1u << lane) - 1u));
+    const uint32_t *tw = rbw - lane;                     // column 0 of the tile
+    double *tsw = sw - lane;
+    for (unsigned m = qm; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const int Rj = __shfl_sync(wmask, R, j);
+        double vj[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) vj[k] = __shfl_sync(wmask, vo_q[k], j);
+        for (int i = rank; i < Rj; i += nw) {
+            const double sq = friq_dist2<K>(pb, tw[(size_t)i * FRIQ_TILE + j], vj);
+            unsigned bad = 0;
+            double wq = friq_shepard_weight_fast<P, SAFE>(sq, bad);      // sq != 0: the agent has no rule at this point
+            if (bad) wq = friq_shepard_weight_slow<P>(sq);
+            tsw[(size_t)i * FRIQ_TILE + j] = wq;
+        }
+    }
+    __syncwarp(wmask);                                   // the weights written by the other lanes are visible
+    vagq = 0.0; wsq = 0.0;
+    if ((qm >> lane) & 1u)
+        for (int i = 0; i < R; i++) {
+            const double wi = sw[(size_t)i * FRIQ_TILE];
+            vagq = __dadd_rn(vagq, __dmul_rn(wi, rbq[(size_t)i * FRIQ_TILE]));     // FIVEVagConcl.c:234
+            wsq = __dadd_rn(wsq, wi);                                              // :235
+        }
 }
 
 // first index of the maximum (src/inl/max.inl:16-28, strict <)

@@ -26,6 +26,9 @@
 #ifndef FRIQ_MINB
 #define FRIQ_MINB 2
 #endif
+#ifndef FRIQ_QCOOP_MAX
+#define FRIQ_QCOOP_MAX 8     /* fewer lanes than this needing Q(s,a): friq_q_cooperative instead of the WITHQ pass */
+#endif
 
 struct __align__(16) friq_smem_t {
     unsigned char prob[FRIQ_DEVPROB_SMEM_BYTES];
@@ -114,10 +117,13 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         if (upd && (hitq == -2 || !pb.qp_reuse)) hitq = friq_first_hit<K>(pb, rbw, R, vo);
         const bool needq = upd && hitq < 0;
         double actconc[A], vagq, wsq; int hidx[A];
-        if (__any_sync(wmask, needq))
+        const unsigned qm = __ballot_sync(wmask, needq);
+        if (__popc(qm) >= FRIQ_QCOOP_MAX)                // many lanes need Q(s,a): its chain rides in the pass
             friq_best_action_pass<S, P, A, ACH, true, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, needq, vagq, wsq);
-        else
+        else {                                           // none or a few: the warp serves them one by one
             friq_best_action_pass<S, P, A, ACH, false, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, false, vagq, wsq);
+            if (qm) friq_q_cooperative<K, P, SAFE>(pb, rbw, rbq, sw, R, vo, wmask, qm, vagq, wsq);
+        }
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }

@@ -385,7 +385,7 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     friq_batch *b = (friq_batch *)calloc(1, sizeof *b);
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
     b->retile_interval = 100;
-    { const char *e = getenv("FRIQ_HEAVY_PCT"); b->heavy_pct = e ? atoi(e) : 20; if (b->heavy_pct < 0) b->heavy_pct = 0; if (b->heavy_pct > 100) b->heavy_pct = 100; }
+    { const char *e = getenv("FRIQ_HEAVY_PCT"); b->heavy_pct = e ? atoi(e) : 0; if (b->heavy_pct < 0) b->heavy_pct = 0; if (b->heavy_pct > 100) b->heavy_pct = 100; }
     { const char *e = getenv("FRIQ_W3"); b->variant = (e && atoi(e) && P->hp.A == 3) ? 1 : 0; }
     {   /* groups of >= 8192 agents, tile aligned; FRIQ_GROUPS overrides (experiments) */
         const char *e = getenv("FRIQ_GROUPS");
