@@ -195,9 +195,9 @@ __device__ __forceinline__ void friq_pass_trip(const friq_devprob &pb, const uin
     }
     unsigned bad = 0;
     friq_shepard_weights_n<P, SAFE, NC>(sv, wv, bad, live);
-    if (bad) {                                           // rare: an operand outside the proven fast paths -> library routines
+    if (bad) {                                           // rare: a chain outside the proven fast paths -> library routines, that chain only
 #pragma unroll
-        for (int n = 0; n < NC; n++) wv[n] = friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
+        for (int n = 0; n < NC; n++) if ((bad >> n) & 1u) wv[n] = friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
     }
 #pragma unroll
     for (int u = 0; u < UNR; u++) {
