@@ -124,7 +124,10 @@ def main():
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "mountaincar FRIQ-learning (reference C/AVX2 build, no_random=1), independent agents on all host cores",
+            "config": {"workload": WORKLOAD, "agents_per_gpu": args.agents, "env_steps_per_agent_per_step": args.chunk,
+                       "reference_arm": "the unmodified reference (oracle/_ref, C + AVX2 inline asm, -O2 -mavx2) on all host cores: one process per "
+                                        "core stepping independent single agents through frirl_episode(); a bounded sample of the workload "
+                                        "(no_random = 1: the reference's libc rand() stream is unseedable)",
                        "steps_per_agent": steps_per_agent},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -149,6 +152,7 @@ def main():
     b = fq.Batch(P, n, 192, device=local, seed0=0x5EED0000, first_agent=first_agent)
     b.set_retile_interval(args.retile)
     launches_per_step = (-(-args.chunk // args.retile) if args.retile > 0 else 1)
+    groups = int(os.environ.get("FRIQ_GROUPS", 0)) or min(8, max(1, n // 32768))     # friq_batch_create: agent groups on their own streams
     mode = fq.RUN_LEARN | fq.RUN_RETILE      # agents are re-assigned to warps by rule count before every launch
 
     # device-side result buffers for the NCCL gather of per-agent (return f64, steps i32, rules i32)
@@ -172,12 +176,12 @@ def main():
 
     def timed(step_fn):
         b.reset()
+        clk = ClockSampler(local) if rank == 0 else None     # nvidia-smi needs ~100 ms to start: sample from the warm-up on (same load)
         for _ in range(args.warmup):
             step_fn()
         o0 = b.gather()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        clk = ClockSampler(local) if rank == 0 else None
         e0.record(stream)
         for _ in range(args.steps):
             step_fn()
@@ -229,6 +233,12 @@ def main():
     ach_gbs = bytes_alg / t / 1e9
     frac_fp64 = ach_tflops / (fp64_peak_g / 1e3); frac_hbm = ach_gbs / hbm_peak
 
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (profiles/), or null
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))["k_run_steps"]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -245,18 +255,20 @@ def main():
         "five_evals_per_sec": value * EVALS_PER_STEP,
         "e2e": {"value": nsteps_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 16 * n,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": args.steps * (5 * launches_per_step + 3),   # per launch: 4 re-tiling kernels + k_run_steps; per step: 3 result un-permute kernels
-        
+        # per group and launch: 4 re-tiling kernels (histogram, scan, assign, move) + k_run_steps; per step: 3 result un-permute kernels
+        "gpu_launches": args.steps * (5 * launches_per_step * groups + 3),
         "clocks": clocks,
         "roofline": {"bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",
                      "achieved": ach_tflops if frac_fp64 >= frac_hbm else ach_gbs,
                      "peak": fp64_peak_g / 1e3 if frac_fp64 >= frac_hbm else hbm_peak,
                      "unit": "TFLOP/s" if frac_fp64 >= frac_hbm else "GB/s",
-                     "frac": max(frac_fp64, frac_hbm), "traffic": None,
+                     "frac": max(frac_fp64, frac_hbm), "traffic": traffic,
                      "kernel": "k_run_steps<2,3,3,3,mountaincar>",
                      "note": "algorithmic FP64 ops of the reference path (SURVEY 8d: 82*R per env step, sqrt and / counted as 1) over the "
                              "measured non-FMA FP64 issue rate of this GPU (friq_device_fp64_peak, DADD/DMUL lane-ops/s); "
-                             "hbm view: %.1f GB/s algorithmic of %.0f GB/s measured = %.3f" % (ach_gbs, hbm_peak, frac_hbm)},
+                             "hbm view: %.1f GB/s algorithmic of %.0f GB/s measured = %.3f; achieved is over the whole timed step "
+                             "(re-tiling + result gather included, k_run_steps is > 97 %% of it: profiles/)" % (ach_gbs, hbm_peak, frac_hbm)},
+        "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": frac_hbm, "traffic": traffic},
     }
     if not args.no_cpu_baseline and world == 1:
         try:

@@ -385,6 +385,160 @@ __device__ __forceinline__ void friq_q_cooperative(const friq_devprob &pb, const
         }
 }
 
+// ---------------------------------------------------------------------------------------
+// Exact hits first (FIVEVagConcl_FRIRL_BestAct.c:89-93, FIVEVagConcl.c:96-105): the reference returns the consequent
+// of the first rule at distance 0 and never evaluates the Shepard sums then.  Once an agent has learned for a while
+// almost every (observation, action) pair it visits has such a rule (mountaincar: 92-98 %), so evaluating all A
+// Shepard chains for all 32 lanes and discarding most of them wastes the FP64 pipe.  When the problem block says
+// that distance 0 is the same as equal dictionary indices (hit_scan), a first sweep compares packed rule words with
+// the packed (observation, action) targets - one integer compare per rule and action - and only the pairs WITHOUT a
+// hit go on to the Shepard sums: cooperatively when they are few (friq_actions_cooperative), through the lock-step
+// pass when they are many.
+// ---------------------------------------------------------------------------------------
+#define FRIQ_NO_TARGET 0xfffffffeu                      /* never equals a packed rule word (K * 6 <= 30 bits) nor the padding word */
+
+// packed dictionary indices of the observation with VE values vo[] (grid indices ci[k] when known), or FRIQ_NO_TARGET when
+// some dimension's VE value is no dictionary entry's (then no rule can be at distance 0)
+template <int S>
+__device__ __forceinline__ uint32_t friq_obs_word(const friq_devprob &pb, const double *vo, const int *ci)
+{
+    uint32_t word = 0; bool ok = true;
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+        int j = ci[k];
+        if (j < 0) { for (int t = 0; t < pb.dict_len[k]; t++) if (pb.dict_ve[k][t] == vo[k]) { j = t; break; } }
+        ok = ok && j >= 0;
+        word |= (uint32_t)(j & (FRIQ_MAXDICT - 1)) << (FRIQ_IDX_BITS * k);
+    }
+    return ok ? word : FRIQ_NO_TARGET;
+}
+
+// first rule equal to each target word, -1 if none
+template <int A>
+__device__ __forceinline__ void friq_hit_scan(const uint32_t *rbw, int R, const uint32_t (&tgt)[A], int (&hidx)[A])
+{
+    unsigned hi[A];
+#pragma unroll
+    for (int a = 0; a < A; a++) hi[a] = 0xffffffffu;
+#pragma unroll 1
+    for (int i = 0; i < R; i += 4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) w[u] = (i + u < R) ? rbw[(size_t)(i + u) * FRIQ_TILE] : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int a = 0; a < A; a++) hi[a] = min(hi[a], (w[u] == tgt[a]) ? (unsigned)(i + u) : 0xffffffffu);
+    }
+#pragma unroll
+    for (int a = 0; a < A; a++) hidx[a] = (int)hi[a];
+}
+
+// Shepard sums of the (lane, channel) pairs that have no exact-hit rule - COMPACTED onto the lanes of the warp.
+//   channels 0 .. A-1  the conclusion of action a at the current observation vo_obs[] (BestAct.c:212-217, :265), pairs nm[a]
+//   channel  A         Q(s,a) of the pending update at the previous antecedents vo_q[] (FIVEVagConcl.c:224-235), lanes qm;
+//                      its weights are also written to sw[] for the weighted update
+// The lock-step pass spends A chains per rule on every lane although, once learning is under way, only a few of the warp's
+// 32 * (A + 1) pairs still need Shepard sums.  Here pair number p of the warp is handed to lane p: the lane fetches the
+// owner's point (shuffles), walks the OWNER's rule-base column - the 32 columns of a tile share their cache lines row by
+// row, so these reads stay coalesced - and accumulates the sums sequentially in its own registers exactly like the
+// lock-step pass does (UNR rules = UNR independent chains per trip, friq_shepard_weights_n).  One round serves as many
+// pairs as the warp has lanes for the price of ONE chain per rule; the owners then pick their results up with a shuffle.  Bit-identical sums.
+template <int S, int P, int A, int UNR, bool SAFE>
+__device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
+                                                     const double *vo_obs, const double *vo_q, unsigned wmask, const unsigned (&nm)[A], unsigned qm,
+                                                     double (&conc)[A], double &vagq, double &wsq)
+{
+    constexpr int K = S + 1, C = A + 1;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t *tw = rbw - lane;                     // column 0 of the tile
+    const double *tq = rbq - lane;
+    double *tsw = sw - lane;
+    unsigned chm[C]; int ofs[C + 1];
+#pragma unroll
+    for (int a = 0; a < A; a++) chm[a] = nm[a];
+    chm[A] = qm;
+    ofs[0] = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) ofs[c + 1] = ofs[c] + __popc(chm[c]);
+    const int np = ofs[C];
+    vagq = 0.0; wsq = 0.0;
+    const int nw = __popc(wmask), rank = __popc(wmask & lt);          // the last warp of a batch may be partial
+    for (int p0 = 0; p0 < np; p0 += nw) {
+        // ---- which pair is mine?  channel c, owner lane j
+        const int p = p0 + rank;
+        int c = 0, j = 0;
+        const bool has = p < np;
+#pragma unroll
+        for (int t = 0; t < C; t++) if (has && p >= ofs[t]) { c = t; }
+        unsigned mask_c = chm[0];
+#pragma unroll
+        for (int t = 1; t < C; t++) if (c == t) mask_c = chm[t];
+        int base_c = 0;
+#pragma unroll
+        for (int t = 1; t < C; t++) if (c == t) base_c = ofs[t];
+        if (has) j = __fns(mask_c, 0, p - base_c + 1);   // lane of the (p - base_c)-th set bit
+        // ---- the owner's point and rule count
+        double pt[K];
+#pragma unroll
+        for (int k = 0; k < S; k++) {
+            const double x = __shfl_sync(wmask, vo_obs[k], j), y = __shfl_sync(wmask, vo_q[k], j);
+            pt[k] = (c == A) ? y : x;
+        }
+        {
+            const double y = __shfl_sync(wmask, vo_q[S], j);
+            pt[S] = (c == A) ? y : pb.act_ve[c < A ? c : 0];
+        }
+        const int Rj = __shfl_sync(wmask, R, j);
+        const int Rp = has ? Rj : 0;
+        const bool isq = has && c == A;
+        // ---- sequential Shepard sums over the owner's rules, UNR rules per trip
+        double vag = 0.0, ws = 0.0;
+        uint32_t w[UNR]; double q[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) { w[u] = 0; q[u] = 0.0; if (u < Rp) { w[u] = tw[(size_t)u * FRIQ_TILE + j]; q[u] = tq[(size_t)u * FRIQ_TILE + j]; } }
+#pragma unroll 1
+        for (int i = 0; i < Rp; i += UNR) {
+            uint32_t wn[UNR]; double qn[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                wn[u] = 0; qn[u] = 0.0;
+                if (i + UNR + u < Rp) { wn[u] = tw[(size_t)(i + UNR + u) * FRIQ_TILE + j]; qn[u] = tq[(size_t)(i + UNR + u) * FRIQ_TILE + j]; }
+            }
+            double sv[UNR], wv[UNR]; bool live[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) { sv[u] = friq_dist2<K>(pb, w[u], pt); live[u] = i + u < Rp; }   // != 0 for real rules: no exact hit
+            unsigned bad = 0;
+            friq_shepard_weights_n<P, SAFE, UNR>(sv, wv, bad, live);
+            if (bad) {
+#pragma unroll
+                for (int u = 0; u < UNR; u++) if ((bad >> u) & 1u) wv[u] = friq_shepard_weight_slow<P>(live[u] ? sv[u] : 1.0);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                if (u == 0 || i + u < Rp) {
+                    if (isq) tsw[(size_t)(i + u) * FRIQ_TILE + j] = wv[u];
+                    vag = __dadd_rn(vag, __dmul_rn(wv[u], q[u]));                             // BestAct.c:216 / FIVEVagConcl.c:234
+                    ws = __dadd_rn(ws, wv[u]);                                                // :217 / :235
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
+        }
+        const double res = __ddiv_rn(vag, ws);                                               // BestAct.c:265
+        // ---- hand the results back to the owners
+#pragma unroll
+        for (int t = 0; t < C; t++) {
+            const int src = ofs[t] + __popc(chm[t] & lt) - p0;       // rank of the lane that holds my pair of channel t (if I have one in this round)
+            const bool mine = ((chm[t] >> lane) & 1u) && src >= 0 && src < nw;
+            const int sl = mine ? __fns(wmask, 0, src + 1) : lane;
+            if (t < A) { const double r = __shfl_sync(wmask, res, sl); if (mine) conc[t < A ? t : 0] = r; }
+            else { const double a1 = __shfl_sync(wmask, vag, sl), a2 = __shfl_sync(wmask, ws, sl); if (mine) { vagq = a1; wsq = a2; } }
+        }
+    }
+}
+
 // first index of the maximum (src/inl/max.inl:16-28, strict <)
 template <int A>
 __device__ __forceinline__ int friq_argmax(const double *v)

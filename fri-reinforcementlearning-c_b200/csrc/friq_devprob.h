@@ -40,10 +40,13 @@ enum { FRIQ_M_LEARN = 1, FRIQ_M_TRACK = 2, FRIQ_M_STOP_ON_CONVERGE = 4, FRIQ_M_S
 typedef struct friq_devprob {
     int S, K, A, U, p, env, skip_rules, no_random;
     int max_steps, max_episodes, qp_reuse, ncorner;
-    int safe_range, pad1, pad2, pad3;         /* all squared distances in {0} U [2^-200, 2^200] (host-verified) */
+    int safe_range, hit_scan, pad2, pad3;     /* safe_range: all squared distances in {0} U [2^-200, 2^200] (host-verified);
+                                               * hit_scan: distance 0 <=> equal dictionary indices (VE values of distinct dictionary
+                                               * entries differ in every dimension), so exact hits can be found by comparing packed words */
     int grid_len[FRIQ_MAXK];
     int dict_len[FRIQ_MAXK];
     int act_dict[FRIQ_MAXA];                  /* dictionary index (dimension S) of action a */
+    int act_hit[FRIQ_MAXA];                   /* dictionary index whose VE value equals act_ve[a] (what a rule at distance 0 holds), -1 none */
     double qdiff_pos, qdiff_neg, wsig, qdiff_final_tol, reward_good_above, pad0;
     double u0[FRIQ_MAXK], udiv[FRIQ_MAXK];
     double values_def[FRIQ_MAXK], ve_def[FRIQ_MAXK];

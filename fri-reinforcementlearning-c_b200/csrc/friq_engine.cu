@@ -26,6 +26,15 @@
 #ifndef FRIQ_MINB
 #define FRIQ_MINB 2
 #endif
+#ifndef FRIQ_MINB_COOP
+#define FRIQ_MINB_COOP 2
+#endif
+#ifndef FRIQ_COMPACT_UNR
+#define FRIQ_COMPACT_UNR 6    /* rules per trip (= independent chains per lane) of friq_pairs_compacted */
+#endif
+#ifndef FRIQ_COOP_MAXPAIRS
+#define FRIQ_COOP_MAXPAIRS 64 /* at most this many (lane, action) pairs of a warp without an exact hit: compacted Shepard sums (<= 2 rounds) */
+#endif
 #ifndef FRIQ_QCOOP_MAX
 #define FRIQ_QCOOP_MAX 8     /* fewer lanes than this needing Q(s,a): friq_q_cooperative instead of the WITHQ pass */
 #endif
@@ -47,8 +56,11 @@ struct __align__(16) friq_smem_t {
     double *sw = st.sw + tile_off;
 
 // ---------------------------------------------------------------------------------------
-template <int S, int P, int A, int ACH, int ENV, int UNR, bool SAFE>
-__global__ void __launch_bounds__(FRIQ_BLOCK, FRIQ_MINB)
+// COOP: exact hits by the integer sweep and cooperative Shepard sums ONLY (problems with hit_scan whose visited
+// (observation, action) pairs mostly have a rule - mountaincar); the lock-step pass is not even compiled in, which halves the
+// register count and doubles the resident warps of this then latency-bound kernel.
+template <int S, int P, int A, int ACH, int ENV, int UNR, bool SAFE, bool COOP>
+__global__ void __launch_bounds__(FRIQ_BLOCK, COOP ? FRIQ_MINB_COOP : FRIQ_MINB)
 k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
 {
     constexpr int K = S + 1;
@@ -118,11 +130,32 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         const bool needq = upd && hitq < 0;
         double actconc[A], vagq, wsq; int hidx[A];
         const unsigned qm = __ballot_sync(wmask, needq);
-        if (__popc(qm) >= FRIQ_QCOOP_MAX)                // many lanes need Q(s,a): its chain rides in the pass
-            friq_best_action_pass<S, P, A, ACH, true, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, needq, vagq, wsq);
-        else {                                           // none or a few: the warp serves them one by one
-            friq_best_action_pass<S, P, A, ACH, false, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, false, vagq, wsq);
-            if (qm) friq_q_cooperative<K, P, SAFE>(pb, rbw, rbq, sw, R, vo, wmask, qm, vagq, wsq);
+        // exact hits first (BestAct.c:89-93): where distance 0 <=> equal dictionary indices, an integer sweep finds them, and only
+        // the (lane, action) pairs without one need Shepard sums - cooperatively when few, else through the lock-step pass
+        bool lockstep = true;
+        if constexpr (COOP || A == ACH) if (COOP || pb.hit_scan) {
+            const uint32_t ow = friq_obs_word<S>(pb, vc, ci);
+            uint32_t tgt[A]; unsigned nm[A]; int pairs = 0;
+#pragma unroll
+            for (int a = 0; a < A; a++) tgt[a] = (ow != FRIQ_NO_TARGET && pb.act_hit[a] >= 0) ? (ow | ((uint32_t)pb.act_hit[a] << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET;
+            friq_hit_scan<A>(rbw, act ? R : 0, tgt, hidx);
+#pragma unroll
+            for (int a = 0; a < A; a++) { nm[a] = __ballot_sync(wmask, act && hidx[a] < 0); pairs += __popc(nm[a]); }
+            if (COOP || pairs <= FRIQ_COOP_MAXPAIRS) {
+                lockstep = false;
+#pragma unroll
+                for (int a = 0; a < A; a++) actconc[a] = (hidx[a] >= 0) ? rbq[(size_t)hidx[a] * FRIQ_TILE] : 0.0;
+                vagq = 0.0; wsq = 0.0;
+                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE>(pb, rbw, rbq, sw, R, vc, vo, wmask, nm, qm, actconc, vagq, wsq);
+            }
+        }
+        if (!COOP && lockstep) {
+            if (__popc(qm) >= FRIQ_QCOOP_MAX)            // many lanes need Q(s,a): its chain rides in the pass
+                friq_best_action_pass<S, P, A, ACH, true, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, needq, vagq, wsq);
+            else {                                       // none or a few: the warp serves them one by one
+                friq_best_action_pass<S, P, A, ACH, false, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, false, vagq, wsq);
+                if (qm) friq_q_cooperative<K, P, SAFE>(pb, rbw, rbq, sw, R, vo, wmask, qm, vagq, wsq);
+            }
         }
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
@@ -947,12 +980,13 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
 }
 
 int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, int variant, void *stream)
-{   // variant 1: three warps per tile (k_run_steps_w3, A = 3 problems); 0: one thread per agent
+{   // variant 0: one thread per agent, lock-step pass (+ hit sweep / cooperative sums when few pairs lack a hit);
+    // 1: three warps per tile (k_run_steps_w3, A = 3 problems); 2: one thread per agent, hit sweep + cooperative sums only
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
 #define FRIQ_LAUNCH_STEP(S_, P_, A_, ACH_, ENV_, UNR_)                                                                   \
     do {                                                                                                              \
-        if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
-        else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
+        if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
+        else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
     } while (0)
 #define FRIQ_LAUNCH_W3(S_, P_, ENV_)                                                                                   \
     do {                                                                                                              \
@@ -963,6 +997,10 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     const int w3 = variant == 1;
     if (w3 && hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_W3(2, 3, FRIQ_ENV_MOUNTAINCAR);
     else if (w3 && hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_W3(4, 5, FRIQ_ENV_ACROBOT);
+    else if (variant == 2 && hp->hit_scan && hp->safe_range && hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp))
+        k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (variant == 2 && hp->hit_scan && hp->safe_range && hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp))
+        k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_STEP(2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, FRIQ_UNR_MC);
     else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_STEP(4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2);
     else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) FRIQ_LAUNCH_STEP(4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1);

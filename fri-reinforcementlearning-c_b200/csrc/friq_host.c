@@ -137,6 +137,25 @@ static void vague_env_row(const double *u, int U, const double *pts, int npts, d
     free(sc);
 }
 
+/* hit_scan / act_hit of the problem block: an exact hit (scaled distance 0) is the same as equal dictionary indices when, in
+ * every dimension, distinct dictionary entries have distinct VE values (and no squared difference can underflow).  Called
+ * whenever a dictionary grows. */
+static void refresh_hit_scan(friq_problem *P)
+{
+    friq_devprob *hp = &P->hp;
+    int injective = 1;
+    for (int k = 0; k < hp->K; k++)
+        for (int i = 0; i < hp->dict_len[k]; i++)
+            for (int j = i + 1; j < hp->dict_len[k]; j++)
+                if (hp->dict_ve[k][i] == hp->dict_ve[k][j]) injective = 0;
+    for (int a = 0; a < hp->A; a++) {
+        hp->act_hit[a] = -1;
+        for (int j = 0; j < hp->dict_len[hp->S]; j++)
+            if (hp->dict_ve[hp->S][j] == hp->act_ve[a]) { hp->act_hit[a] = j; break; }
+    }
+    hp->hit_scan = (injective && hp->safe_range) ? 1 : 0;
+}
+
 static int dict_find_or_add(friq_problem *P, int k, double v)
 {
     friq_devprob *hp = &P->hp;
@@ -237,6 +256,7 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
         }
         hp->corner[r] = w;
     }
+    refresh_hit_scan(P);
     *out = P;
     return 0;
 }
@@ -386,7 +406,11 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
     b->retile_interval = 100;
     { const char *e = getenv("FRIQ_HEAVY_PCT"); b->heavy_pct = e ? atoi(e) : 0; if (b->heavy_pct < 0) b->heavy_pct = 0; if (b->heavy_pct > 100) b->heavy_pct = 100; }
-    { const char *e = getenv("FRIQ_W3"); b->variant = (e && atoi(e) && P->hp.A == 3) ? 1 : 0; }
+    /* evaluation policy of the fused kernel (friqd_run_steps variant): mountaincar agents find an exact-hit rule for > 90 % of
+     * the (observation, action) pairs they visit, so the integer hit sweep + cooperative Shepard sums win by a wide margin;
+     * acrobot / cartpole rarely hit and keep the lock-step pass.  FRIQ_POLICY=0|1|2 overrides (experiments). */
+    b->variant = (P->hp.env == FRIQ_ENV_MOUNTAINCAR && P->hp.hit_scan) ? 2 : 0;
+    { const char *e = getenv("FRIQ_POLICY"); if (e) b->variant = atoi(e); }
     {   /* groups of >= 8192 agents, tile aligned; FRIQ_GROUPS overrides (experiments) */
         const char *e = getenv("FRIQ_GROUPS");
         int g = e ? atoi(e) : (int)(n / 32768);
@@ -467,7 +491,7 @@ int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant
         }
         w[i] = word;
     }
-    if (grew) DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob)));
+    if (grew) { refresh_hit_scan(P); DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob))); }
     if (agent >= 0) {
         const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE);
         if (R) {
@@ -640,11 +664,11 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
                     DEV(friqd_event_record(b->hfork[g], b->gstream[g]));
                     DEV(friqd_stream_wait_event(b->hstream[g], b->hfork[g]));
                     DEV(friqd_run_steps(&b->P->hp, b->P->dp, hv, m, mode, 1, b->gstream[g]));
-                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, lt, m, mode, 0, b->hstream[g]));
+                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, lt, m, mode, b->variant == 1 ? 0 : b->variant, b->hstream[g]));
                     DEV(friqd_event_record(b->hjoin[g], b->hstream[g]));
                     DEV(friqd_stream_wait_event(b->gstream[g], b->hjoin[g]));
                 } else
-                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, dst, m, mode, heavy > 0, b->gstream[g]));
+                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, dst, m, mode, heavy > 0 ? 1 : b->variant, b->gstream[g]));
             }
             friq_devstate t = b->st; b->st = b->st2; b->st2 = t;
             b->permuted = 1 + G;
@@ -879,7 +903,7 @@ int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double 
         grew |= (P->hp.dict_len[k] != before);
         word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
     }
-    if (grew) DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob)));
+    if (grew) { refresh_hit_scan(P); DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob))); }
     const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE) + (size_t)R * FRIQ_TILE;
     DEV(friqd_h2d(b->st.rbw + off, &word, 4)); DEV(friqd_h2d(b->st.rbq + off, &q, 8));
     R++;
