@@ -76,38 +76,53 @@ def run_reference(steps_per_agent, target_seconds=15.0):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the run by a background thread (NVML; one-shot nvidia-smi calls as a fallback)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, index, period=0.02):
+        import threading
+        self.index, self.period = index, period
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), None
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.how = "nvml"
+            bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))); self.mx.append(float(mx))
+                r = get_reasons(h)
+                self.reasons.update(k for k, b in bits.items() if r & b)
+                time.sleep(self.period)
+            return
+        except Exception:       # noqa: BLE001 - fall back to nvidia-smi
             pass
+        self.how = "nvidia-smi"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout
+                c = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(float(c[0])); self.mx.append(float(c[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:   # noqa: BLE001
+                self.how = "unavailable"
+                return
 
     def stop(self):
-        if self.p is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.p.terminate(); self.p.wait()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 8:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    samples=len(sm), reasons=sorted(reasons))
+        self._stop.set(); self._t.join(timeout=10)
+        return dict(sm_mhz=statistics.median(self.sm) if self.sm else None, sm_max_mhz=max(self.mx) if self.mx else None,
+                    samples=len(self.sm), reasons=sorted(self.reasons), source=self.how)
 
 
 # ------------------------------------------------------------------------------------------ our arm

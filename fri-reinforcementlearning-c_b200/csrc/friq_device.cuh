@@ -90,6 +90,12 @@ __device__ __noinline__ double friq_shepard_weight_slow(double s)
 {
     return friq_shepard_weight<P>(s);
 }
+// fall-back of a chain whose square root d is known to be right (SAFE problems: only the power's acceptance test can fail)
+template <int P>
+__device__ __noinline__ double friq_shepard_weight_from_sqrt(double d)
+{
+    return __drcp_rn(friq_pow_x87_exact(d, P));
+}
 // same value, branch-free; bad != 0 => not proven, recompute with friq_shepard_weight
 template <int P, bool SAFE>
 __device__ __forceinline__ double friq_shepard_weight_fast(double s, unsigned &bad, bool live = true)
@@ -194,10 +200,12 @@ __device__ __forceinline__ void friq_pass_trip(const friq_devprob &pb, const uin
         }
     }
     unsigned bad = 0;
-    friq_shepard_weights_n<P, SAFE, NC>(sv, wv, bad, live);
-    if (bad) {                                           // rare: a chain outside the proven fast paths -> library routines, that chain only
+    double dv[NC];
+    friq_shepard_weights_n<P, SAFE, NC>(sv, wv, bad, live, dv);
+    if (bad) {                                           // rare: a chain outside the proven fast paths -> exact routines, that chain only
 #pragma unroll
-        for (int n = 0; n < NC; n++) if ((bad >> n) & 1u) wv[n] = friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
+        for (int n = 0; n < NC; n++)
+            if ((bad >> n) & 1u) wv[n] = SAFE ? friq_shepard_weight_from_sqrt<P>(dv[n]) : friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
     }
 #pragma unroll
     for (int u = 0; u < UNR; u++) {
@@ -444,9 +452,14 @@ __device__ __forceinline__ void friq_hit_scan(const uint32_t *rbw, int R, const 
 // row, so these reads stay coalesced - and accumulates the sums sequentially in its own registers exactly like the
 // lock-step pass does (UNR rules = UNR independent chains per trip, friq_shepard_weights_n).  One round serves as many
 // pairs as the warp has lanes for the price of ONE chain per rule; the owners then pick their results up with a shuffle.  Bit-identical sums.
+#ifndef FRIQ_COMPACT_GMAX
+#define FRIQ_COMPACT_GMAX 1     /* lane groups per pair (2, 4, 8) measured SLOWER on B200 than one lane per pair: the segment shuffles of the
+                                * ordered sums cost more than the idle lanes save (gpurun_out/variants14.log); kept for experiments */
+#endif
 template <int S, int P, int A, int UNR, bool SAFE>
 __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
                                                      const double *vo_obs, const double *vo_q, unsigned wmask, const unsigned (&nm)[A], unsigned qm,
+                                                     unsigned char *plist /* 32 bytes of shared memory per warp */,
                                                      double (&conc)[A], double &vagq, double &wsq)
 {
     constexpr int K = S + 1, C = A + 1;
@@ -465,20 +478,26 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
     const int np = ofs[C];
     vagq = 0.0; wsq = 0.0;
     const int nw = __popc(wmask), rank = __popc(wmask & lt);          // the last warp of a batch may be partial
-    for (int p0 = 0; p0 < np; p0 += nw) {
-        // ---- which pair is mine?  channel c, owner lane j
-        const int p = p0 + rank;
-        int c = 0, j = 0;
-        const bool has = p < np;
+    // Few pairs: every pair gets a GROUP of g lanes (g = 2, 4, 8).  The lanes of a group compute the weights of g consecutive
+    // blocks of UNR rules in parallel - the expensive part - and then all of them add the g * UNR weights up in rule order,
+    // fetching each other's values with segment shuffles, so the order of the sums is still the reference's.
+    int g = 1;
+    if (FRIQ_COMPACT_GMAX > 1 && wmask == 0xffffffffu) { if (np <= 4 && FRIQ_COMPACT_GMAX >= 8) g = 8; else if (np <= 8 && FRIQ_COMPACT_GMAX >= 4) g = 4; else if (np <= 16) g = 2; }
+    const int per_round = nw / g, gi = rank / g, gt = rank % g;
+    const unsigned gmask = (g == 1) ? (1u << lane) : (((g == 32 ? 0u : (1u << g)) - 1u) << (lane & ~(g - 1)));
+    for (int p0 = 0; p0 < np; p0 += per_round) {
+        // ---- which pair is my group's?  the owners post (lane, channel) of their pairs of this round, group gi reads entry gi
+        __syncwarp(wmask);
 #pragma unroll
-        for (int t = 0; t < C; t++) if (has && p >= ofs[t]) { c = t; }
-        unsigned mask_c = chm[0];
-#pragma unroll
-        for (int t = 1; t < C; t++) if (c == t) mask_c = chm[t];
-        int base_c = 0;
-#pragma unroll
-        for (int t = 1; t < C; t++) if (c == t) base_c = ofs[t];
-        if (has) j = __fns(mask_c, 0, p - base_c + 1);   // lane of the (p - base_c)-th set bit
+        for (int t = 0; t < C; t++) {
+            const int e = ofs[t] + __popc(chm[t] & lt) - p0;
+            if (((chm[t] >> lane) & 1u) && e >= 0 && e < per_round) plist[e] = (unsigned char)(lane | (t << 5));
+        }
+        __syncwarp(wmask);
+        const int p = p0 + gi;
+        const bool has = p < np && gi < per_round;
+        const int ent = has ? plist[gi] : 0;
+        const int c = ent >> 5, j = ent & 31;
         // ---- the owner's point and rule count
         double pt[K];
 #pragma unroll
@@ -493,46 +512,66 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
         const int Rj = __shfl_sync(wmask, R, j);
         const int Rp = has ? Rj : 0;
         const bool isq = has && c == A;
-        // ---- sequential Shepard sums over the owner's rules, UNR rules per trip
+        // ---- sequential Shepard sums over the owner's rules: g * UNR rules per trip, my block starts at i + gt * UNR
         double vag = 0.0, ws = 0.0;
+        const int stride = g * UNR;
         uint32_t w[UNR]; double q[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; u++) { w[u] = 0; q[u] = 0.0; if (u < Rp) { w[u] = tw[(size_t)u * FRIQ_TILE + j]; q[u] = tq[(size_t)u * FRIQ_TILE + j]; } }
+        for (int u = 0; u < UNR; u++) {
+            const int r = gt * UNR + u;
+            w[u] = 0; q[u] = 0.0;
+            if (r < Rp) { w[u] = tw[(size_t)r * FRIQ_TILE + j]; q[u] = tq[(size_t)r * FRIQ_TILE + j]; }
+        }
 #pragma unroll 1
-        for (int i = 0; i < Rp; i += UNR) {
+        for (int i = 0; i < Rp; i += stride) {
+            const int i0 = i + gt * UNR;                 // my block
             uint32_t wn[UNR]; double qn[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) {
+            for (int u = 0; u < UNR; u++) {              // prefetch my block of the next trip
+                const int r = i0 + stride + u;
                 wn[u] = 0; qn[u] = 0.0;
-                if (i + UNR + u < Rp) { wn[u] = tw[(size_t)(i + UNR + u) * FRIQ_TILE + j]; qn[u] = tq[(size_t)(i + UNR + u) * FRIQ_TILE + j]; }
+                if (r < Rp) { wn[u] = tw[(size_t)r * FRIQ_TILE + j]; qn[u] = tq[(size_t)r * FRIQ_TILE + j]; }
             }
-            double sv[UNR], wv[UNR]; bool live[UNR];
+            double sv[UNR], wv[UNR], wq[UNR], dv[UNR]; bool live[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) { sv[u] = friq_dist2<K>(pb, w[u], pt); live[u] = i + u < Rp; }   // != 0 for real rules: no exact hit
+            for (int u = 0; u < UNR; u++) { sv[u] = friq_dist2<K>(pb, w[u], pt); live[u] = i0 + u < Rp; }   // != 0 for real rules: no exact hit
             unsigned bad = 0;
-            friq_shepard_weights_n<P, SAFE, UNR>(sv, wv, bad, live);
+            friq_shepard_weights_n<P, SAFE, UNR>(sv, wv, bad, live, dv);
             if (bad) {
 #pragma unroll
-                for (int u = 0; u < UNR; u++) if ((bad >> u) & 1u) wv[u] = friq_shepard_weight_slow<P>(live[u] ? sv[u] : 1.0);
+                for (int u = 0; u < UNR; u++)
+                    if ((bad >> u) & 1u) wv[u] = SAFE ? friq_shepard_weight_from_sqrt<P>(dv[u]) : friq_shepard_weight_slow<P>(live[u] ? sv[u] : 1.0);
             }
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
-                if (u == 0 || i + u < Rp) {
-                    if (isq) tsw[(size_t)(i + u) * FRIQ_TILE + j] = wv[u];
-                    vag = __dadd_rn(vag, __dmul_rn(wv[u], q[u]));                             // BestAct.c:216 / FIVEVagConcl.c:234
-                    ws = __dadd_rn(ws, wv[u]);                                                // :217 / :235
+                wq[u] = __dmul_rn(wv[u], q[u]);                                               // BestAct.c:216 / FIVEVagConcl.c:234, the product
+                if (isq && live[u]) tsw[(size_t)(i0 + u) * FRIQ_TILE + j] = wv[u];
+            }
+            if (g == 1) {
+#pragma unroll
+                for (int u = 0; u < UNR; u++)
+                    if (u == 0 || i + u < Rp) { vag = __dadd_rn(vag, wq[u]); ws = __dadd_rn(ws, wv[u]); }   // :216-217 / :234-235
+            } else {
+                for (int tt = 0; tt < g; tt++) {         // blocks in rule order; every lane of the group adds the same values
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        const double a1 = __shfl_sync(gmask, wq[u], tt, g), a2 = __shfl_sync(gmask, wv[u], tt, g);
+                        if (i + tt * UNR + u < Rp) { vag = __dadd_rn(vag, a1); ws = __dadd_rn(ws, a2); }
+                    }
                 }
             }
 #pragma unroll
             for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
         }
         const double res = __ddiv_rn(vag, ws);                                               // BestAct.c:265
-        // ---- hand the results back to the owners
+        // ---- hand the results back to the owners (first lane of the pair's group)
+        __syncwarp(wmask);
 #pragma unroll
         for (int t = 0; t < C; t++) {
-            const int src = ofs[t] + __popc(chm[t] & lt) - p0;       // rank of the lane that holds my pair of channel t (if I have one in this round)
-            const bool mine = ((chm[t] >> lane) & 1u) && src >= 0 && src < nw;
-            const int sl = mine ? __fns(wmask, 0, src + 1) : lane;
+            const int e = ofs[t] + __popc(chm[t] & lt) - p0;         // my pair of channel t is entry e of this round (if I have one)
+            const bool mine = ((chm[t] >> lane) & 1u) && e >= 0 && e < per_round;
+            const int src = mine ? e * g : rank;                      // rank of the group's first lane
+            const int sl = (wmask == 0xffffffffu) ? src : __fns(wmask, 0, src + 1);
             if (t < A) { const double r = __shfl_sync(wmask, res, sl); if (mine) conc[t < A ? t : 0] = r; }
             else { const double a1 = __shfl_sync(wmask, vag, sl), a2 = __shfl_sync(wmask, ws, sl); if (mine) { vagq = a1; wsq = a2; } }
         }

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(FRIQ_BLOCK, COOP ? FRIQ_MINB_COOP : FRIQ_MINB)
 k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
 {
     constexpr int K = S + 1;
+    __shared__ unsigned char pair_list[FRIQ_BLOCK / 32][32];            // friq_pairs_compacted, per warp
     FRIQ_SMEM_PROLOGUE();
     double *prevq = st.prevq ? st.prevq + tile_off : nullptr;
 
@@ -146,7 +147,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 #pragma unroll
                 for (int a = 0; a < A; a++) actconc[a] = (hidx[a] >= 0) ? rbq[(size_t)hidx[a] * FRIQ_TILE] : 0.0;
                 vagq = 0.0; wsq = 0.0;
-                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE>(pb, rbw, rbq, sw, R, vc, vo, wmask, nm, qm, actconc, vagq, wsq);
+                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE>(pb, rbw, rbq, sw, R, vc, vo, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq);
             }
         }
         if (!COOP && lockstep) {
