@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--agents", type=int, default=65536, help="agents per GPU")
     ap.add_argument("--chunk", type=int, default=250, help="env steps per agent per bench step (one kernel launch)")
-    ap.add_argument("--retile", type=int, default=100, help="env steps between re-tilings by rule count inside a step (0 = once per step)")
+    ap.add_argument("--retile", type=int, default=125, help="env steps between re-tilings by rule count inside a step (0 = once per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -812,11 +812,20 @@ __global__ void k_retile_hist(friq_devstate st, int *work)
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < st.n) atomicAdd(&work[st.R[p]], 1);
 }
+// exclusive prefix sums of the histogram in DESCENDING rule-count order (one block): work[r] = #agents with more than r rules
 __global__ void k_retile_scan(int *work, int cap)
 {
-    if (threadIdx.x || blockIdx.x) return;
-    int off = 0;
-    for (int r = cap; r >= 0; r--) { const int c = work[r]; work[r] = off; off += c; }
+    __shared__ int seg[256];
+    const int n = cap + 1, t = threadIdx.x, len = (n + 255) / 256;
+    const int hi = cap - t * len, lo = max(hi - len + 1, 0);          // thread t owns counts [lo, hi], thread 0 the largest
+    int sum = 0;
+    for (int r = hi; r >= lo; r--) sum += work[r];
+    seg[t] = sum;
+    __syncthreads();
+    if (t == 0) { int off = 0; for (int i = 0; i < 256; i++) { const int c = seg[i]; seg[i] = off; off += c; } }
+    __syncthreads();
+    int off = seg[t];
+    for (int r = hi; r >= lo; r--) { const int c = work[r]; work[r] = off; off += c; }
 }
 __global__ void k_retile_assign(friq_devstate st, int *work, int by_rules)
 {
@@ -943,7 +952,7 @@ int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules
     if (by_rules) {
         CK(cudaMemsetAsync(d_work, 0, sizeof(int) * (src.cap + 1), s));
         k_retile_hist<<<g, FRIQ_BLOCK, 0, s>>>(src, d_work);
-        k_retile_scan<<<1, 32, 0, s>>>(d_work, src.cap);
+        k_retile_scan<<<1, 256, 0, s>>>(d_work, src.cap);
     }
     k_retile_assign<<<g, FRIQ_BLOCK, 0, s>>>(src, d_work, by_rules);
     k_retile_move<<<g, FRIQ_BLOCK, 0, s>>>(src, dst, d_work);

@@ -404,7 +404,7 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     int rc = problem_upload(P, device); if (rc) return rc;
     friq_batch *b = (friq_batch *)calloc(1, sizeof *b);
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
-    b->retile_interval = 100;
+    b->retile_interval = 125;
     { const char *e = getenv("FRIQ_HEAVY_PCT"); b->heavy_pct = e ? atoi(e) : 0; if (b->heavy_pct < 0) b->heavy_pct = 0; if (b->heavy_pct > 100) b->heavy_pct = 100; }
     /* evaluation policy of the fused kernel (friqd_run_steps variant): mountaincar agents find an exact-hit rule for > 90 % of
      * the (observation, action) pairs they visit, so the integer hit sweep + cooperative Shepard sums win by a wide margin;

@@ -109,7 +109,7 @@ int friq_batch_get_inserted(friq_batch *b, int *inserted);
  * (a cudaStream_t passed as void*, NULL = default stream). */
 int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream);
 int friq_batch_sync(friq_batch *b, void *stream);
-/* with FRIQ_RUN_RETILE a run is split into launches of `steps` env steps with a re-tiling before each (default 100; 0 = once per run) */
+/* with FRIQ_RUN_RETILE a run is split into launches of `steps` env steps with a re-tiling before each (default 125; 0 = once per run) */
 int friq_batch_set_retile_interval(friq_batch *b, long steps);
 /* results -> host arrays of n_agents (any pointer may be NULL): last finished episode's total reward /
  * steps / rule count (the per-episode printf of frirl_sequential_run.c:77-80), episodes finished,

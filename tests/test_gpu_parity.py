@@ -178,6 +178,69 @@ def test_random_exploration_matches_oracle_port(fq, name):
     b.close(); P.close()
 
 
+@pytest.mark.parametrize("name,policy", [("mountaincar", 0), ("mountaincar", 1), ("mountaincar", 2), ("acrobot", 1), ("acrobot", 2)])
+def test_every_evaluation_policy_matches_oracle(fq, name, policy, monkeypatch):
+    """The fused kernel has three evaluation policies (FRIQ_POLICY): 0 lock-step pass over all actions (+ hit sweep /
+    compacted sums when few pairs lack an exact hit), 1 three warps per tile, 2 hit sweep + compacted Shepard sums only
+    (mountaincar's default).  All of them must reproduce the oracle bit for bit - here on a hard mix: a partial last
+    warp (70 agents), random OFF-GRID episode start states (no exact hit possible at episode start: every pair needs its
+    Shepard sums), heavy exploration, per-agent hyper-parameters, chunked and re-tiled launches."""
+    monkeypatch.setenv("FRIQ_POLICY", str(policy))
+    P = fq.Problem(name, no_random=0)
+    n, first = 70, 7
+    rng = np.random.default_rng(100 + policy)
+    alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.02, 0.1, 0.3], n)
+    lo = {"mountaincar": [-1.2, -0.05], "acrobot": [-1.0, -1.0, -0.5, -0.5]}[name]
+    hi = {"mountaincar": [0.3, 0.05], "acrobot": [1.0, 1.0, 0.5, 0.5]}[name]
+    s0 = rng.uniform(lo, hi, size=(n, P.S))
+    b = fq.Batch(P, n, CAP[name], seed0=0x5EED0000, first_agent=first)
+    b.set_hyper(alpha, gamma, eps)
+    b.set_initial_state(s0)
+    steps = 900 if name == "mountaincar" else 400
+    for chunk, mode in ((3, fq.RUN_LEARN), (steps - 303, fq.RUN_LEARN | fq.RUN_RETILE), (300, fq.RUN_LEARN | fq.RUN_RETILE)):
+        b.run(chunk, mode)
+    o = b.gather()
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
+    for i in range(n):
+        a = _oracle.Agent(OP, CAP[name], seed=0x5EED0000 + first + i)
+        a.set_hyper(alpha[i], gamma[i], eps[i]); a.set_initial_state(s0[i])
+        a.run_steps(steps)
+        sm = a.summary()
+        R, rant, rconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(rant, orant) and np.array_equal(rconc, orconc), i
+        assert (o["episodes"][i], o["last_steps"][i], o["last_return"][i], o["total_steps"][i], o["sum_rules"][i]) == \
+            (sm["episode_num"] - 1, sm["last_steps"], sm["last_return"], sm["total_steps"], sm["sum_rules"])
+    b.close(); P.close()
+
+
+def test_hit_sweep_is_disabled_when_dictionary_ve_values_collide(fq):
+    """The integer hit sweep is only valid while distinct dictionary entries have distinct VE values.  A loaded rule base
+    whose antecedent value lies off the grid but snaps to the same universe point as a grid value creates such a
+    collision (distance 0 between DIFFERENT dictionary indices): the engine must notice and fall back to the
+    floating-point exact-hit test - results still equal the oracle."""
+    name = "mountaincar"
+    P = fq.Problem(name, no_random=0)
+    g = _golden.load(name)
+    rant, rconc = g["final"][1].copy(), g["final"][2].copy()
+    u = P.tables()["u"]
+    rant[5, 0] = rant[5, 0] + 0.2 * (u[0][1] - u[0][0])      # same nearest universe point, different value
+    n = 40
+    b = fq.Batch(P, n, CAP[name], seed0=77, first_agent=0)
+    b.set_rulebase(rant, rconc)
+    eps = np.full(n, 0.05); b.set_hyper(np.full(n, 0.5), np.ones(n), eps)
+    b.run(500, fq.RUN_LEARN | fq.RUN_RETILE)
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
+    for i in (0, 13, 39):
+        a = _oracle.Agent(OP, CAP[name], seed=77 + i)
+        a.set_rb(rant, rconc); a.set_hyper(0.5, 1.0, 0.05)
+        a.run_steps(500)
+        R, brant, brconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(brant, orant) and np.array_equal(brconc, orconc), i
+    b.close(); P.close()
+
+
 def test_retiled_results_are_reported_in_agent_order(fq):
     """FRIQ_RUN_RETILE moves agents between warps (sorted by rule count); device-side gathers and the
     host-buffer end-to-end call must still report per-agent results in agent order."""
