@@ -930,6 +930,126 @@ int friq_batch_remove_rule(friq_batch *b, long agent, int rule)
     return rc;
 }
 
+/* ------------------------------------------------------------------- rule-base reduction */
+/* Reduction strategies 1 (smallest |Q| first) and 2 (largest |Q| first) of frirl_sequential_run.c:170-350 for a problem with a
+ * built-in environment: take one rule out, replay one greedy episode without updates (reduction_state = 1), keep the removal
+ * when the episode still takes steps_ref steps, its reward is good and within reward_tolerance of the last accepted reward,
+ * else put the rule back and mark it important.  The reference tests one candidate per episode; here up to `width`
+ * candidates are tested SPECULATIVELY in one launch - agent i replays the rule base with the first i + 1 candidates of the
+ * chain removed, assuming the earlier ones were accepted - and the results are then consumed in order up to the first
+ * rejection (whose successors are discarded and re-speculated), which yields exactly the sequential result.  With verbose
+ * the reference's own log lines are printed.  Deterministic episodes only (no_random = 1 or epsilon = 0). */
+static int pick_candidate(const double *cand, int R, int strategy, double *mv_out)
+{
+    double mv = fabs(cand[0]); int pick = 0;                                  /* frirl_sequential_run.c:262-275 / 305-318 */
+    for (int j = 1; j < R; j++) {
+        const double a = fabs(cand[j]);
+        const int better = (strategy == 1) ? (mv > a) : (mv < a);
+        if (better || (mv != mv && cand[j] == cand[j])) { mv = a; pick = j; }
+    }
+    *mv_out = mv;
+    return pick;
+}
+
+int friq_reduce_rulebase(friq_problem *P, int device, int strategy, double reward_tolerance, int width,
+                         int *R_io, double *rant, double *rconc, int verbose, int *episodes_run)
+{
+    const friq_devprob *hp = &P->hp; const int K = hp->K, R0 = *R_io;
+    if (hp->env == FRIQ_ENV_HOST_CALLBACKS) FAIL(6, "friq_reduce_rulebase: the problem has no built-in environment");
+    if (!(hp->no_random == 1 || P->epsilon == 0.0)) FAIL(6, "friq_reduce_rulebase: needs deterministic episodes (no_random = 1 or epsilon = 0)");
+    if (strategy != 1 && strategy != 2) FAIL(6, "friq_reduce_rulebase: strategy must be 1 (min |Q| first) or 2 (max |Q| first)");
+    if (R0 < 1 || width < 1) FAIL(6, "friq_reduce_rulebase: empty rule base or width < 1");
+    friq_batch *b;
+    int rc = friq_batch_create(P, device, width, R0 > hp->ncorner ? R0 : hp->ncorner, 0, 0, &b); if (rc) return rc;
+    double *ret = (double *)malloc(sizeof(double) * width); int *stp = (int *)malloc(sizeof(int) * width);
+    double *cand = (double *)malloc(sizeof(double) * R0), *tant = (double *)malloc(sizeof(double) * (size_t)R0 * K), *tq = (double *)malloc(sizeof(double) * R0);
+    double *tcand = (double *)malloc(sizeof(double) * R0), *removed = (double *)malloc(sizeof(double) * (size_t)width * (K + 1));
+    int *picks = (int *)malloc(sizeof(int) * width);
+    int R = R0, ep = 0, done = 0, total_eps = 0;
+#define REDUCE_FAIL(r) do { rc = (r); goto out; } while (0)
+    /* the reference first replays the full rule base to learn steps_ref (:193-194), then episode 1 replays it again (:198) */
+    if ((rc = friq_batch_set_rulebase(b, -1, R, rant, rconc))) REDUCE_FAIL(rc);
+    if ((rc = friq_batch_run(b, hp->max_steps, FRIQ_RUN_STOP_AT_EPISODE_END, NULL))) REDUCE_FAIL(rc);
+    if ((rc = friq_batch_gather(b, ret, stp, NULL, NULL, NULL, NULL, NULL))) REDUCE_FAIL(rc);
+    total_eps += 2;
+    const int steps_ref = stp[0];
+    double prev_reward = ret[0];
+    const int iterations = R0 + 1;
+    memcpy(cand, rconc, sizeof(double) * R);
+    ep = 1;
+    printf("Reduction Episode: %d\tSteps: %d\tReward: %f\tEpsilon: %f\tRules: %d\n", ep, stp[0], ret[0], P->epsilon, R);
+    while (!done) {
+        /* ---- speculate: chain of picks from the current state, each assuming the previous ones were accepted */
+        int m = 0, tR = R;
+        memcpy(tant, rant, sizeof(double) * (size_t)R * K); memcpy(tq, rconc, sizeof(double) * R); memcpy(tcand, cand, sizeof(double) * R);
+        if ((rc = friq_batch_reset(b))) REDUCE_FAIL(rc);
+        while (m < width && ep + m < iterations) {
+            double mv; const int pick = pick_candidate(tcand, tR, strategy, &mv);
+            if (mv != mv) break;                                              /* every remaining rule is marked important */
+            picks[m] = pick;
+            memcpy(removed + (size_t)m * (K + 1), tant + (size_t)pick * K, sizeof(double) * K); removed[(size_t)m * (K + 1) + K] = tcand[pick];
+            memmove(tant + (size_t)pick * K, tant + (size_t)(pick + 1) * K, sizeof(double) * (size_t)(tR - 1 - pick) * K);
+            memmove(tq + pick, tq + pick + 1, sizeof(double) * (tR - 1 - pick));
+            memmove(tcand + pick, tcand + pick + 1, sizeof(double) * (tR - 1 - pick));
+            tR--;
+            if ((rc = friq_batch_set_rulebase(b, m, tR, tant, tq))) REDUCE_FAIL(rc);
+            m++;
+        }
+        if (m == 0) {                                                         /* nothing left to try (:276-281) or out of iterations */
+            double mv; pick_candidate(cand, R, strategy, &mv);
+            if (mv != mv && verbose) printf("Smallest rulebase found. Exiting.\n");
+            break;
+        }
+        if ((rc = friq_batch_run(b, hp->max_steps, FRIQ_RUN_STOP_AT_EPISODE_END, NULL))) REDUCE_FAIL(rc);
+        if ((rc = friq_batch_gather(b, ret, stp, NULL, NULL, NULL, NULL, NULL))) REDUCE_FAIL(rc);
+        /* ---- consume the results in order */
+        for (int i = 0; i < m; i++) {
+            const int pick = picks[i];
+            ep++; total_eps++;
+            printf("Reduction Episode: %d\tSteps: %d\tReward: %f\tEpsilon: %f\tRules: %d\n", ep, stp[i], ret[i], P->epsilon, R - 1);
+            const double diff = prev_reward - ret[i];
+            if (ret[i] > hp->reward_good_above && stp[i] == steps_ref && fabs(diff) <= reward_tolerance) {       /* :206-219 */
+                if (verbose) {
+                    printf("Reduction Episode: %d\tEliminated rule: no: %d. - ", ep, pick + 1);
+                    for (int j = 0; j <= K; j++) printf(" %f", removed[(size_t)i * (K + 1) + j]);
+                    printf(" \tReward diff was: %f\n", diff);
+                }
+                prev_reward = ret[i];
+                memmove(rant + (size_t)pick * K, rant + (size_t)(pick + 1) * K, sizeof(double) * (size_t)(R - 1 - pick) * K);
+                memmove(rconc + pick, rconc + pick + 1, sizeof(double) * (R - 1 - pick));
+                memmove(cand + pick, cand + pick + 1, sizeof(double) * (R - 1 - pick));
+                R--;
+            } else {                                                          /* :220-237: the rule stays and is marked important */
+                cand[pick] = NAN;
+                if (verbose) {
+                    printf("Reduction Episode: %d\tRule stays: no: %d. - ", ep, pick + 1);
+                    for (int j = 0; j < K; j++) printf(" %f", rant[(size_t)pick * K + j]);
+                    printf(" %f\n", rconc[pick]);
+                }
+                break;                                                        /* later speculations assumed this removal */
+            }
+        }
+        if (ep >= iterations) {                                               /* the last iteration still picks (:262-300) ... */
+            double mv; const int pick = pick_candidate(cand, R, strategy, &mv);
+            if (mv != mv) { if (verbose) printf("Smallest rulebase found. Exiting.\n"); }
+            else {                                                            /* ... and its removal is never replayed */
+                memmove(rant + (size_t)pick * K, rant + (size_t)(pick + 1) * K, sizeof(double) * (size_t)(R - 1 - pick) * K);
+                memmove(rconc + pick, rconc + pick + 1, sizeof(double) * (R - 1 - pick));
+                R--;
+            }
+            done = 1;
+        }
+    }
+    *R_io = R;
+    if (episodes_run) *episodes_run = total_eps;
+    rc = 0;
+out:
+    friq_batch_destroy(b);
+    free(ret); free(stp); free(cand); free(tant); free(tq); free(tcand); free(removed); free(picks);
+    return rc;
+#undef REDUCE_FAIL
+}
+
 /* ----------------------------------------------------------------------- rule-base files */
 /* frirl_save_rb_to_text_file (frirl_utils.c:100-146): "%.18f " per antecedent, "%.18f \n" for Q */
 int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double *rant, const double *rconc)

@@ -72,6 +72,7 @@ SYMBOLS = {
     "friq_batch_bestact_from_dists": (C.c_int, [C.c_void_p, dp, dp]),
     "friq_batch_append_rule": (C.c_int, [C.c_void_p, C.c_long, dp, C.c_double]),
     "friq_batch_remove_rule": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
+    "friq_reduce_rulebase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, ip, dp, dp, C.c_int, ip]),
     "friq_save_rb_to_text_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
     "friq_save_rb_to_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
     "friq_load_rb_from_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, ip, dp, dp]),
@@ -274,6 +275,14 @@ def device_fp64_peak():
     g = C.c_double(0)
     _ck(lib().friq_device_fp64_peak(C.byref(g)))
     return g.value
+
+
+def reduce_rulebase(problem, rant, rconc, strategy=1, reward_tolerance=0.0, width=32, device=0, verbose=0):
+    """friq_reduce_rulebase: returns (rant, rconc, episodes_run) of the reduced rule base."""
+    rant = _f64(rant).copy(); rconc = _f64(rconc).copy()
+    R = C.c_int(len(rconc)); eps = C.c_int(0)
+    _ck(lib().friq_reduce_rulebase(problem.h, device, strategy, reward_tolerance, width, C.byref(R), _p(rant), _p(rconc), verbose, C.byref(eps)))
+    return rant[:R.value].copy(), rconc[:R.value].copy(), eps.value
 
 
 def save_rb_text(path, rant, rconc):

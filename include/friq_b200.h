@@ -146,6 +146,13 @@ int friq_batch_bestact_from_dists(friq_batch *b, const double *dists, double *co
 int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double q);
 int friq_batch_remove_rule(friq_batch *b, long agent, int rule);
 
+/* ---- rule-base reduction (frirl_sequential_run.c:170-350, strategy 1: smallest |Q| first, 2: largest |Q| first) of ONE rule
+ * base rant [R][K], rconc [R] (reduced in place, *R updated) on a problem with a built-in environment.  Each candidate removal
+ * is tested by one greedy episode without updates; up to `width` candidates are tested speculatively per launch and consumed
+ * in order, which gives exactly the reference's sequential result.  verbose != 0 prints the reference's log lines. */
+int friq_reduce_rulebase(friq_problem *p, int device, int strategy, double reward_tolerance, int width,
+                         int *R, double *rant, double *rconc, int verbose, int *episodes_run);
+
 /* ---- rule-base files, byte-compatible with frirl_utils.c:100-281 */
 int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double *rant, const double *rconc);
 int friq_save_rb_to_bin_file(const char *file_name, int K, int R, const double *rant, const double *rconc);

@@ -333,3 +333,23 @@ def test_capacity_overflow_is_flagged(fq):
     o = b.gather()
     assert np.all(o["rules"] == 12) and np.all(o["flags"] & fq.F_OVERFLOW)
     b.close(); P.close()
+
+
+@pytest.mark.parametrize("width", [1, 7, 64])
+def test_batched_rule_base_reduction_equals_reference(fq, width, capfd):
+    """Rule-base reduction (frirl_sequential_run.c:170-350) with `width` candidate removals tested speculatively per launch must
+    give exactly what the reference's one-candidate-per-episode loop gives: the shipped mountaincar run (`-f <constructed rule
+    base>`) reduces 110 rules to 28; the reduced rule base and the log lines are golden fixtures recorded from the reference."""
+    import os
+    g = _golden.load("mountaincar")
+    P = fq.Problem("mountaincar")
+    capfd.readouterr()
+    rant, rconc, episodes = fq.reduce_rulebase(P, g["final"][1], g["final"][2], strategy=1, width=width, verbose=1)
+    out = capfd.readouterr().out
+    want = open(os.path.join(_golden.GOLDEN, "mountaincar_reduced.frirlrb.txt"), "rb").read()
+    assert _golden.rb_text(rant, rconc) == want
+    log = [l for l in out.splitlines() if l.startswith(("Reduction Episode", "Smallest"))]
+    ref = [l for l in open(os.path.join(_golden.GOLDEN, "mountaincar_reduction.log")).read().splitlines() if not l.startswith("Loaded")]
+    assert log == ref
+    assert episodes == 2 + 110                          # the reference replays 1 + 111 episodes; speculation never adds accepted work
+    P.close()
