@@ -1088,6 +1088,133 @@ int friq_load_rb_from_bin_file(const char *file_name, int K, int max_rules, int 
     return 0;
 }
 
+/* ------------------------------------------------------------------- batched rule-base I/O */
+/* rule bases of the agents [first, first + count) -> host: R [count], rant [count][cap][K], rconc [count][cap] (bulk copies
+ * of whole tiles, unpacked on the host) */
+static int fetch_rulebases(friq_batch *b, long first, long count, int *R, double *rant, double *rconc)
+{
+    const friq_devprob *hp = &b->P->hp; const int K = hp->K, cap = b->st.cap;
+    if (first < 0 || count < 0 || first + count > b->st.n) FAIL(5, "rule-base range [%ld, %ld) out of range", first, first + count);
+    DEV(friqd_set_device(b->device));
+    DEV(friqd_device_sync());
+    IDENTITY(b);
+    const long t0 = first / FRIQ_TILE, t1 = (first + count + FRIQ_TILE - 1) / FRIQ_TILE;
+    const size_t tile_slots = (size_t)cap * FRIQ_TILE;
+    unsigned int *w = (unsigned int *)malloc(tile_slots * 4); double *q = (double *)malloc(tile_slots * 8);
+    int rc = friqd_d2h(R, b->st.R + first, 4ul * count);
+    for (long t = t0; t < t1 && !rc; t++) {
+        rc = friqd_d2h(w, b->st.rbw + (size_t)t * tile_slots, tile_slots * 4);
+        if (!rc) rc = friqd_d2h(q, b->st.rbq + (size_t)t * tile_slots, tile_slots * 8);
+        for (int l = 0; l < FRIQ_TILE && !rc; l++) {
+            const long ag = t * FRIQ_TILE + l;
+            if (ag < first || ag >= first + count) continue;
+            const long o = ag - first;
+            for (int i = 0; i < R[o]; i++) {
+                const unsigned int word = w[(size_t)i * FRIQ_TILE + l];
+                for (int k = 0; k < K; k++) rant[((size_t)o * cap + i) * K + k] = hp->dict_val[k][(word >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+                rconc[(size_t)o * cap + i] = q[(size_t)i * FRIQ_TILE + l];
+            }
+        }
+    }
+    free(w); free(q);
+    if (rc) FAIL(rc, "fetch_rulebases: %s", friqd_error_string(rc));
+    return 0;
+}
+
+/* one rule-base file per agent in the reference's formats (frirl_utils.c:100-203): `pattern` is a printf format with one %ld
+ * (the agent index), e.g. "run7/agent%06ld.frirlrb.bin"; text != 0 writes the "%.18f " text format */
+int friq_batch_save_rb_files(friq_batch *b, long first, long count, const char *pattern, int text)
+{
+    const int K = b->P->hp.K, cap = b->st.cap;
+    const long chunk = 1024;
+    int *R = (int *)malloc(sizeof(int) * chunk);
+    double *rant = (double *)malloc(sizeof(double) * (size_t)chunk * cap * K), *rconc = (double *)malloc(sizeof(double) * (size_t)chunk * cap);
+    int rc = 0;
+    for (long lo = first; lo < first + count && !rc; lo += chunk) {
+        const long c = (first + count - lo < chunk) ? first + count - lo : chunk;
+        rc = fetch_rulebases(b, lo, c, R, rant, rconc);
+        for (long i = 0; i < c && !rc; i++) {
+            char name[1024];
+            snprintf(name, sizeof name, pattern, lo + i);
+            rc = text ? friq_save_rb_to_text_file(name, K, R[i], rant + (size_t)i * cap * K, rconc + (size_t)i * cap)
+                      : friq_save_rb_to_bin_file(name, K, R[i], rant + (size_t)i * cap * K, rconc + (size_t)i * cap);
+        }
+    }
+    free(R); free(rant); free(rconc);
+    return rc;
+}
+
+/* warm start (`-f file`, frirl_app_helpers.c:53-62): the rule base of a reference .frirlrb.bin file for one agent, or for every
+ * agent when agent < 0; fus_is_rule_inserted is cleared like frirl_load_rb_from_bin_file does (frirl_utils.c:263) */
+int friq_batch_load_rb_file(friq_batch *b, long agent, const char *file_name)
+{
+    const int K = b->P->hp.K, cap = b->st.cap;
+    double *rant = (double *)malloc(sizeof(double) * (size_t)cap * K), *rconc = (double *)malloc(sizeof(double) * cap);
+    int R = 0;
+    int rc = friq_load_rb_from_bin_file(file_name, K, cap, &R, rant, rconc);
+    if (!rc) rc = friq_batch_set_rulebase(b, agent, R, rant, rconc);
+    free(rant); free(rconc);
+    if (rc) return rc;
+    int *f = (int *)malloc(sizeof(int) * b->st.n);
+    rc = friq_batch_get_inserted(b, f);
+    if (!rc) { if (agent < 0) memset(f, 0, sizeof(int) * b->st.n); else f[agent] = 0; rc = friq_batch_set_inserted(b, f); }
+    free(f);
+    return rc;
+}
+
+/* Checkpoint of a whole batch in ONE file: header {magic "FRIQCKP1", int64 n_agents, int32 K, int32 reserved}, then per agent
+ * {int32 R, int32 fus_is_rule_inserted, R x (K antecedents + consequent) f64} - the per-agent record is the reference's binary
+ * rule-base format (frirl_utils.c:175-203) with the sticky flag in front.  Like the reference, no episode state is saved. */
+int friq_batch_save_checkpoint(friq_batch *b, const char *file_name)
+{
+    const int K = b->P->hp.K, cap = b->st.cap; const long n = b->st.n, chunk = 1024;
+    FILE *f = fopen(file_name, "wb");
+    if (!f) { perror("friq_batch_save_checkpoint: open()"); FAIL(-1, "cannot open %s", file_name); }
+    const long long n64 = n; const int32_t k32 = K, zero = 0;
+    fwrite("FRIQCKP1", 1, 8, f); fwrite(&n64, 8, 1, f); fwrite(&k32, 4, 1, f); fwrite(&zero, 4, 1, f);
+    int *R = (int *)malloc(sizeof(int) * chunk), *ins = (int *)malloc(sizeof(int) * n);
+    double *rant = (double *)malloc(sizeof(double) * (size_t)chunk * cap * K), *rconc = (double *)malloc(sizeof(double) * (size_t)chunk * cap);
+    int rc = friq_batch_get_inserted(b, ins);
+    for (long lo = 0; lo < n && !rc; lo += chunk) {
+        const long c = (n - lo < chunk) ? n - lo : chunk;
+        rc = fetch_rulebases(b, lo, c, R, rant, rconc);
+        for (long i = 0; i < c && !rc; i++) {
+            const int32_t r32 = R[i], i32 = ins[lo + i];
+            fwrite(&r32, 4, 1, f); fwrite(&i32, 4, 1, f);
+            for (int r = 0; r < R[i]; r++) { fwrite(rant + ((size_t)i * cap + r) * K, 8, K, f); fwrite(rconc + (size_t)i * cap + r, 8, 1, f); }
+        }
+    }
+    free(R); free(ins); free(rant); free(rconc);
+    if (fclose(f) != 0 && !rc) FAIL(-1, "%s: write failed", file_name);
+    return rc;
+}
+
+int friq_batch_load_checkpoint(friq_batch *b, const char *file_name)
+{
+    const int K = b->P->hp.K, cap = b->st.cap; const long n = b->st.n;
+    FILE *f = fopen(file_name, "rb");
+    if (!f) { perror("friq_batch_load_checkpoint: open()"); FAIL(-1, "cannot open %s", file_name); }
+    char magic[8]; long long n64 = 0; int32_t k32 = 0, res = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "FRIQCKP1", 8) || fread(&n64, 8, 1, f) != 1 || fread(&k32, 4, 1, f) != 1 || fread(&res, 4, 1, f) != 1) {
+        fclose(f); FAIL(-1, "%s: not a FRIQCKP1 checkpoint", file_name);
+    }
+    if (n64 != n || k32 != K) { fclose(f); FAIL(-1, "%s: checkpoint of %lld agents / K = %d, batch has %ld / %d", file_name, n64, k32, n, K); }
+    double *rant = (double *)malloc(sizeof(double) * (size_t)cap * K), *rconc = (double *)malloc(sizeof(double) * cap);
+    int *ins = (int *)malloc(sizeof(int) * n);
+    int rc = 0;
+    for (long a = 0; a < n && !rc; a++) {
+        int32_t r32 = 0, i32 = 0;
+        if (fread(&r32, 4, 1, f) != 1 || fread(&i32, 4, 1, f) != 1 || r32 < 0 || r32 > cap) { snprintf(g_err, sizeof g_err, "%s: bad record of agent %ld", file_name, a); rc = -1; break; }
+        for (int r = 0; r < r32; r++)
+            if (fread(rant + (size_t)r * K, 8, K, f) != (size_t)K || fread(rconc + r, 8, 1, f) != 1) { snprintf(g_err, sizeof g_err, "%s: truncated", file_name); rc = -1; break; }
+        if (!rc) rc = friq_batch_set_rulebase(b, a, r32, rant, rconc);
+        ins[a] = i32;
+    }
+    if (!rc) rc = friq_batch_set_inserted(b, ins);
+    fclose(f); free(rant); free(rconc); free(ins);
+    return rc;
+}
+
 /* --------------------------------------------------------------------- device self-tests */
 int friq_device_trig(const double *x, double *s, double *c, long n)
 {

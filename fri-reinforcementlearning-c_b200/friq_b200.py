@@ -72,6 +72,10 @@ SYMBOLS = {
     "friq_batch_bestact_from_dists": (C.c_int, [C.c_void_p, dp, dp]),
     "friq_batch_append_rule": (C.c_int, [C.c_void_p, C.c_long, dp, C.c_double]),
     "friq_batch_remove_rule": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
+    "friq_batch_save_rb_files": (C.c_int, [C.c_void_p, C.c_long, C.c_long, C.c_char_p, C.c_int]),
+    "friq_batch_load_rb_file": (C.c_int, [C.c_void_p, C.c_long, C.c_char_p]),
+    "friq_batch_save_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "friq_batch_load_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
     "friq_reduce_rulebase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, ip, dp, dp, C.c_int, ip]),
     "friq_save_rb_to_text_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
     "friq_save_rb_to_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
@@ -190,6 +194,18 @@ class Batch:
         rant = np.zeros((self.cap, self.P.K)); rconc = np.zeros(self.cap)
         _ck(lib().friq_batch_get_rulebase(self.h, agent, C.byref(R), _p(rant), _p(rconc)))
         return R.value, rant[:R.value].copy(), rconc[:R.value].copy()
+
+    def save_rb_files(self, pattern, first=0, count=None, text=False):
+        _ck(lib().friq_batch_save_rb_files(self.h, first, self.n - first if count is None else count, pattern.encode(), int(text)))
+
+    def load_rb_file(self, path, agent=-1):
+        _ck(lib().friq_batch_load_rb_file(self.h, agent, path.encode()))
+
+    def save_checkpoint(self, path):
+        _ck(lib().friq_batch_save_checkpoint(self.h, path.encode()))
+
+    def load_checkpoint(self, path):
+        _ck(lib().friq_batch_load_checkpoint(self.h, path.encode()))
 
     def get_state(self):
         s = np.zeros((self.n, self.P.S)); a = np.zeros(self.n, np.int32)

@@ -158,6 +158,15 @@ int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double 
 int friq_save_rb_to_bin_file(const char *file_name, int K, int R, const double *rant, const double *rconc);
 int friq_load_rb_from_bin_file(const char *file_name, int K, int max_rules, int *R, double *rant, double *rconc);
 
+/* ---- batched rule-base I/O: the reference's formats either side of the batch */
+/* one file per agent of [first, first + count): `pattern` is a printf format with one %ld (agent index); text != 0: "%.18f " format */
+int friq_batch_save_rb_files(friq_batch *b, long first, long count, const char *pattern, int text);
+/* warm start (`-f file`, frirl_app_helpers.c:53-62) of one agent, or of all agents when agent < 0 */
+int friq_batch_load_rb_file(friq_batch *b, long agent, const char *file_name);
+/* all rule bases + fus_is_rule_inserted flags of a batch in ONE file (per-agent records in the reference's binary layout) */
+int friq_batch_save_checkpoint(friq_batch *b, const char *file_name);
+int friq_batch_load_checkpoint(friq_batch *b, const char *file_name);
+
 /* ---- device self-tests / calibration used by tests and bench.py */
 int friq_device_trig(const double *x, double *sin_out, double *cos_out, long n);        /* correctly rounded sin/cos */
 int friq_device_pow_x87(const double *x, double *out, long n, int p, int force_exact);  /* fast_pow.inl:17-27 */

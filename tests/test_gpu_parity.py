@@ -353,3 +353,42 @@ def test_batched_rule_base_reduction_equals_reference(fq, width, capfd):
     assert log == ref
     assert episodes == 2 + 110                          # the reference replays 1 + 111 episodes; speculation never adds accepted work
     P.close()
+
+
+def test_batched_rule_base_io_and_checkpoint_resume(fq, tmp_path):
+    """Per-agent dumps in the reference's text / binary formats, `-f` warm start for a batch, and a one-file checkpoint: a run
+    that is checkpointed, destroyed and resumed in a NEW batch must continue bit-identically to the uninterrupted run (rule
+    bases and the sticky fus_is_rule_inserted flag are the learner's whole persistent state between episodes)."""
+    import os
+    g = _golden.load("mountaincar")
+    P = fq.Problem("mountaincar", no_random=0)
+    n = 70
+    a = fq.Batch(P, n, 192, seed0=99)
+    a.run(700, fq.RUN_LEARN | fq.RUN_RETILE | fq.RUN_STOP_AT_EPISODE_END)   # everyone stops at an episode boundary
+    a.save_checkpoint(str(tmp_path / "ck.bin"))
+    a.save_rb_files(str(tmp_path / "agent%04ld.frirlrb.bin"), first=60, count=10)
+    a.save_rb_files(str(tmp_path / "agent%04ld.frirlrb.txt"), first=60, count=10, text=True)
+    for i in (60, 69):
+        R, rant, rconc = a.get_rulebase(i)
+        frant, frconc = fq.load_rb_bin(str(tmp_path / f"agent{i:04d}.frirlrb.bin"), P.K)
+        assert np.array_equal(frant, rant) and np.array_equal(frconc, rconc)
+        assert open(tmp_path / f"agent{i:04d}.frirlrb.txt", "rb").read() == _golden.rb_text(rant, rconc)
+    ep = a.gather()["episodes"]
+    # resume in a fresh batch: same seeds; the Philox counter is (episode, step), so the episode numbers must line up -
+    # a fresh batch starts at episode 1, hence compare against a reference batch that is ALSO restarted from the checkpoint
+    b = fq.Batch(P, n, 192, seed0=99); b.load_checkpoint(str(tmp_path / "ck.bin"))
+    c = fq.Batch(P, n, 192, seed0=99)
+    for i in range(n):
+        R, rant, rconc = a.get_rulebase(i); c.set_rulebase(rant, rconc, agent=i)
+    c.set_inserted(a.get_inserted())
+    b.run(400, fq.RUN_LEARN); c.run(400, fq.RUN_LEARN)
+    for i in (0, 31, 32, 69):
+        assert all(np.array_equal(x, y) for x, y in zip(b.get_rulebase(i), c.get_rulebase(i))), i
+    assert np.array_equal(b.gather()["last_return"], c.gather()["last_return"])
+    # warm start of every agent from the reference's own golden file == set_rulebase of its contents
+    d = fq.Batch(P, 33, 192, seed0=5); d.load_rb_file(os.path.join(_golden.GOLDEN, "mountaincar.frirlrb.bin"))
+    R, rant, rconc = d.get_rulebase(32)
+    assert np.array_equal(rant, g["final"][1]) and np.array_equal(rconc, g["final"][2]) and not d.get_inserted().any()
+    for x in (a, b, c, d):
+        x.close()
+    P.close()
