@@ -170,19 +170,13 @@ def main():
     groups = int(os.environ.get("FRIQ_GROUPS", 0)) or min(8, max(1, n // 32768))     # friq_batch_create: agent groups on their own streams
     mode = fq.RUN_LEARN | fq.RUN_RETILE      # agents are re-assigned to warps by rule count before every launch
 
-    # device-side result buffers for the NCCL gather of per-agent (return f64, steps i32, rules i32)
-    d_ret = torch.empty(n, dtype=torch.float64, device="cuda"); d_steps = torch.empty(n, dtype=torch.int32, device="cuda")
-    d_rules = torch.empty(n, dtype=torch.int32, device="cuda")
-    if world > 1:
-        g_ret = torch.empty(world * n, dtype=torch.float64, device="cuda"); g_steps = torch.empty(world * n, dtype=torch.int32, device="cuda")
-        g_rules = torch.empty(world * n, dtype=torch.int32, device="cuda")
-    stats = torch.zeros(3, dtype=torch.float64, device="cuda")
+    # the path's only exchange: per-agent (return f64, steps i32, rules i32) + rule-base statistics, ONE all-gather per step
+    xch = friq_dist.ResultExchange(dist if world > 1 else None, n, "cuda")
 
     def gather_results():
-        b.gather_device(ctypes.c_void_p(d_ret.data_ptr()), ctypes.c_void_p(d_steps.data_ptr()), ctypes.c_void_p(d_rules.data_ptr()), sptr)
-        if world > 1:       # the path's only exchange: per-agent results + rule-base statistics over NCCL/NVLink
-            friq_dist.gather_agent_results(dist, d_ret, d_steps, d_rules, out=(g_ret, g_steps, g_rules))
-            friq_dist.reduce_stats(dist, d_ret, d_rules, stats)
+        b.gather_device(ctypes.c_void_p(xch.ret.data_ptr()), ctypes.c_void_p(xch.steps.data_ptr()), ctypes.c_void_p(xch.rules.data_ptr()), sptr)
+        if world > 1:
+            xch.exchange()
 
     def barrier():
         if world > 1:

@@ -38,3 +38,34 @@ def reduce_stats(dist, ret, rules, stats=None):
     dist.all_reduce(stats[:2])
     dist.all_reduce(stats[2:], op=dist.ReduceOp.MAX)
     return stats
+
+
+class ResultExchange:
+    """The path's ONE exchange per step, as ONE collective: per-agent (return f64, steps i32, rules i32) live in a single
+    16 B/agent device buffer (three SoA segments; `ret`, `steps`, `rules` are views the engine writes into with
+    friq_batch_gather_device), which is all-gathered in one call; every rank then holds every agent's results, so the
+    rule-base statistics need no further all-reduce.  Outputs are in global agent order (contiguous shards)."""
+
+    def __init__(self, dist, n, device):
+        self.dist, self.n = dist, n
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.local = torch.empty(16 * n, dtype=torch.uint8, device=device)
+        self.ret = self.local[:8 * n].view(torch.float64)
+        self.steps = self.local[8 * n:12 * n].view(torch.int32)
+        self.rules = self.local[12 * n:].view(torch.int32)
+        self.all = torch.empty(self.world * 16 * n, dtype=torch.uint8, device=device) if self.world > 1 else self.local
+        self.g_ret = torch.empty(self.world * n, dtype=torch.float64, device=device)
+        self.g_steps = torch.empty(self.world * n, dtype=torch.int32, device=device)
+        self.g_rules = torch.empty(self.world * n, dtype=torch.int32, device=device)
+        self.stats = torch.zeros(3, dtype=torch.float64, device=device)
+
+    def exchange(self):
+        n, w = self.n, self.world
+        if w > 1:
+            self.dist.all_gather_into_tensor(self.all, self.local)
+        blocks = self.all.view(w, 16 * n)
+        self.g_ret.view(w, n).copy_(blocks[:, :8 * n].contiguous().view(torch.float64).view(w, n))
+        self.g_steps.view(w, n).copy_(blocks[:, 8 * n:12 * n].contiguous().view(torch.int32).view(w, n))
+        self.g_rules.view(w, n).copy_(blocks[:, 12 * n:].contiguous().view(torch.int32).view(w, n))
+        self.stats[0] = self.g_rules.sum(); self.stats[1] = self.g_ret.sum(); self.stats[2] = self.g_rules.max()
+        return self.g_ret, self.g_steps, self.g_rules, self.stats

@@ -31,6 +31,10 @@ def _worker(rank, world, port, n, q):
     ret = ids.double() * -10.0; steps = (ids % 1000).int(); rules = (8 + ids % 173).int()
     g_ret, g_steps, g_rules = friq_dist.gather_agent_results(dist, ret, steps, rules)
     stats = friq_dist.reduce_stats(dist, ret, rules)
+    x = friq_dist.ResultExchange(dist, cnt, "cpu")           # the one-collective form bench.py uses
+    x.ret.copy_(ret); x.steps.copy_(steps); x.rules.copy_(rules)
+    x_ret, x_steps, x_rules, x_stats = x.exchange()
+    assert torch.equal(x_ret, g_ret) and torch.equal(x_steps, g_steps) and torch.equal(x_rules, g_rules) and torch.equal(x_stats, stats)
     if rank == 0:
         q.put((g_ret.numpy(), g_steps.numpy(), g_rules.numpy(), stats.numpy()))
     dist.barrier()
