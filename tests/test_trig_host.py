@@ -19,6 +19,7 @@ def test_trig_is_correctly_rounded(tmp_path):
     dp = C.POINTER(C.c_double)
     L.shim_check.restype = C.c_long; L.shim_check.argtypes = [dp, C.c_long, dp]
     L.shim_dd_err.restype = C.c_double; L.shim_dd_err.argtypes = [dp, C.c_long]
+    L.shim_quick_err.restype = C.c_double; L.shim_quick_err.argtypes = [dp, C.c_long, dp]
     rng = np.random.default_rng(2024)
     k = np.arange(-12, 13)
     sets = [rng.uniform(-10, 10, 300000), rng.uniform(-4.5, 1.5, 200000), rng.uniform(-1e-3, 1e-3, 50000),
@@ -28,3 +29,7 @@ def test_trig_is_correctly_rounded(tmp_path):
         w = C.c_double()
         assert L.shim_check(x.ctypes.data_as(dp), x.size, C.byref(w)) == 0, w.value
         assert L.shim_dd_err(x.ctypes.data_as(dp), min(x.size, 40000)) < 1.0
+        # quick phase (Ziv): its error must stay well inside the bound the rounding test assumes (FRIQ_QUICK_ERR = 2^-61),
+        # and the test must send only a small share of the calls to the accurate phase
+        fb = C.c_double()
+        assert L.shim_quick_err(x.ctypes.data_as(dp), min(x.size, 100000), C.byref(fb)) < 2.0 and fb.value < 0.02

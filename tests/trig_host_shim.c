@@ -26,3 +26,19 @@ double shim_dd_err(const double *x, long n) {
     }
     return worst;
 }
+/* quick phase: max relative error of (h + l) vs binary128 in units of 2^-64, and the share of points the rounding test
+ * sends to the accurate phase */
+double shim_quick_err(const double *x, long n, double *fallback_share) {
+    double worst = 0; long fb = 0;
+    for (long i = 0; i < n; i++) {
+        friq_dd s, c; friq_sincos_quick(x[i], &s, &c);
+        __float128 es = sinq((__float128)x[i]), ec = cosq((__float128)x[i]);
+        __float128 ds = ((__float128)s.h + s.l - es) / es, dc = ((__float128)c.h + c.l - ec) / ec;
+        double a = fabs((double)ds) * 0x1p64, b = fabs((double)dc) * 0x1p64;
+        if (es != 0 && a > worst) worst = a;
+        if (ec != 0 && b > worst) worst = b;
+        if (!friq_quick_ok(s) || !friq_quick_ok(c)) fb++;
+    }
+    *fallback_share = (double)fb / (double)n;
+    return worst;
+}
