@@ -429,12 +429,12 @@ __device__ __forceinline__ void friq_hit_scan(const uint32_t *rbw, int R, const 
 #pragma unroll
     for (int a = 0; a < A; a++) hi[a] = 0xffffffffu;
 #pragma unroll 1
-    for (int i = 0; i < R; i += 4) {
-        uint32_t w[4];
+    for (int i = 0; i < R; i += 8) {
+        uint32_t w[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) w[u] = (i + u < R) ? rbw[(size_t)(i + u) * FRIQ_TILE] : 0xffffffffu;
+        for (int u = 0; u < 8; u++) w[u] = (i + u < R) ? rbw[(size_t)(i + u) * FRIQ_TILE] : 0xffffffffu;
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < 8; u++)
 #pragma unroll
             for (int a = 0; a < A; a++) hi[a] = min(hi[a], (w[u] == tgt[a]) ? (unsigned)(i + u) : 0xffffffffu);
     }
@@ -681,13 +681,21 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
         return;                                                                                          // :61-63
     }
     if (pb.skip_rules == 0) { rules = R; flags &= ~FRIQ_F_INSERTED; }
-    const double pre = __dmul_rn(0.04, ws);            // cheap superset of (wi/ws > wsig >= 0.05)
-    const bool filter = pb.wsig >= 0.05;
-    for (int i = 0; i < rules; i++) {
-        const double wi = sw[(size_t)i * FRIQ_TILE];
-        if (filter && !(wi > pre)) continue;
-        const double wgt = __ddiv_rn(wi, ws);                                                            // A6
-        if (wgt > pb.wsig) rbq[(size_t)i * FRIQ_TILE] = __dadd_rn(qnow, __dmul_rn(qdiff, wgt));          // A7
+    // cheap superset of (wi/ws > wsig): only the few rules that pass it pay the division; four rules per trip, one branch
+    const double pre = (pb.wsig >= 0.05) ? __dmul_rn(0.04, ws) : -1.0;
+#pragma unroll 1
+    for (int i = 0; i < rules; i += 4) {
+        double wi[4]; bool any = false;
+#pragma unroll
+        for (int u = 0; u < 4; u++) { wi[u] = (i + u < rules) ? sw[(size_t)(i + u) * FRIQ_TILE] : -2.0; any = any || (wi[u] > pre); }
+        if (!any) continue;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (wi[u] > pre) {
+                const double wgt = __ddiv_rn(wi[u], ws);                                                         // A6
+                if (wgt > pb.wsig) rbq[(size_t)(i + u) * FRIQ_TILE] = __dadd_rn(qnow, __dmul_rn(qdiff, wgt));    // A7
+            }
+        }
     }
 }
 

@@ -21,8 +21,10 @@
 
 #if defined(__CUDACC__)
 #define FRIQ_HD __host__ __device__ __forceinline__
+#define FRIQ_HD_COLD __host__ __device__ __noinline__      /* the accurate phase is rare: a real call keeps the kernels' hot code small */
 #else
 #define FRIQ_HD static inline
+#define FRIQ_HD_COLD static __attribute__((noinline))
 #endif
 
 #define FRIQ_PIO2_1 0x1.921fb54400000p+0
@@ -112,7 +114,7 @@ FRIQ_HD friq_dd friq_dd_add(friq_dd a, friq_dd b) {
 }
 
 /* sin and cos of x as double-doubles */
-FRIQ_HD void friq_sincos_dd(double x, friq_dd *sn, friq_dd *cs) {
+FRIQ_HD_COLD void friq_sincos_dd(double x, friq_dd *sn, friq_dd *cs) {
     /* 1. x = k*pi/2 + r, |r| <= pi/4 (+ rounding), r as double-double */
     double k = rint(x * FRIQ_TWO_OVER_PI);
     double r0 = fma(-k, FRIQ_PIO2_1, x);                 /* exact */
