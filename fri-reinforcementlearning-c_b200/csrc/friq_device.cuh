@@ -407,6 +407,9 @@ __device__ __forceinline__ void friq_q_cooperative(const friq_devprob &pb, const
 
 // packed dictionary indices of the observation with VE values vo[] (grid indices ci[k] when known), or FRIQ_NO_TARGET when
 // some dimension's VE value is no dictionary entry's (then no rule can be at distance 0)
+//   ci[k] >= 0   the observation is the grid value with that index (quantiser)
+//   ci[k] == -1  unknown: search the dictionary for the VE value (custom start states)
+//   ci[k] == -2  the default episode start state: the host has done the search (def_hit)
 template <int S>
 __device__ __forceinline__ uint32_t friq_obs_word(const friq_devprob &pb, const double *vo, const int *ci)
 {
@@ -414,7 +417,8 @@ __device__ __forceinline__ uint32_t friq_obs_word(const friq_devprob &pb, const 
 #pragma unroll
     for (int k = 0; k < S; k++) {
         int j = ci[k];
-        if (j < 0) { for (int t = 0; t < pb.dict_len[k]; t++) if (pb.dict_ve[k][t] == vo[k]) { j = t; break; } }
+        if (j == -2) j = pb.def_hit[k];
+        else if (j < 0) { for (int t = 0; t < pb.dict_len[k]; t++) if (pb.dict_ve[k][t] == vo[k]) { j = t; break; } }
         ok = ok && j >= 0;
         word |= (uint32_t)(j & (FRIQ_MAXDICT - 1)) << (FRIQ_IDX_BITS * k);
     }

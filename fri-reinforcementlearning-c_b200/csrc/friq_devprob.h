@@ -47,6 +47,7 @@ typedef struct friq_devprob {
     int dict_len[FRIQ_MAXK];
     int act_dict[FRIQ_MAXA];                  /* dictionary index (dimension S) of action a */
     int act_hit[FRIQ_MAXA];                   /* dictionary index whose VE value equals act_ve[a] (what a rule at distance 0 holds), -1 none */
+    int def_hit[FRIQ_MAXK];                   /* the same for the episode start state: index whose VE value equals ve_def[k], -1 none */
     double qdiff_pos, qdiff_neg, wsig, qdiff_final_tol, reward_good_above, pad0;
     double u0[FRIQ_MAXK], udiv[FRIQ_MAXK];
     double values_def[FRIQ_MAXK], ve_def[FRIQ_MAXK];

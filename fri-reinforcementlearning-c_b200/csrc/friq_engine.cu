@@ -104,9 +104,9 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             if (initial) {                               // frirl_episode.c:46-82
 #pragma unroll
                 for (int k = 0; k < S; k++) {
-                    if (st.s0) { s[k] = qs[k] = st.s0[(size_t)k * st.n_pad + ag]; vo[k] = vc[k] = friq_obs_ve(pb, k, s[k]); }
-                    else { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; }
-                    cur[k] = cq[k] = s[k]; qi[k] = ci[k] = -1;
+                    if (st.s0) { s[k] = qs[k] = st.s0[(size_t)k * st.n_pad + ag]; vo[k] = vc[k] = friq_obs_ve(pb, k, s[k]); ci[k] = -1; }
+                    else { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; ci[k] = -2; }   // -2: dictionary index known to the host (def_hit)
+                    cur[k] = cq[k] = s[k]; qi[k] = -1;
                 }
                 ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
                 prev_numru = R;

@@ -153,6 +153,11 @@ static void refresh_hit_scan(friq_problem *P)
         for (int j = 0; j < hp->dict_len[hp->S]; j++)
             if (hp->dict_ve[hp->S][j] == hp->act_ve[a]) { hp->act_hit[a] = j; break; }
     }
+    for (int k = 0; k < hp->S; k++) {
+        hp->def_hit[k] = -1;
+        for (int j = 0; j < hp->dict_len[k]; j++)
+            if (hp->dict_ve[k][j] == hp->ve_def[k]) { hp->def_hit[k] = j; break; }
+    }
     hp->hit_scan = (injective && hp->safe_range) ? 1 : 0;
 }
 
