@@ -540,8 +540,8 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
             const double *tb = tile[bsel];
 #pragma unroll 1
             for (int i = 0; i < cnt; i += UNR) {
-                double wv[UNR][A]; bool z[UNR][A]; double q[UNR];
-                unsigned bad = 0;
+                constexpr int NC = UNR * A;              // all chains of the trip, evaluated stage by stage
+                double sv[NC], wv[NC], dv[NC], q[UNR]; bool live[NC];
 #pragma unroll
                 for (int u = 0; u < UNR; u++) {
                     const double *r = tb + (size_t)min(i + u, cnt - 1) * RW;
@@ -556,33 +556,25 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
 #pragma unroll
                     for (int a = 0; a < A; a++) {
                         const double da = __dsub_rn(ave[a], r[S]);
-                        const double sv = __dadd_rn(__dmul_rn(da, da), ssum);
-                        z[u][a] = friq_is_zero(sv);
-                        wv[u][a] = friq_shepard_weight_fast<P, SAFE>(sv, bad, !z[u][a]);
+                        sv[u * A + a] = __dadd_rn(__dmul_rn(da, da), ssum);
+                        live[u * A + a] = !friq_is_zero(sv[u * A + a]);
                     }
                 }
+                unsigned bad = 0;
+                friq_shepard_weights_n<P, SAFE, NC>(sv, wv, bad, live, dv);
                 if (bad) {
 #pragma unroll
-                    for (int u = 0; u < UNR; u++) {
-                        const double *r = tb + (size_t)min(i + u, cnt - 1) * RW;
-                        double ssum = 0.0;
-#pragma unroll
-                        for (int k = 0; k < S; k++) { const double d = __dsub_rn(vc[k], r[k]); ssum = (k == 0) ? __dmul_rn(d, d) : __dadd_rn(ssum, __dmul_rn(d, d)); }
-#pragma unroll
-                        for (int a = 0; a < A; a++) {
-                            const double da = __dsub_rn(ave[a], r[S]);
-                            wv[u][a] = friq_shepard_weight<P>(z[u][a] ? 1.0 : __dadd_rn(__dmul_rn(da, da), ssum));
-                        }
-                    }
+                    for (int n = 0; n < NC; n++)
+                        if ((bad >> n) & 1u) wv[n] = SAFE ? friq_shepard_weight_from_sqrt<P>(dv[n]) : friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
                 }
 #pragma unroll
                 for (int u = 0; u < UNR; u++) {
                     if (u == 0 || i + u < cnt) {
 #pragma unroll
                         for (int a = 0; a < A; a++) {
-                            if (z[u][a] && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q[u]; }
-                            vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u][a], q[u]));
-                            ws[a] = __dadd_rn(ws[a], wv[u][a]);
+                            if (!live[u * A + a] && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q[u]; }
+                            vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u * A + a], q[u]));
+                            ws[a] = __dadd_rn(ws[a], wv[u * A + a]);
                         }
                     }
                 }
