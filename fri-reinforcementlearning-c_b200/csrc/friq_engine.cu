@@ -723,6 +723,71 @@ k_classic_step(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
     for (int a = 0; a < A; a++) o[4 + a] = actconc[a];
 }
 
+// ---- any number of actions (runtime A <= FRIQ_MAXA): the per-call kernels behind the drop-in API for problems that are not
+// one of the three example shapes.  One action at a time (friq_action_pass with one rule per trip, library sqrt / rcp range
+// checks on: nothing is assumed about the problem), conclusions written straight to global memory.
+template <int S, int P>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
+k_best_action_anyA(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ states, double *actconc_out, int *best)
+{
+    FRIQ_SMEM_PROLOGUE();
+    (void)sw;
+    const int A = pb.A;
+    double vo[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) vo[k] = friq_obs_ve(pb, k, states[(size_t)ag * S + k]);    // get_best_action.c:60-63
+    int b = 0; double bv = 0.0;
+    for (int a = 0; a < A; a++) {
+        double conc; int hidx;
+        friq_action_pass<S, P, 1, false>(pb, rbw, rbq, st.R[ag], vo, pb.act_ve[a], conc, hidx);
+        actconc_out[(size_t)ag * A + a] = conc;
+        if (a == 0 || bv < conc) { bv = conc; b = a; }                                    // first maximum wins (max.inl:16-28)
+    }
+    best[ag] = b;
+}
+
+template <int S, int P>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
+k_classic_step_anyA(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ in, double *__restrict__ out)
+{
+    constexpr int K = S + 1, NIN = K + S + 3;
+    FRIQ_SMEM_PROLOGUE();
+    const int A = pb.A, NOUT = 4 + A;
+    const double *x = in + (size_t)ag * NIN;
+    double *o = out + (size_t)ag * NOUT;
+    double qs[K], vq[K], vc[K], cq[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { qs[k] = x[k]; vq[k] = friq_obs_ve(pb, k, qs[k]); }
+#pragma unroll
+    for (int k = 0; k < S; k++) { cq[k] = x[K + 1 + k]; vc[k] = friq_obs_ve(pb, k, cq[k]); }
+    const double reward = x[K];
+    int a2 = (int)x[K + 1 + S];
+    const bool learn = x[K + 2 + S] != 0.0;
+    int R = st.R[ag], flags = st.flags[ag];
+    for (int a = 0; a < A; a++) o[4 + a] = 0.0;
+    if (a2 < 0) {
+        double bv = 0.0;
+        for (int a = 0; a < A; a++) {
+            double conc; int hidx;
+            friq_action_pass<S, P, 1, false>(pb, rbw, rbq, R, vc, pb.act_ve[a], conc, hidx);
+            o[4 + a] = conc;
+            if (a == 0 || bv < conc) { bv = conc; a2 = a; }
+        }
+    }
+    if (learn) {
+        cq[S] = pb.act_val[a2]; vc[S] = friq_obs_ve(pb, S, cq[S]);
+        double qp, qnow, wsp, ws;
+        friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vc, qp, wsp);
+        const int hitq = friq_vag_concl<K, P>(pb, rbw, rbq, sw, R, vq, qnow, ws);
+        int qi[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) qi[k] = -1;
+        friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
+        st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
+    }
+    o[0] = (double)a2; o[1] = (double)R; o[2] = (flags & FRIQ_F_INSERTED) ? 1.0 : 0.0; o[3] = (flags & FRIQ_F_OVERFLOW) ? 1.0 : 0.0;
+}
+
 // five_rule_distance (five_rule_distance.c:63-295): every rule's scaled distance from the point, and the first
 // rule at distance 0 (-1: none).  All distances are written (the reference stops at the first exact hit and
 // leaves the rest stale).
@@ -969,7 +1034,7 @@ int friqd_device_sync(void) { CK(cudaDeviceSynchronize()); return 0; }
 int friqd_sync(void *stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
 const char *friqd_error_string(int err)
 {
-    if (err == FRIQ_ERR_SHAPE) return "unsupported problem shape (S, p, A): supported are (2,3,3), (4,5,3), (4,5,21)";
+    if (err == FRIQ_ERR_SHAPE) return "unsupported problem shape: per-call entry points need 1 <= S <= 4 state dimensions, p = S + 1 and A <= 32 actions; the fused kernels the shapes (S, p, A) of the three examples";
     return cudaGetErrorString((cudaError_t)err);
 }
 
@@ -1032,6 +1097,8 @@ int friqd_vag_concl(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
     if (hp->S == 2 && hp->p == 3) k_vag_concl<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
     else if (hp->S == 4 && hp->p == 5) k_vag_concl<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
+    else if (hp->S == 1 && hp->p == 2) k_vag_concl<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
+    else if (hp->S == 3 && hp->p == 4) k_vag_concl<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1044,6 +1111,11 @@ int friqd_best_action(const friq_devprob *hp, const friq_devprob *dprob, friq_de
     if (FRIQ_SHAPE_MC(hp)) k_best_action<2, 3, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else if (FRIQ_SHAPE_AC(hp)) k_best_action<4, 5, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else if (FRIQ_SHAPE_CP(hp)) k_best_action<4, 5, 21, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (hp->A < 1 || hp->A > FRIQ_MAXA) return FRIQ_ERR_SHAPE;
+    else if (hp->S == 1 && hp->p == 2) k_best_action_anyA<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (hp->S == 2 && hp->p == 3) k_best_action_anyA<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (hp->S == 3 && hp->p == 4) k_best_action_anyA<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (hp->S == 4 && hp->p == 5) k_best_action_anyA<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1055,6 +1127,8 @@ int friqd_update_sarsa(const friq_devprob *hp, const friq_devprob *dprob, friq_d
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
     if (hp->S == 2 && hp->p == 3) k_update_sarsa<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
     else if (hp->S == 4 && hp->p == 5) k_update_sarsa<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
+    else if (hp->S == 1 && hp->p == 2) k_update_sarsa<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
+    else if (hp->S == 3 && hp->p == 4) k_update_sarsa<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1066,6 +1140,11 @@ int friqd_classic_step(const friq_devprob *hp, const friq_devprob *dprob, friq_d
     if (FRIQ_SHAPE_MC(hp)) k_classic_step<2, 3, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
     else if (FRIQ_SHAPE_AC(hp)) k_classic_step<4, 5, 3, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
     else if (FRIQ_SHAPE_CP(hp)) k_classic_step<4, 5, 21, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (hp->A < 1 || hp->A > FRIQ_MAXA) return FRIQ_ERR_SHAPE;
+    else if (hp->S == 1 && hp->p == 2) k_classic_step_anyA<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (hp->S == 2 && hp->p == 3) k_classic_step_anyA<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (hp->S == 3 && hp->p == 4) k_classic_step_anyA<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (hp->S == 4 && hp->p == 5) k_classic_step_anyA<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1076,6 +1155,8 @@ int friqd_rule_distance(const friq_devprob *hp, const friq_devprob *dprob, friq_
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
     if (hp->S == 2) k_rule_distance<2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
     else if (hp->S == 4) k_rule_distance<4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
+    else if (hp->S == 1) k_rule_distance<1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
+    else if (hp->S == 3) k_rule_distance<3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;

@@ -60,6 +60,14 @@ def main():
         keep = [l.split(" rules from")[0] if l.startswith("Loaded") else l for l in keep]
         open(os.path.join(out, "mountaincar_reduction.log"), "w").write("\n".join(keep) + "\n")
         print(f"mountaincar reduction: {len(open(os.path.join(out, 'mountaincar_reduced.frirlrb.txt')).readlines())} rules, {len(keep)} log lines")
+    # a problem that is none of the examples (3 state dimensions, 5 actions, skip_rules = 0): tests/dropin/custom_problem.c, our own
+    # program on the reference's public API, built against the reference by oracle/Makefile
+    exe = os.path.join(HERE, "_ref", "custom_ref")
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe], cwd=tmp, check=True, capture_output=True, text=True)
+        open(os.path.join(out, "custom_problem.out"), "w").write(r.stdout)
+        shutil.copy(os.path.join(tmp, "custom.frirlrb.txt"), os.path.join(out, "custom_problem.frirlrb.txt"))
+        print(f"custom problem: {len(r.stdout.splitlines())} output lines")
 
 
 if __name__ == "__main__":

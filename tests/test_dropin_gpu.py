@@ -172,3 +172,15 @@ def test_reference_api_calls_match_oracle(env, tmp_path):
     hit, conc = ag.vag_concl(pts[0])
     f = next(it).split()
     assert int(f[1]) == hit and float.fromhex(f[2]) == conc
+
+
+def test_custom_problem_on_the_reference_api_matches_the_reference(tmp_path):
+    """tests/dropin/custom_problem.c - a program on the reference's public API for a problem that is none of the examples
+    (3 state dimensions, 5 actions, skip_rules = 0, host-callback environment) - prints, built against the B200 engine, exactly
+    what it prints built against the reference (golden recorded by oracle/make_golden.py from oracle/_ref/custom_ref): the
+    per-episode log, the learned rule base and per-call results, all as hex floats.  Exercises the generic-shape kernels."""
+    r = subprocess.run([_exe("custom_dropin")], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = open(os.path.join(_golden.GOLDEN, "custom_problem.out")).read()
+    assert r.stdout.splitlines() == want.splitlines()
+    assert open(tmp_path / "custom.frirlrb.txt", "rb").read() == open(os.path.join(_golden.GOLDEN, "custom_problem.frirlrb.txt"), "rb").read()
