@@ -392,3 +392,68 @@ def test_batched_rule_base_io_and_checkpoint_resume(fq, tmp_path):
     for x in (a, b, c, d):
         x.close()
     P.close()
+
+
+def test_full_size_batch_properties(fq):
+    """BASELINE config 3 at its full size (65,536 mountaincar agents on one GPU), checked through size-independent properties:
+    (1) with no_random = 1 every one of the 65,536 agents must walk the reference's own trajectory (SURVEY 8d, C3's self-check):
+        same rule count, return and steps as the oracle's single agent, and a sampled agent's rule base bit for bit;
+    (2) sharding invariance - the batch cut into two shards with first_agent offsets (what two GPUs would run) gives every
+        agent exactly the result it gets in the whole batch, with exploration on and re-tiling between launches."""
+    n, steps = 65536, 900
+    P = fq.Problem("mountaincar")                                   # no_random = 1
+    b = fq.Batch(P, n, 192)
+    for _ in range(3):
+        b.run(steps // 3, fq.RUN_LEARN | fq.RUN_RETILE)
+    o = b.gather()
+    a = _oracle.Agent(_oracle.Problem(0, trig=1), 192); a.run_steps(steps); sm = a.summary()
+    assert np.all(o["rules"] == sm["R"]) and np.all(o["total_steps"] == steps)
+    assert np.all(o["last_return"] == sm["last_return"]) and np.all(o["last_steps"] == sm["last_steps"]) and np.all(o["episodes"] == sm["episode_num"] - 1)
+    for agent in (0, 31337, n - 1):
+        R, rant, rconc = b.get_rulebase(agent); oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(rant, orant) and np.array_equal(rconc, orconc)
+    b.close(); P.close()
+    P = fq.Problem("mountaincar", no_random=0)
+    whole = fq.Batch(P, n, 192, seed0=0x5EED0000, first_agent=0)
+    lo = fq.Batch(P, n // 2, 192, seed0=0x5EED0000, first_agent=0)
+    hi = fq.Batch(P, n // 2, 192, seed0=0x5EED0000, first_agent=n // 2)
+    for x in (whole, lo, hi):
+        for _ in range(2):
+            x.run(300, fq.RUN_LEARN | fq.RUN_RETILE)
+    w, l, h = whole.gather(), lo.gather(), hi.gather()
+    for k in ("rules", "last_return", "last_steps", "episodes", "sum_rules"):
+        assert np.array_equal(w[k], np.concatenate([l[k], h[k]])), k
+    assert len(np.unique(w["rules"])) > 10                          # exploration really diversifies the agents
+    for agent in (5, n // 2 + 77):
+        src = lo if agent < n // 2 else hi
+        assert all(np.array_equal(x, y) for x, y in zip(whole.get_rulebase(agent), src.get_rulebase(agent % (n // 2))))
+    for x in (whole, lo, hi):
+        x.close()
+    P.close()
+
+
+def test_shared_rule_base_at_config4_size_matches_oracle_samples(fq):
+    """BASELINE config 4 at one GPU's share of its full size (131,072 acrobot agents against ONE 10,240-rule base, greedy
+    inference): sampled agents must end in exactly the state the oracle port reaches, and the batch must be deterministic."""
+    rng = np.random.default_rng(1234)
+    P = fq.Problem("acrobot")
+    n, R, steps = 131072, 10240, 40
+    u = P.tables()["u"]
+    idx = np.unique(rng.integers(0, P.U, size=(3 * R, P.K)), axis=0)
+    idx = idx[rng.permutation(len(idx))[:R]]
+    rant = np.stack([u[k][idx[:, k]] for k in range(P.K)], axis=1)
+    rconc = np.random.default_rng(1235).uniform(-1000, 1000, R)
+    s0 = np.zeros((n, P.S)); s0[:, :2] = np.random.default_rng(4242).uniform(-np.pi / 2, np.pi / 2, size=(n, 2))
+    res = []
+    for _ in range(2):
+        b = fq.Batch(P, n, P.ncorner)
+        b.set_shared_rulebase(rant, rconc); b.set_initial_state(s0)
+        b.run(steps, 0)
+        res.append(b.get_state()); b.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    OP = _oracle.Problem(1, trig=1)
+    for i in (0, 65535, n - 1):
+        ag = _oracle.Agent(OP, R + 8); ag.set_rb(rant, rconc); ag.set_learning(0); ag.set_initial_state(s0[i])
+        ag.run_steps(steps)
+        assert np.array_equal(res[0][0][i], ag.summary()["s"]), i
+    P.close()
