@@ -460,9 +460,94 @@ __device__ __forceinline__ void friq_hit_scan(const uint32_t *rbw, int R, const 
 #define FRIQ_COMPACT_GMAX 1     /* lane groups per pair (2, 4, 8) measured SLOWER on B200 than one lane per pair: the segment shuffles of the
                                 * ordered sums cost more than the idle lanes save (gpurun_out/variants14.log); kept for experiments */
 #endif
-template <int S, int P, int A, int UNR, bool SAFE>
-__device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw, int R,
-                                                     const double *vo_obs, const double *vo_q, unsigned wmask, const unsigned (&nm)[A], unsigned qm,
+// dictionary cell of a packed word (row / column of the memoised weights pb.wtab)
+template <int K>
+__device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
+{
+    int c = (int)(w & (FRIQ_MAXDICT - 1));
+#pragma unroll
+    for (int k = 1; k < K; k++) c += (int)((w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)) * pb.wlin[k];
+    return c;
+}
+
+// ---- table mode: the per-agent list of rule cells (friq_devstate.rbc) is stored in blocks of FRIQ_CELL_VEC rules per lane,
+// [tile][slot / 8][lane][8] u16, so that a lane fetches the cells of 8 consecutive rules of a column with ONE 16-byte load;
+// the unused tail of the last block holds cell 0 (any valid column: those weights are loaded but never added).
+#define FRIQ_CELL_VEC 8
+__host__ __device__ __forceinline__ size_t friq_cap8(int cap) { return (size_t)((cap + FRIQ_CELL_VEC - 1) & ~(FRIQ_CELL_VEC - 1)); }
+__device__ __forceinline__ size_t friq_rbc_index(int i, int lane) { return ((size_t)(i >> 3) * FRIQ_TILE + lane) * FRIQ_CELL_VEC + (i & 7); }
+
+// weights (looked up in the pair's table row through the block's cells) and consequents of one block of 8 rules
+__device__ __forceinline__ void friq_tab_load(const double *__restrict__ rowd, const uint4 c, const double *pq, double (&t)[8], double (&q)[8])
+{
+    const unsigned cc[8] = { c.x & 0xffffu, c.x >> 16, c.y & 0xffffu, c.y >> 16, c.z & 0xffffu, c.z >> 16, c.w & 0xffffu, c.w >> 16 };
+#pragma unroll
+    for (int u = 0; u < 8; u++) { t[u] = __ldg(rowd + cc[u]); q[u] = pq[(size_t)u * FRIQ_TILE]; }
+}
+// the block's terms added in rule order (BestAct.c:216-217 / FIVEVagConcl.c:234-235); cnt < 8 only for a column's last block
+template <bool FULL>
+__device__ __forceinline__ void friq_tab_acc(const double (&t)[8], const double (&q)[8], int cnt, bool isq, double *psw, double &vag, double &ws)
+{
+    if (isq) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (FULL || u < cnt) psw[(size_t)u * FRIQ_TILE] = t[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+        if (FULL || u < cnt) { vag = __dadd_rn(vag, __dmul_rn(t[u], q[u])); ws = __dadd_rn(ws, t[u]); }
+}
+// Shepard sums of one pair from the memoised weights: rules 0 .. Rt-1 of column j of the tile; block b+1's loads and block
+// b+2's cells are in flight while block b is added up
+__device__ __forceinline__ void friq_tab_sums(const double *__restrict__ rowd, const unsigned short *rbc_tile, const double *tq, double *tsw,
+                                              int j, int Rt, bool isq, double &vag, double &ws)
+{
+    const uint4 *pc = reinterpret_cast<const uint4 *>(rbc_tile) + j;        // block b of the column: pc[b * 32]
+    const double *pq = tq + j; double *psw = tsw + j;
+    const int nb = (Rt + 7) >> 3;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    double tA[8], qA[8], tB[8], qB[8];
+    uint4 cn = zero;
+    if (nb > 0) friq_tab_load(rowd, pc[0], pq, tA, qA);
+    if (nb > 1) cn = pc[FRIQ_TILE];
+#pragma unroll 1
+    for (int b = 0; b < nb; b += 2) {
+        uint4 cnn = zero;
+        if (b + 1 < nb) friq_tab_load(rowd, cn, pq + 8 * FRIQ_TILE, tB, qB);
+        if (b + 2 < nb) cnn = pc[(size_t)(b + 2) * FRIQ_TILE];
+        { const int cnt = Rt - 8 * b; if (cnt >= 8) friq_tab_acc<true>(tA, qA, 8, isq, psw, vag, ws); else friq_tab_acc<false>(tA, qA, cnt, isq, psw, vag, ws); }
+        if (b + 1 < nb) {
+            if (b + 2 < nb) friq_tab_load(rowd, cnn, pq + 16 * FRIQ_TILE, tA, qA);
+            cn = zero;
+            if (b + 3 < nb) cn = pc[(size_t)(b + 3) * FRIQ_TILE];
+            const int cnt = Rt - 8 * (b + 1);
+            if (cnt >= 8) friq_tab_acc<true>(tB, qB, 8, isq, psw + 8 * FRIQ_TILE, vag, ws); else friq_tab_acc<false>(tB, qB, cnt, isq, psw + 8 * FRIQ_TILE, vag, ws);
+        }
+        pq += 16 * FRIQ_TILE; psw += 16 * FRIQ_TILE;
+    }
+}
+// the computed sums of one pair, one rule at a time through the library-exact chain: the table-mode kernel's rare fall-back
+// (a point that is no dictionary cell: custom off-grid start states), kept out of line so that it costs the kernel no registers
+template <int K, int P>
+__device__ __noinline__ void friq_pair_sums_slow(const friq_devprob *pbp, const uint32_t *cw, const double *cq, double *csw, int Rp, int isq,
+                                                 const double *pt, double *out)
+{
+    double vag = 0.0, ws = 0.0, p[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) p[k] = pt[k];
+    for (int i = 0; i < Rp; i++) {
+        const double wi = friq_shepard_weight<P>(friq_dist2<K>(*pbp, cw[(size_t)i * FRIQ_TILE], p));
+        if (isq) csw[(size_t)i * FRIQ_TILE] = wi;
+        vag = __dadd_rn(vag, __dmul_rn(wi, cq[(size_t)i * FRIQ_TILE]));
+        ws = __dadd_rn(ws, wi);
+    }
+    out[0] = vag; out[1] = ws;
+}
+
+template <int S, int P, int A, int UNR, bool SAFE, bool TAB>
+__device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw,
+                                                     const unsigned short *rbc /* TAB: the TILE's rule cells (friq_devstate.rbc layout) */, int R,
+                                                     const double *vo_obs, const double *vo_q, uint32_t ow, uint32_t qw,
+                                                     unsigned wmask, const unsigned (&nm)[A], unsigned qm,
                                                      unsigned char *plist /* 32 bytes of shared memory per warp */,
                                                      double (&conc)[A], double &vagq, double &wsq)
 {
@@ -514,10 +599,32 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             pt[S] = (c == A) ? y : pb.act_ve[c < A ? c : 0];
         }
         const int Rj = __shfl_sync(wmask, R, j);
-        const int Rp = has ? Rj : 0;
         const bool isq = has && c == A;
-        // ---- sequential Shepard sums over the owner's rules: g * UNR rules per trip, my block starts at i + gt * UNR
         double vag = 0.0, ws = 0.0;
+        // ---- table mode: a pair whose point is a dictionary cell looks the weight of every rule up (pb.wtab)
+        bool tab = false;
+        if constexpr (TAB) {
+            const uint32_t x = __shfl_sync(wmask, ow, j), y = __shfl_sync(wmask, qw, j);
+            const int ah = pb.act_hit[c < A ? c : 0];
+            const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET);
+            tab = has && pw != FRIQ_NO_TARGET;
+            if (tab) {
+                const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wcells;
+                asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
+                friq_tab_sums(rowd, rbc, tq, tsw, j, Rj, isq, vag, ws);
+            }
+            const bool slow = has && !tab;
+            if (__any_sync(wmask, slow)) {
+                if (slow) {
+                    double out[2];
+                    friq_pair_sums_slow<K, P>(&pb, tw + j, tq + j, tsw + j, Rj, isq ? 1 : 0, pt, out);
+                    vag = out[0]; ws = out[1];
+                }
+            }
+        }
+        if constexpr (!TAB) {
+        const int Rp = has ? Rj : 0;
+        // ---- sequential Shepard sums over the owner's rules: g * UNR rules per trip, my block starts at i + gt * UNR
         const int stride = g * UNR;
         uint32_t w[UNR]; double q[UNR];
 #pragma unroll
@@ -567,6 +674,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
 #pragma unroll
             for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
         }
+        }   // !TAB
         const double res = __ddiv_rn(vag, ws);                                               // BestAct.c:265
         // ---- hand the results back to the owners (first lane of the pair's group)
         __syncwarp(wmask);

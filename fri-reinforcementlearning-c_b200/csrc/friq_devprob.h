@@ -58,6 +58,10 @@ typedef struct friq_devprob {
     double dict_val[FRIQ_MAXK][FRIQ_MAXDICT];
     double dict_ve[FRIQ_MAXK][FRIQ_MAXDICT];
     const double *u, *ve;                     /* device pointers, [K][U] row-major */
+    const double *wtab;                       /* device pointer or NULL: memoised Shepard weights 1/d^p between any two dictionary cells,
+                                               * [wcells][wcells], cell = sum_k index_k * wlin[k] (built by k_build_wtab with the very device
+                                               * functions the kernels use, so a looked-up weight IS the computed one) */
+    int wcells, wlin[FRIQ_MAXK], padw;
     /* ---- everything above is staged to shared memory; the tail stays in global ---- */
     unsigned int corner[256];                 /* packed 2^K corner rules, frirl_init_rb.c:99-126 */
 } friq_devprob;
@@ -84,6 +88,11 @@ typedef struct friq_devstate {
     int *hitq;                  /* [n_pad] exact-hit rule of Q(s,a) for the pending update, -1 none, -2 unknown */
     double *s0;                 /* [FRIQ_MAXK][n_pad] optional per-agent episode start state (NULL: values_def) */
     int *agent_of_slot;         /* [n_pad] which agent lives in slot p (identity unless re-tiled by rule count) */
+    /* derived per-agent indexes of the fused kernel's table mode (friq_devprob.wtab); rebuilt from rbw before every launch
+     * (k_refresh_index) and kept current by the kernel when it appends a rule; NULL when the problem has no table */
+    unsigned short *rbc;        /* [tiles][cap][32] dictionary cell of every rule (column of wtab) */
+    unsigned short *cmap;       /* [tiles][idx_cells][32] 1 + index of the first rule in that cell, 0 = none: exact hits in O(1) */
+    int idx_cells;              /* cells per agent in cmap (= friq_devprob.wcells when the arrays were sized) */
 } friq_devstate;
 
 #ifdef __cplusplus
@@ -127,6 +136,7 @@ int friqd_update_sarsa(const friq_devprob *hprob, const friq_devprob *dprob, fri
 int friqd_classic_step(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_in, double *d_out, void *stream);
 int friqd_rule_distance(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_dists, int *d_hit, void *stream);
 int friqd_bestact_dists(const friq_devprob *hprob, friq_devstate st, const double *d_dists, double *d_conc, void *stream);
+int friqd_build_wtab(const friq_devprob *hprob, const friq_devprob *dprob, double *d_wtab);
 int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream);
 int friqd_pow_x87(const double *d_x, double *d_out, long n, int p, int force_exact, void *stream);
 int friqd_fp64_peak(double *out_ginstr_per_s, int iters);

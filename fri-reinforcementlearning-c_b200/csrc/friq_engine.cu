@@ -29,6 +29,9 @@
 #ifndef FRIQ_MINB_COOP
 #define FRIQ_MINB_COOP 2
 #endif
+#ifndef FRIQ_MINB_TAB
+#define FRIQ_MINB_TAB 2      /* table mode (COOP = 2); 3 and 4 CTAs per SM spill and measured 25-35 % slower */
+#endif
 #ifndef FRIQ_COMPACT_UNR
 #define FRIQ_COMPACT_UNR 6    /* rules per trip (= independent chains per lane) of friq_pairs_compacted */
 #endif
@@ -37,6 +40,14 @@
 #endif
 #ifndef FRIQ_QCOOP_MAX
 #define FRIQ_QCOOP_MAX 8     /* fewer lanes than this needing Q(s,a): friq_q_cooperative instead of the WITHQ pass */
+#endif
+
+#ifdef FRIQ_TIMELINE   /* experiments only (tools/timeline.py): one record per warp of k_run_steps */
+#define FRIQ_TL_MAX (1 << 18)
+__device__ unsigned long long friq_tl_buf[FRIQ_TL_MAX][4];
+__device__ unsigned int friq_tl_n;
+__device__ __forceinline__ unsigned long long friq_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int friq_smid() { unsigned int v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
 #endif
 
 struct __align__(16) friq_smem_t {
@@ -59,12 +70,17 @@ struct __align__(16) friq_smem_t {
 // COOP: exact hits by the integer sweep and cooperative Shepard sums ONLY (problems with hit_scan whose visited
 // (observation, action) pairs mostly have a rule - mountaincar); the lock-step pass is not even compiled in, which halves the
 // register count and doubles the resident warps of this then latency-bound kernel.
-template <int S, int P, int A, int ACH, int ENV, int UNR, bool SAFE, bool COOP>
-__global__ void __launch_bounds__(FRIQ_BLOCK, COOP ? FRIQ_MINB_COOP : FRIQ_MINB)
+// COOP = 2: the same in TABLE MODE - exact hits through the agent's cell-to-rule map, Shepard weights looked up in the problem's
+// memoised table (friq_devprob.wtab); the computed chain survives only as an out-of-line fall-back.
+template <int S, int P, int A, int ACH, int ENV, int UNR, bool SAFE, int COOP>
+__global__ void __launch_bounds__(FRIQ_BLOCK, COOP == 2 ? FRIQ_MINB_TAB : COOP ? FRIQ_MINB_COOP : FRIQ_MINB)
 k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
 {
     constexpr int K = S + 1;
     __shared__ unsigned char pair_list[FRIQ_BLOCK / 32][32];            // friq_pairs_compacted, per warp
+#ifdef FRIQ_TIMELINE
+    const unsigned long long tl_t0 = friq_globaltimer();
+#endif
     FRIQ_SMEM_PROLOGUE();
     double *prevq = st.prevq ? st.prevq + tile_off : nullptr;
 
@@ -88,6 +104,20 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     for (int k = 0; k < K; k++) {
         qi[k] = -1;
         for (int j = 0; j < pb.grid_len[k]; j++) if (pb.dict_val[k][j] == qs[k]) { qi[k] = j; break; }
+    }
+    // table mode: memoised weights (pb.wtab) + this agent's rule-cell list and cell-to-rule map
+    constexpr bool tabmode = COOP == 2;                  // the host launches this variant only with a table and sized indexes
+    unsigned short *rbc = tabmode ? st.rbc + (size_t)(ag >> 5) * friq_cap8(st.cap) * FRIQ_TILE : nullptr;      // the TILE's rule cells
+    unsigned short *cmap = tabmode ? st.cmap + (size_t)(ag >> 5) * st.idx_cells * FRIQ_TILE + (ag & 31) : nullptr;
+    uint32_t qw = FRIQ_NO_TARGET;                        // packed dictionary indices of the pending update's point vo[], if it has them
+    if (tabmode) {
+        int unk[S];
+#pragma unroll
+        for (int k = 0; k < S; k++) unk[k] = -1;
+        const uint32_t w0 = friq_obs_word<S>(pb, vo, unk);
+        int ah = -1;
+        for (int j = 0; j < pb.dict_len[S]; j++) if (pb.dict_ve[S][j] == vo[S]) { ah = j; break; }
+        if (w0 != FRIQ_NO_TARGET && ah >= 0) qw = w0 | ((uint32_t)ah << (FRIQ_IDX_BITS * S));
     }
 
     // All lanes of a warp iterate in lockstep (explicit reconvergence at the loop top): a lane that starts
@@ -134,12 +164,19 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         // exact hits first (BestAct.c:89-93): where distance 0 <=> equal dictionary indices, an integer sweep finds them, and only
         // the (lane, action) pairs without one need Shepard sums - cooperatively when few, else through the lock-step pass
         bool lockstep = true;
+        uint32_t ow = FRIQ_NO_TARGET;
         if constexpr (COOP || A == ACH) if (COOP || pb.hit_scan) {
-            const uint32_t ow = friq_obs_word<S>(pb, vc, ci);
+            ow = friq_obs_word<S>(pb, vc, ci);
             uint32_t tgt[A]; unsigned nm[A]; int pairs = 0;
 #pragma unroll
             for (int a = 0; a < A; a++) tgt[a] = (ow != FRIQ_NO_TARGET && pb.act_hit[a] >= 0) ? (ow | ((uint32_t)pb.act_hit[a] << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET;
-            friq_hit_scan<A>(rbw, act ? R : 0, tgt, hidx);
+            if (tabmode) {                               // exact hits in O(1): the first rule of the target's dictionary cell
+                const int oc = (ow != FRIQ_NO_TARGET) ? friq_cell<S>(pb, ow) : 0;
+#pragma unroll
+                for (int a = 0; a < A; a++)
+                    hidx[a] = (act && tgt[a] != FRIQ_NO_TARGET) ? (int)cmap[(size_t)(oc + pb.act_hit[a] * pb.wlin[S]) * FRIQ_TILE] - 1 : -1;
+            } else
+                friq_hit_scan<A>(rbw, act ? R : 0, tgt, hidx);
 #pragma unroll
             for (int a = 0; a < A; a++) { nm[a] = __ballot_sync(wmask, act && hidx[a] < 0); pairs += __popc(nm[a]); }
             if (COOP || pairs <= FRIQ_COOP_MAXPAIRS) {
@@ -147,7 +184,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 #pragma unroll
                 for (int a = 0; a < A; a++) actconc[a] = (hidx[a] >= 0) ? rbq[(size_t)hidx[a] * FRIQ_TILE] : 0.0;
                 vagq = 0.0; wsq = 0.0;
-                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE>(pb, rbw, rbq, sw, R, vc, vo, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq);
+                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq);
             }
         }
         if (!COOP && lockstep) {
@@ -160,6 +197,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         }
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
+        if (act) qw = (ow != FRIQ_NO_TARGET && pb.act_hit[a2] >= 0) ? (ow | ((uint32_t)pb.act_hit[a2] << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET;
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }
         if (act && !initial) {
             sum_rules += (unsigned long long)R;
@@ -178,6 +216,13 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 const int R0 = R;
                 friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma);
                 hitq = next_hit;
+                if (R > R0 && tabmode) {                 // a rule was appended: keep the indexes current
+                    const int cn = friq_cell<K>(pb, rbw[(size_t)R0 * FRIQ_TILE]);
+                    unsigned short *e = rbc + friq_rbc_index(R0, (int)(ag & 31));
+                    if ((R0 & 7) == 0) *reinterpret_cast<uint4 *>(e) = make_uint4((unsigned)cn, 0u, 0u, 0u);   // a new block: cell 0 in its unused tail
+                    else *e = (unsigned short)cn;
+                    if (!cmap[(size_t)cn * FRIQ_TILE]) cmap[(size_t)cn * FRIQ_TILE] = (unsigned short)(R0 + 1);
+                }
                 if (R > R0 && hitq == -1) {              // a rule was appended: is it at the next step's (s,a)?
                     const uint32_t wnew = rbw[(size_t)R0 * FRIQ_TILE];
                     bool same = pb.dict_ve[S][(wnew >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)] == pb.act_ve_eval[a2];
@@ -219,6 +264,20 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     st.prev_reward[ag] = prev_reward; st.prev_steps[ag] = prev_steps; st.prev_numru[ag] = prev_numru;
     st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
     st.total_steps[ag] = total_steps; st.sum_rules[ag] = sum_rules;
+#ifdef FRIQ_TIMELINE
+    {
+        int rmax = R, rmin = R;
+        for (int o = 16; o; o >>= 1) { rmax = max(rmax, __shfl_xor_sync(wmask, rmax, o)); rmin = min(rmin, __shfl_xor_sync(wmask, rmin, o)); }
+        if ((threadIdx.x & 31) == 0) {
+            const unsigned int i = atomicAdd(&friq_tl_n, 1u);
+            if (i < FRIQ_TL_MAX) {
+                friq_tl_buf[i][0] = tl_t0; friq_tl_buf[i][1] = friq_globaltimer();
+                friq_tl_buf[i][2] = ((unsigned long long)friq_smid() << 32) | (unsigned long long)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+                friq_tl_buf[i][3] = ((unsigned long long)rmax << 32) | (unsigned long long)rmin | ((unsigned long long)(st.n & 0xffff) << 48);
+            }
+        }
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -847,6 +906,28 @@ __global__ void k_init_agents(const friq_devprob *__restrict__ gprob, friq_devst
     st.agent_of_slot[ag] = (int)ag; st.hitq[ag] = -2;
 }
 
+// derived indexes of the table mode (friq_devstate.rbc / .cmap), rebuilt from the packed rule words before every fused launch
+__global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_devstate st)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n) return;
+    const int K = gprob->K, cells = st.idx_cells;
+    const size_t tile_off = (size_t)(ag >> 5) * st.cap * FRIQ_TILE + (ag & 31);
+    unsigned short *cmap = st.cmap + (size_t)(ag >> 5) * cells * FRIQ_TILE + (ag & 31);
+    unsigned short *rbc = st.rbc + (size_t)(ag >> 5) * friq_cap8(st.cap) * FRIQ_TILE;
+    for (int c = 0; c < cells; c++) cmap[(size_t)c * FRIQ_TILE] = 0;
+    const int R = st.R[ag];
+    for (int i = 0; i < R; i++) {
+        const uint32_t w = st.rbw[tile_off + (size_t)i * FRIQ_TILE];
+        int c = 0;
+        for (int k = 0; k < K; k++) c += (int)((w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)) * gprob->wlin[k];
+        if (c >= cells) c = 0;                       // cannot happen for indices below dict_len; never index out of bounds
+        rbc[friq_rbc_index(i, (int)(ag & 31))] = (unsigned short)c;
+        if (!cmap[(size_t)c * FRIQ_TILE]) cmap[(size_t)c * FRIQ_TILE] = (unsigned short)(i + 1);
+    }
+    for (int i = R; i < ((R + 7) & ~7); i++) rbc[friq_rbc_index(i, (int)(ag & 31))] = 0;   // unused tail of the last block
+}
+
 __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict__ words, const double *__restrict__ q, int R)
 {
     const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -921,6 +1002,24 @@ __global__ void k_unpermute(friq_devstate st, const T *src, T *dst)
 {
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < st.n) dst[st.agent_of_slot[p]] = src[p];
+}
+
+// memoised Shepard weights (friq_devprob.wtab): wtab[q * cells + r] = 1 / d(q, r)^p for every pair of dictionary cells, through the
+// same device functions as a computed chain (friq_dist2 left-to-right over the dimensions, sqrt, x87 power, reciprocal)
+template <int K, int P>
+__global__ void k_build_wtab(const friq_devprob *__restrict__ gprob, double *__restrict__ wtab, int cells)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)cells * cells) return;
+    int q = (int)(t / cells), r = (int)(t % cells);
+    double pt[K]; uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int n = gprob->dict_len[k];
+        pt[k] = gprob->dict_ve[k][q % n]; q /= n;
+        w |= (uint32_t)(r % n) << (FRIQ_IDX_BITS * k); r /= n;
+    }
+    wtab[t] = friq_shepard_weight<P>(friq_dist2<K>(*gprob, w, pt));
 }
 
 __global__ void k_trig(const double *x, double *s, double *c, long n)
@@ -1024,6 +1123,18 @@ int friqd_unpermute(friq_devstate st, const void *src, void *dst, int elem_bytes
     CK(cudaGetLastError());
     return 0;
 }
+#ifdef FRIQ_TIMELINE
+int friqd_timeline_fetch(unsigned long long *host, int max_entries, int reset)
+{
+    unsigned int n = 0; CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(&n, friq_tl_n, sizeof n));
+    if (n > FRIQ_TL_MAX) n = FRIQ_TL_MAX;
+    if ((int)n > max_entries) n = max_entries;
+    if (host && n) CK(cudaMemcpyFromSymbol(host, friq_tl_buf, (size_t)n * 32));
+    if (reset) { const unsigned int z = 0; CK(cudaMemcpyToSymbol(friq_tl_n, &z, sizeof z)); }
+    return (int)n;
+}
+#endif
 int friqd_stream_create(void **s) { cudaStream_t t; CK(cudaStreamCreate(&t)); *s = (void *)t; return 0; }
 int friqd_stream_destroy(void *s) { CK(cudaStreamDestroy((cudaStream_t)s)); return 0; }
 int friqd_event_create(void **e) { cudaEvent_t t; CK(cudaEventCreateWithFlags(&t, cudaEventDisableTiming)); *e = (void *)t; return 0; }
@@ -1050,10 +1161,15 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
 {   // variant 0: one thread per agent, lock-step pass (+ hit sweep / cooperative sums when few pairs lack a hit);
     // 1: three warps per tile (k_run_steps_w3, A = 3 problems); 2: one thread per agent, hit sweep + cooperative sums only
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    // table mode (memoised weights + per-agent indexes) only where the COOP kernels run and the indexes are sized for this table
+    const bool coop = variant == 2 && hp->hit_scan && hp->safe_range &&
+                      ((hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) || (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)));
+    const bool tab = coop && hp->wtab && st.rbc && st.idx_cells == hp->wcells;
+    if (tab) k_refresh_index<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st);
 #define FRIQ_LAUNCH_STEP(S_, P_, A_, ACH_, ENV_, UNR_)                                                                   \
     do {                                                                                                              \
-        if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
-        else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
+        if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
+        else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
     } while (0)
 #define FRIQ_LAUNCH_W3(S_, P_, ENV_)                                                                                   \
     do {                                                                                                              \
@@ -1064,10 +1180,14 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     const int w3 = variant == 1;
     if (w3 && hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_W3(2, 3, FRIQ_ENV_MOUNTAINCAR);
     else if (w3 && hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_W3(4, 5, FRIQ_ENV_ACROBOT);
-    else if (variant == 2 && hp->hit_scan && hp->safe_range && hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp))
-        k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    else if (variant == 2 && hp->hit_scan && hp->safe_range && hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp))
-        k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR)
+        k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (tab && hp->env == FRIQ_ENV_ACROBOT)
+        k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (coop && hp->env == FRIQ_ENV_MOUNTAINCAR)
+        k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (coop && hp->env == FRIQ_ENV_ACROBOT)
+        k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_STEP(2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, FRIQ_UNR_MC);
     else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_STEP(4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2);
     else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) FRIQ_LAUNCH_STEP(4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1);
@@ -1169,6 +1289,17 @@ int friqd_bestact_dists(const friq_devprob *hp, friq_devstate st, const double *
     return 0;
 }
 
+int friqd_build_wtab(const friq_devprob *hp, const friq_devprob *dprob, double *d_wtab)
+{
+    const long n = (long)hp->wcells * hp->wcells;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    if (hp->K == 3 && hp->p == 3) k_build_wtab<3, 3><<<g, 256>>>(dprob, d_wtab, hp->wcells);
+    else if (hp->K == 5 && hp->p == 5) k_build_wtab<5, 5><<<g, 256>>>(dprob, d_wtab, hp->wcells);
+    else return (int)cudaErrorInvalidValue;
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
 int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream)
 {
     k_trig<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_sin, d_cos, n);

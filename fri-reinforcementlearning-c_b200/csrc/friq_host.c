@@ -30,6 +30,7 @@ struct friq_problem {
     friq_devprob *dp;         /* device copy */
     double *u, *ve;           /* host tables [K][U] */
     double *d_u, *d_ve;
+    double *d_wtab;           /* memoised Shepard weights between dictionary cells (friq_devprob.wtab), or NULL */
     int device;               /* device the tables live on, -1 = not uploaded yet */
     double alpha, gamma, epsilon;
 };
@@ -262,6 +263,14 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
         hp->corner[r] = w;
     }
     refresh_hit_scan(P);
+    /* the episode start state as dictionary entries: its observation word is then always known (friq_obs_word) and the
+     * memoised weights cover the first step of an episode too; no rule ever holds these indices unless a loaded rule base does */
+    if (hp->hit_scan) {
+        int added = 0;
+        for (int k = 0; k < S; k++)
+            if (hp->def_hit[k] < 0 && hp->dict_len[k] < FRIQ_MAXDICT) { dict_find_or_add(P, k, hp->values_def[k]); added = 1; }
+        if (added) refresh_hit_scan(P);
+    }
     *out = P;
     return 0;
 }
@@ -298,6 +307,35 @@ int friq_problem_set_learning_params(friq_problem *P, double qdiff_pos, double q
     return 0;
 }
 
+/* (Re)build the memoised Shepard weights of the problem on its device and publish the problem block.  A learner's query
+ * points and rule antecedents both live on the finite dictionary grid, so the weight 1/d^p of a (query cell, rule cell)
+ * pair is a constant of the problem: the fused kernel looks it up instead of running the sqrt -> x87 power -> reciprocal
+ * chain per rule and pair.  The table is computed on the device by the same functions (friq_dist2, friq_shepard_weight).
+ * Only for problems where exact hits are index equality (hit_scan) and Q(s',a') is actconc[a'] (qp_reuse), i.e. where the
+ * fused kernel's policy 2 runs; FRIQ_NO_WTAB=1 disables it (experiments, parity tests of the computed path). */
+#define FRIQ_WTAB_MAX_BYTES (64ul << 20)
+static int problem_publish(friq_problem *P)
+{
+    friq_devprob *hp = &P->hp;
+    if (P->d_wtab) { DEV(friqd_device_sync()); DEV(friqd_free(P->d_wtab)); P->d_wtab = NULL; }
+    hp->wtab = NULL; hp->wcells = 0;
+    const char *off = getenv("FRIQ_NO_WTAB");
+    if ((hp->env == FRIQ_ENV_MOUNTAINCAR || hp->env == FRIQ_ENV_ACROBOT) && hp->hit_scan && hp->qp_reuse && !(off && atoi(off))) {
+        unsigned long cells = 1; int ok = 1;
+        for (int k = 0; k < hp->K; k++) { hp->wlin[k] = (int)cells; cells *= (unsigned long)hp->dict_len[k]; if (cells > 65535ul) { ok = 0; break; } }
+        for (int a = 0; a < hp->A; a++) if (hp->act_hit[a] < 0) ok = 0;
+        if (ok && cells * cells * 8ul <= FRIQ_WTAB_MAX_BYTES) {
+            DEV(friqd_h2d(P->dp, hp, sizeof(friq_devprob)));          /* the build kernel reads the dictionaries */
+            DEV(friqd_malloc((void **)&P->d_wtab, cells * cells * 8ul));
+            hp->wcells = (int)cells;
+            DEV(friqd_build_wtab(hp, P->dp, P->d_wtab));
+            hp->wtab = P->d_wtab;
+        }
+    }
+    DEV(friqd_h2d(P->dp, hp, sizeof(friq_devprob)));
+    return 0;
+}
+
 static int problem_upload(friq_problem *P, int device)
 {
     friq_devprob *hp = &P->hp;
@@ -309,6 +347,7 @@ static int problem_upload(friq_problem *P, int device)
         DEV(friqd_h2d(P->d_u, P->u, tb)); DEV(friqd_h2d(P->d_ve, P->ve, tb));
         hp->u = P->d_u; hp->ve = P->d_ve;
         P->device = device;
+        return problem_publish(P);
     }
     DEV(friqd_h2d(P->dp, hp, sizeof(friq_devprob)));
     return 0;
@@ -317,7 +356,7 @@ static int problem_upload(friq_problem *P, int device)
 void friq_problem_destroy(friq_problem *P)
 {
     if (!P) return;
-    if (P->device != -1) { friqd_set_device(P->device); friqd_free(P->d_u); friqd_free(P->d_ve); friqd_free(P->dp); }
+    if (P->device != -1) { friqd_set_device(P->device); friqd_free(P->d_u); friqd_free(P->d_ve); friqd_free(P->dp); if (P->d_wtab) friqd_free(P->d_wtab); }
     free(P->u); free(P->ve); free(P);
 }
 
@@ -347,7 +386,8 @@ static int alloc_state(friq_devstate *st, int clear)
     const size_t slots = (size_t)st->n_pad * st->cap, np = (size_t)st->n_pad;
     const size_t rows8 = 3 * FRIQ_MAXK + 9, rows4 = 12;
     void *slab;
-    DEV(friqd_malloc((void **)&st->rbw, slots * 4)); DEV(friqd_malloc((void **)&st->rbq, slots * 8));
+    DEV(friqd_malloc((void **)&st->rbw, slots * 4));
+    DEV(friqd_malloc((void **)&st->rbq, slots * 8 + 8 * FRIQ_TILE * 8));   /* slack: the table-mode loop reads whole blocks of 8 rules */
     DEV(friqd_malloc(&slab, np * (rows8 * 8 + rows4 * 4)));
     if (clear) { DEV(friqd_memset(st->rbw, 0, slots * 4)); DEV(friqd_memset(st->rbq, 0, slots * 8)); }
     DEV(friqd_memset(slab, 0, np * (rows8 * 8 + rows4 * 4)));
@@ -365,6 +405,8 @@ static int alloc_state(friq_devstate *st, int clear)
 static void free_state(friq_devstate *st)
 {
     friqd_free(st->rbw); friqd_free(st->rbq); if (st->prevq) friqd_free(st->prevq);
+    if (st->rbc) friqd_free(st->rbc);
+    if (st->cmap) friqd_free(st->cmap);
     friqd_free(st->s);        /* slab base */
 }
 
@@ -373,7 +415,7 @@ static int retile(friq_batch *b, int by_rules, void *stream)
 {
     if (!by_rules && !b->permuted) return 0;
     if (!b->have_st2) {
-        b->st2 = b->st; b->st2.prevq = NULL; b->st2.s0 = NULL;
+        b->st2 = b->st; b->st2.prevq = NULL; b->st2.s0 = NULL; b->st2.rbc = NULL; b->st2.cmap = NULL;
         int rc = alloc_state(&b->st2, 0); if (rc) return rc;
         if (b->st.s0) DEV(friqd_malloc((void **)&b->st2.s0, 8 * FRIQ_MAXK * (size_t)b->st.n_pad));
         DEV(friqd_malloc((void **)&b->d_work, sizeof(int) * (FRIQ_MAXGROUPS * ((size_t)b->st.cap + 2 + FRIQ_TILE) + (size_t)b->st.n_pad)));
@@ -393,12 +435,32 @@ static friq_devstate state_view(const friq_devstate *st, long lo, long n)
     const size_t ro = (size_t)(lo / FRIQ_TILE) * st->cap * FRIQ_TILE;
     v.n = n;
     v.rbw += ro; v.rbq += ro; v.sw += ro; if (v.prevq) v.prevq += ro;
+    if (v.rbc) { v.rbc += (size_t)(lo / FRIQ_TILE) * (size_t)((st->cap + 7) & ~7) * FRIQ_TILE; v.cmap += (size_t)(lo / FRIQ_TILE) * st->idx_cells * FRIQ_TILE; }
     v.s += lo; v.qs += lo; v.vo += lo;
     v.aidx += lo; v.flags += lo; v.R += lo; v.step_in_ep += lo; v.last_steps += lo; v.last_rules += lo; v.prev_steps += lo; v.prev_numru += lo;
     v.ep_num += lo; v.ep_return += lo; v.last_return += lo; v.prev_reward += lo;
     v.total_steps += lo; v.sum_rules += lo; v.seed += lo; v.alpha += lo; v.gamma += lo; v.epsilon += lo;
     v.agent_of_slot += lo; v.hitq += lo; if (v.s0) v.s0 += lo;
     return v;
+}
+/* the per-agent rule-cell / cell-to-rule indexes of the fused kernel's table mode, sized for the problem's current table */
+static int ensure_index_one(friq_devstate *st, int cells)
+{
+    if (st->rbc && st->idx_cells == cells) return 0;
+    if (st->rbc) { DEV(friqd_device_sync()); DEV(friqd_free(st->rbc)); DEV(friqd_free(st->cmap)); st->rbc = NULL; st->cmap = NULL; }
+    st->idx_cells = cells;
+    if (cells > 0) {
+        DEV(friqd_malloc((void **)&st->rbc, (size_t)st->n_pad * (size_t)((st->cap + 7) & ~7) * 2));
+        DEV(friqd_malloc((void **)&st->cmap, (size_t)st->n_pad * cells * 2));
+    }
+    return 0;
+}
+static int ensure_index(friq_batch *b)
+{
+    const int cells = b->P->hp.wtab ? b->P->hp.wcells : 0;
+    int rc = ensure_index_one(&b->st, cells); if (rc) return rc;
+    if (b->have_st2) { rc = ensure_index_one(&b->st2, cells); if (rc) return rc; }
+    return 0;
 }
 #define IDENTITY(b) do { if ((b)->permuted) { DEV(friqd_device_sync()); int rc_ = retile((b), 0, NULL); if (rc_) return rc_; DEV(friqd_device_sync()); } } while (0)
 
@@ -497,7 +559,7 @@ int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant
         }
         w[i] = word;
     }
-    if (grew) { refresh_hit_scan(P); DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob))); }
+    if (grew) { refresh_hit_scan(P); int rcp_ = problem_publish(P); if (rcp_) return rcp_; }
     if (agent >= 0) {
         const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE);
         if (R) {
@@ -629,6 +691,7 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         DEV(friqd_run_shared(&b->P->hp, b->P->dp, b->st, b->d_srb, b->shared_R, n_steps, mode, stream));
         return 0;
     }
+    { int rci = ensure_index(b); if (rci) return rci; }
     if ((mode & FRIQ_RUN_TRACK_CONVERGENCE) && !b->st.prevq) {
         const size_t slots = (size_t)b->st.n_pad * b->st.cap;
         DEV(friqd_malloc((void **)&b->st.prevq, slots * 8)); DEV(friqd_memset(b->st.prevq, 0, slots * 8));
@@ -640,7 +703,7 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
          * bases) overlaps the next group's launch instead of idling the GPU. */
         const int G = b->groups;
         if (b->permuted && b->permuted != 1 + G) { int rc = retile(b, 0, stream); if (rc) return rc; }   /* group layout changed */
-        if (!b->have_st2) { int rc = retile(b, 1, stream); if (rc) return rc; rc = retile(b, 0, stream); if (rc) return rc; }  /* allocate buffers */
+        if (!b->have_st2) { int rc = retile(b, 1, stream); if (rc) return rc; rc = retile(b, 0, stream); if (rc) return rc; rc = ensure_index(b); if (rc) return rc; }  /* allocate buffers */
         if (b->st.prevq && !b->st2.prevq) DEV(friqd_malloc((void **)&b->st2.prevq, (size_t)b->st.n_pad * b->st.cap * 8));
         if (!b->gstart) DEV(friqd_event_create(&b->gstart));
         for (int g = 0; g < G; g++) if (!b->gstream[g]) {
@@ -909,7 +972,7 @@ int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double 
         grew |= (P->hp.dict_len[k] != before);
         word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
     }
-    if (grew) { refresh_hit_scan(P); DEV(friqd_h2d(P->dp, &P->hp, sizeof(friq_devprob))); }
+    if (grew) { refresh_hit_scan(P); int rcp_ = problem_publish(P); if (rcp_) return rcp_; }
     const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE) + (size_t)R * FRIQ_TILE;
     DEV(friqd_h2d(b->st.rbw + off, &word, 4)); DEV(friqd_h2d(b->st.rbq + off, &q, 8));
     R++;
