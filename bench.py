@@ -264,8 +264,9 @@ def main():
         "five_evals_per_sec": value * EVALS_PER_STEP,
         "e2e": {"value": nsteps_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 16 * n,
                 "ms_per_step": ms_e2e / args.steps},
-        # per group and launch: 4 re-tiling kernels (histogram, scan, assign, move) + k_run_steps; per step: 3 result un-permute kernels
-        "gpu_launches": args.steps * (5 * launches_per_step * groups + 3),
+        # per group and launch: 4 re-tiling kernels (histogram, scan, assign, move) + k_refresh_index (table mode) + k_run_steps;
+        # per step: 3 result un-permute kernels
+        "gpu_launches": args.steps * ((5 if os.environ.get("FRIQ_NO_WTAB", "0") not in ("", "0") else 6) * launches_per_step * groups + 3),
         "clocks": clocks,
         "roofline": {"bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",
                      "achieved": ach_tflops if frac_fp64 >= frac_hbm else ach_gbs,
@@ -274,7 +275,9 @@ def main():
                      "frac": max(frac_fp64, frac_hbm), "traffic": traffic,
                      "kernel": "k_run_steps<2,3,3,3,mountaincar>",
                      "note": "algorithmic FP64 ops of the reference path (SURVEY 8d: 82*R per env step, sqrt and / counted as 1) over the "
-                             "measured non-FMA FP64 issue rate of this GPU (friq_device_fp64_peak, DADD/DMUL lane-ops/s); "
+                             "measured non-FMA FP64 issue rate of this GPU (friq_device_fp64_peak, DADD/DMUL lane-ops/s); the kernel "
+                             "EXECUTES far fewer: exact hits short-cut the sums (as in the reference) and the Shepard weights are "
+                             "looked up in a memoised table, so this is nominal work per second, not pipe utilisation (ncu: profiles/); "
                              "hbm view: %.1f GB/s algorithmic of %.0f GB/s measured = %.3f; achieved is over the whole timed step "
                              "(re-tiling + result gather included, k_run_steps is > 97 %% of it: profiles/)" % (ach_gbs, hbm_peak, frac_hbm)},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": frac_hbm, "traffic": traffic},

@@ -473,27 +473,43 @@ __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
 // ---- table mode: the per-agent list of rule cells (friq_devstate.rbc) is stored in blocks of FRIQ_CELL_VEC rules per lane,
 // [tile][slot / 8][lane][8] u16, so that a lane fetches the cells of 8 consecutive rules of a column with ONE 16-byte load;
 // the unused tail of the last block holds cell 0 (any valid column: those weights are loaded but never added).
-#define FRIQ_CELL_VEC 8
+#ifndef FRIQ_CELL_VEC
+#define FRIQ_CELL_VEC 8         /* 8 (one 16-byte load per block) or 4 (8-byte loads, half the registers in flight) */
+#endif
 __host__ __device__ __forceinline__ size_t friq_cap8(int cap) { return (size_t)((cap + FRIQ_CELL_VEC - 1) & ~(FRIQ_CELL_VEC - 1)); }
-__device__ __forceinline__ size_t friq_rbc_index(int i, int lane) { return ((size_t)(i >> 3) * FRIQ_TILE + lane) * FRIQ_CELL_VEC + (i & 7); }
+__device__ __forceinline__ size_t friq_rbc_index(int i, int lane) { return ((size_t)(i / FRIQ_CELL_VEC) * FRIQ_TILE + lane) * FRIQ_CELL_VEC + (i % FRIQ_CELL_VEC); }
+#if FRIQ_CELL_VEC == 8
+typedef uint4 friq_cellvec;
+__device__ __forceinline__ friq_cellvec friq_cellvec_zero() { return make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void friq_cellvec_unpack(const friq_cellvec c, unsigned (&cc)[8])
+{ cc[0] = c.x & 0xffffu; cc[1] = c.x >> 16; cc[2] = c.y & 0xffffu; cc[3] = c.y >> 16; cc[4] = c.z & 0xffffu; cc[5] = c.z >> 16; cc[6] = c.w & 0xffffu; cc[7] = c.w >> 16; }
+#else
+typedef uint2 friq_cellvec;
+__device__ __forceinline__ friq_cellvec friq_cellvec_zero() { return make_uint2(0u, 0u); }
+__device__ __forceinline__ void friq_cellvec_unpack(const friq_cellvec c, unsigned (&cc)[4])
+{ cc[0] = c.x & 0xffffu; cc[1] = c.x >> 16; cc[2] = c.y & 0xffffu; cc[3] = c.y >> 16; }
+#endif
 
-// weights (looked up in the pair's table row through the block's cells) and consequents of one block of 8 rules
-__device__ __forceinline__ void friq_tab_load(const double *__restrict__ rowd, const uint4 c, const double *pq, double (&t)[8], double (&q)[8])
+// weights (looked up in the pair's table row through the block's cells) and consequents of one block of rules
+__device__ __forceinline__ void friq_tab_load(const double *__restrict__ rowd, const friq_cellvec c, const double *pq,
+                                              double (&t)[FRIQ_CELL_VEC], double (&q)[FRIQ_CELL_VEC])
 {
-    const unsigned cc[8] = { c.x & 0xffffu, c.x >> 16, c.y & 0xffffu, c.y >> 16, c.z & 0xffffu, c.z >> 16, c.w & 0xffffu, c.w >> 16 };
+    unsigned cc[FRIQ_CELL_VEC];
+    friq_cellvec_unpack(c, cc);
 #pragma unroll
-    for (int u = 0; u < 8; u++) { t[u] = __ldg(rowd + cc[u]); q[u] = pq[(size_t)u * FRIQ_TILE]; }
+    for (int u = 0; u < FRIQ_CELL_VEC; u++) { t[u] = __ldg(rowd + cc[u]); q[u] = pq[(size_t)u * FRIQ_TILE]; }
 }
-// the block's terms added in rule order (BestAct.c:216-217 / FIVEVagConcl.c:234-235); cnt < 8 only for a column's last block
+// the block's terms added in rule order (BestAct.c:216-217 / FIVEVagConcl.c:234-235); cnt < block size only for a column's last block
 template <bool FULL>
-__device__ __forceinline__ void friq_tab_acc(const double (&t)[8], const double (&q)[8], int cnt, bool isq, double *psw, double &vag, double &ws)
+__device__ __forceinline__ void friq_tab_acc(const double (&t)[FRIQ_CELL_VEC], const double (&q)[FRIQ_CELL_VEC], int cnt, bool isq, double *psw,
+                                             double &vag, double &ws)
 {
     if (isq) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) if (FULL || u < cnt) psw[(size_t)u * FRIQ_TILE] = t[u];
+        for (int u = 0; u < FRIQ_CELL_VEC; u++) if (FULL || u < cnt) psw[(size_t)u * FRIQ_TILE] = t[u];
     }
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+    for (int u = 0; u < FRIQ_CELL_VEC; u++)
         if (FULL || u < cnt) { vag = __dadd_rn(vag, __dmul_rn(t[u], q[u])); ws = __dadd_rn(ws, t[u]); }
 }
 // Shepard sums of one pair from the memoised weights: rules 0 .. Rt-1 of column j of the tile; block b+1's loads and block
@@ -501,28 +517,28 @@ __device__ __forceinline__ void friq_tab_acc(const double (&t)[8], const double 
 __device__ __forceinline__ void friq_tab_sums(const double *__restrict__ rowd, const unsigned short *rbc_tile, const double *tq, double *tsw,
                                               int j, int Rt, bool isq, double &vag, double &ws)
 {
-    const uint4 *pc = reinterpret_cast<const uint4 *>(rbc_tile) + j;        // block b of the column: pc[b * 32]
+    constexpr int B = FRIQ_CELL_VEC;
+    const friq_cellvec *pc = reinterpret_cast<const friq_cellvec *>(rbc_tile) + j;        // block b of the column: pc[b * 32]
     const double *pq = tq + j; double *psw = tsw + j;
-    const int nb = (Rt + 7) >> 3;
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    double tA[8], qA[8], tB[8], qB[8];
-    uint4 cn = zero;
+    const int nb = (Rt + B - 1) / B;
+    double tA[B], qA[B], tB[B], qB[B];
+    friq_cellvec cn = friq_cellvec_zero();
     if (nb > 0) friq_tab_load(rowd, pc[0], pq, tA, qA);
     if (nb > 1) cn = pc[FRIQ_TILE];
 #pragma unroll 1
     for (int b = 0; b < nb; b += 2) {
-        uint4 cnn = zero;
-        if (b + 1 < nb) friq_tab_load(rowd, cn, pq + 8 * FRIQ_TILE, tB, qB);
+        friq_cellvec cnn = friq_cellvec_zero();
+        if (b + 1 < nb) friq_tab_load(rowd, cn, pq + B * FRIQ_TILE, tB, qB);
         if (b + 2 < nb) cnn = pc[(size_t)(b + 2) * FRIQ_TILE];
-        { const int cnt = Rt - 8 * b; if (cnt >= 8) friq_tab_acc<true>(tA, qA, 8, isq, psw, vag, ws); else friq_tab_acc<false>(tA, qA, cnt, isq, psw, vag, ws); }
+        { const int cnt = Rt - B * b; if (cnt >= B) friq_tab_acc<true>(tA, qA, B, isq, psw, vag, ws); else friq_tab_acc<false>(tA, qA, cnt, isq, psw, vag, ws); }
         if (b + 1 < nb) {
-            if (b + 2 < nb) friq_tab_load(rowd, cnn, pq + 16 * FRIQ_TILE, tA, qA);
-            cn = zero;
+            if (b + 2 < nb) friq_tab_load(rowd, cnn, pq + 2 * B * FRIQ_TILE, tA, qA);
+            cn = friq_cellvec_zero();
             if (b + 3 < nb) cn = pc[(size_t)(b + 3) * FRIQ_TILE];
-            const int cnt = Rt - 8 * (b + 1);
-            if (cnt >= 8) friq_tab_acc<true>(tB, qB, 8, isq, psw + 8 * FRIQ_TILE, vag, ws); else friq_tab_acc<false>(tB, qB, cnt, isq, psw + 8 * FRIQ_TILE, vag, ws);
+            const int cnt = Rt - B * (b + 1);
+            if (cnt >= B) friq_tab_acc<true>(tB, qB, B, isq, psw + B * FRIQ_TILE, vag, ws); else friq_tab_acc<false>(tB, qB, cnt, isq, psw + B * FRIQ_TILE, vag, ws);
         }
-        pq += 16 * FRIQ_TILE; psw += 16 * FRIQ_TILE;
+        pq += 2 * B * FRIQ_TILE; psw += 2 * B * FRIQ_TILE;
     }
 }
 // the computed sums of one pair, one rule at a time through the library-exact chain: the table-mode kernel's rare fall-back

@@ -136,6 +136,7 @@ int friqd_update_sarsa(const friq_devprob *hprob, const friq_devprob *dprob, fri
 int friqd_classic_step(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_in, double *d_out, void *stream);
 int friqd_rule_distance(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_dists, int *d_hit, void *stream);
 int friqd_bestact_dists(const friq_devprob *hprob, friq_devstate st, const double *d_dists, double *d_conc, void *stream);
+unsigned long friqd_rbc_tile_slots(int cap);      /* u16 entries of friq_devstate.rbc per tile of 32 agents */
 int friqd_build_wtab(const friq_devprob *hprob, const friq_devprob *dprob, double *d_wtab);
 int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream);
 int friqd_pow_x87(const double *d_x, double *d_out, long n, int p, int force_exact, void *stream);

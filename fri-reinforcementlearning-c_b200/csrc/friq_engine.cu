@@ -219,7 +219,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 if (R > R0 && tabmode) {                 // a rule was appended: keep the indexes current
                     const int cn = friq_cell<K>(pb, rbw[(size_t)R0 * FRIQ_TILE]);
                     unsigned short *e = rbc + friq_rbc_index(R0, (int)(ag & 31));
-                    if ((R0 & 7) == 0) *reinterpret_cast<uint4 *>(e) = make_uint4((unsigned)cn, 0u, 0u, 0u);   // a new block: cell 0 in its unused tail
+                    if ((R0 % FRIQ_CELL_VEC) == 0) { friq_cellvec v = friq_cellvec_zero(); v.x = (unsigned)cn; *reinterpret_cast<friq_cellvec *>(e) = v; }   // a new block: cell 0 in its unused tail
                     else *e = (unsigned short)cn;
                     if (!cmap[(size_t)cn * FRIQ_TILE]) cmap[(size_t)cn * FRIQ_TILE] = (unsigned short)(R0 + 1);
                 }
@@ -925,7 +925,7 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
         rbc[friq_rbc_index(i, (int)(ag & 31))] = (unsigned short)c;
         if (!cmap[(size_t)c * FRIQ_TILE]) cmap[(size_t)c * FRIQ_TILE] = (unsigned short)(i + 1);
     }
-    for (int i = R; i < ((R + 7) & ~7); i++) rbc[friq_rbc_index(i, (int)(ag & 31))] = 0;   // unused tail of the last block
+    for (int i = R; i < (int)friq_cap8(R); i++) rbc[friq_rbc_index(i, (int)(ag & 31))] = 0;   // unused tail of the last block
 }
 
 __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict__ words, const double *__restrict__ q, int R)
@@ -1289,6 +1289,7 @@ int friqd_bestact_dists(const friq_devprob *hp, friq_devstate st, const double *
     return 0;
 }
 
+unsigned long friqd_rbc_tile_slots(int cap) { return (unsigned long)(friq_cap8(cap) * FRIQ_TILE); }
 int friqd_build_wtab(const friq_devprob *hp, const friq_devprob *dprob, double *d_wtab)
 {
     const long n = (long)hp->wcells * hp->wcells;

@@ -435,7 +435,7 @@ static friq_devstate state_view(const friq_devstate *st, long lo, long n)
     const size_t ro = (size_t)(lo / FRIQ_TILE) * st->cap * FRIQ_TILE;
     v.n = n;
     v.rbw += ro; v.rbq += ro; v.sw += ro; if (v.prevq) v.prevq += ro;
-    if (v.rbc) { v.rbc += (size_t)(lo / FRIQ_TILE) * (size_t)((st->cap + 7) & ~7) * FRIQ_TILE; v.cmap += (size_t)(lo / FRIQ_TILE) * st->idx_cells * FRIQ_TILE; }
+    if (v.rbc) { v.rbc += (size_t)(lo / FRIQ_TILE) * (size_t)friqd_rbc_tile_slots(st->cap); v.cmap += (size_t)(lo / FRIQ_TILE) * st->idx_cells * FRIQ_TILE; }
     v.s += lo; v.qs += lo; v.vo += lo;
     v.aidx += lo; v.flags += lo; v.R += lo; v.step_in_ep += lo; v.last_steps += lo; v.last_rules += lo; v.prev_steps += lo; v.prev_numru += lo;
     v.ep_num += lo; v.ep_return += lo; v.last_return += lo; v.prev_reward += lo;
@@ -450,7 +450,7 @@ static int ensure_index_one(friq_devstate *st, int cells)
     if (st->rbc) { DEV(friqd_device_sync()); DEV(friqd_free(st->rbc)); DEV(friqd_free(st->cmap)); st->rbc = NULL; st->cmap = NULL; }
     st->idx_cells = cells;
     if (cells > 0) {
-        DEV(friqd_malloc((void **)&st->rbc, (size_t)st->n_pad * (size_t)((st->cap + 7) & ~7) * 2));
+        DEV(friqd_malloc((void **)&st->rbc, (size_t)(st->n_pad / FRIQ_TILE) * (size_t)friqd_rbc_tile_slots(st->cap) * 2));
         DEV(friqd_malloc((void **)&st->cmap, (size_t)st->n_pad * cells * 2));
     }
     return 0;

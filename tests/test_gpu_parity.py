@@ -241,6 +241,66 @@ def test_hit_sweep_is_disabled_when_dictionary_ve_values_collide(fq):
     b.close(); P.close()
 
 
+def test_table_mode_survives_dictionary_growth_and_odd_capacity(fq):
+    """Table mode of the fused kernel (memoised Shepard weights between dictionary cells, per-agent rule-cell lists and
+    cell-to-rule maps).  A loaded rule base with an antecedent value OFF the grid whose universe point no grid value
+    shares makes the dictionary - and with it the weight table and the per-agent indexes - grow after the batch
+    exists; the capacity is no multiple of the 8-rule blocks the cell lists are read in.  Results equal the oracle."""
+    name = "mountaincar"
+    P = fq.Problem(name, no_random=0)
+    g = _golden.load(name)
+    rant, rconc = g["final"][1].copy(), g["final"][2].copy()
+    t = P.tables(); u = t["u"][0]
+    used = {int(np.argmin(np.abs(u - v))) for v in np.unique(rant[:, 0])}
+    used |= {int(np.argmin(np.abs(u - (-0.5))))}
+    free = [i for i in range(3, len(u) - 3) if i not in used]
+    rant[7, 0] = u[free[len(free) // 2]]                      # a new dictionary entry with its own VE value
+    n, cap = 45, 187
+    b = fq.Batch(P, n, cap, seed0=991, first_agent=5)
+    b.run(40, fq.RUN_LEARN | fq.RUN_RETILE)                  # indexes sized for the original table ...
+    b.reset()
+    b.set_rulebase(rant, rconc)                              # ... which now grows
+    b.set_hyper(np.full(n, 0.4), np.ones(n), np.full(n, 0.1))
+    for chunk in (1, 130, 369):
+        b.run(chunk, fq.RUN_LEARN | fq.RUN_RETILE)
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
+    for i in (0, 9, 31, 44):
+        a = _oracle.Agent(OP, cap, seed=991 + 5 + i)
+        a.set_rb(rant, rconc); a.set_hyper(0.4, 1.0, 0.1)
+        a.run_steps(500)
+        R, brant, brconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(brant, orant) and np.array_equal(brconc, orconc), i
+    b.close(); P.close()
+
+
+@pytest.mark.parametrize("name", ["mountaincar", "acrobot"])
+def test_table_mode_equals_computed_chains(fq, name, monkeypatch):
+    """The looked-up weights ARE the computed ones: a larger batch than the oracle comparisons afford, run once in table
+    mode (default) and once with the table disabled (FRIQ_NO_WTAB=1: integer hit sweep + computed sqrt / x87 power /
+    reciprocal chains); every rule base, return and step count must be identical."""
+    n, steps = 4096 + 17, 1200 if name == "mountaincar" else 500
+    rng = np.random.default_rng(8)
+    alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.01, 0.05, 0.2], n)
+    res = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("FRIQ_NO_WTAB", off)
+        P = fq.Problem(name, no_random=0)
+        b = fq.Batch(P, n, CAP[name], seed0=4242, first_agent=0)
+        b.set_hyper(alpha, gamma, eps)
+        for chunk in (steps // 3, steps - steps // 3):
+            b.run(chunk, fq.RUN_LEARN | fq.RUN_RETILE)
+        o = b.gather()
+        rbs = [b.get_rulebase(i) for i in range(0, n, 97)]
+        res.append((o, rbs))
+        b.close(); P.close()
+    (o0, r0), (o1, r1) = res
+    for k in ("last_return", "last_steps", "rules", "episodes", "flags", "total_steps", "sum_rules"):
+        assert np.array_equal(o0[k], o1[k]), k
+    for (Ra, ra, qa), (Rb, rb, qb) in zip(r0, r1):
+        assert Ra == Rb and np.array_equal(ra, rb) and np.array_equal(qa, qb)
+
+
 def test_retiled_results_are_reported_in_agent_order(fq):
     """FRIQ_RUN_RETILE moves agents between warps (sorted by rule count); device-side gathers and the
     host-buffer end-to-end call must still report per-agent results in agent order."""
