@@ -906,26 +906,43 @@ __global__ void k_init_agents(const friq_devprob *__restrict__ gprob, friq_devst
     st.agent_of_slot[ag] = (int)ag; st.hitq[ag] = -2;
 }
 
-// derived indexes of the table mode (friq_devstate.rbc / .cmap), rebuilt from the packed rule words before every fused launch
+// derived indexes of the table mode (friq_devstate.rbc / .cmap), rebuilt from the packed rule words before every fused launch.
+// The cell-to-rule map is cleared by a memset beforehand; rules are visited in DESCENDING order and stored unconditionally, so the
+// entry that survives in a cell is its FIRST rule (a thread's stores to one address are ordered) and no load sits between stores.
 __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_devstate st)
 {
     const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ag >= st.n) return;
-    const int K = gprob->K, cells = st.idx_cells;
-    const size_t tile_off = (size_t)(ag >> 5) * st.cap * FRIQ_TILE + (ag & 31);
-    unsigned short *cmap = st.cmap + (size_t)(ag >> 5) * cells * FRIQ_TILE + (ag & 31);
+    const int K = gprob->K, cells = st.idx_cells, lane = (int)(ag & 31);
+    int wl[FRIQ_MAXK];
+    for (int k = 0; k < FRIQ_MAXK; k++) wl[k] = k < K ? gprob->wlin[k] : 0;
+    const uint32_t *rbw = st.rbw + (size_t)(ag >> 5) * st.cap * FRIQ_TILE + lane;
+    unsigned short *cmap = st.cmap + (size_t)(ag >> 5) * cells * FRIQ_TILE + lane;
     unsigned short *rbc = st.rbc + (size_t)(ag >> 5) * friq_cap8(st.cap) * FRIQ_TILE;
-    for (int c = 0; c < cells; c++) cmap[(size_t)c * FRIQ_TILE] = 0;
-    const int R = st.R[ag];
-    for (int i = 0; i < R; i++) {
-        const uint32_t w = st.rbw[tile_off + (size_t)i * FRIQ_TILE];
-        int c = 0;
-        for (int k = 0; k < K; k++) c += (int)((w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)) * gprob->wlin[k];
-        if (c >= cells) c = 0;                       // cannot happen for indices below dict_len; never index out of bounds
-        rbc[friq_rbc_index(i, (int)(ag & 31))] = (unsigned short)c;
-        if (!cmap[(size_t)c * FRIQ_TILE]) cmap[(size_t)c * FRIQ_TILE] = (unsigned short)(i + 1);
+    const int R = st.R[ag], Rb = (int)friq_cap8(R);
+    for (int i0 = Rb - FRIQ_CELL_VEC; i0 >= 0; i0 -= FRIQ_CELL_VEC) {
+        uint32_t w[FRIQ_CELL_VEC];
+#pragma unroll
+        for (int u = 0; u < FRIQ_CELL_VEC; u++) w[u] = (i0 + u < R) ? rbw[(size_t)(i0 + u) * FRIQ_TILE] : 0u;
+        unsigned c[FRIQ_CELL_VEC];
+#pragma unroll
+        for (int u = 0; u < FRIQ_CELL_VEC; u++) {
+            int cc = 0;
+#pragma unroll
+            for (int k = 0; k < FRIQ_MAXK; k++) cc += (int)((w[u] >> ((FRIQ_IDX_BITS * k) & 31)) & (FRIQ_MAXDICT - 1)) * wl[k];
+            c[u] = (i0 + u < R && cc < cells) ? (unsigned)cc : 0u;      // unused tail of the last block: cell 0; never out of bounds
+        }
+        friq_cellvec v;
+#if FRIQ_CELL_VEC == 8
+        v = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
+#else
+        v = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
+#endif
+        *reinterpret_cast<friq_cellvec *>(rbc + friq_rbc_index(i0, lane)) = v;
+#pragma unroll
+        for (int u = FRIQ_CELL_VEC - 1; u >= 0; u--)
+            if (i0 + u < R) cmap[(size_t)c[u] * FRIQ_TILE] = (unsigned short)(i0 + u + 1);
     }
-    for (int i = R; i < (int)friq_cap8(R); i++) rbc[friq_rbc_index(i, (int)(ag & 31))] = 0;   // unused tail of the last block
 }
 
 __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict__ words, const double *__restrict__ q, int R)
@@ -945,10 +962,14 @@ __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict_
 // work[0..cap] = histogram / running offsets, work[cap+1 ..] = new slot of every old slot.
 // by_rules == 0 restores the identity placement.
 // ---------------------------------------------------------------------------------------
+// one atomic per distinct rule count of a warp (after the first sort the lanes of a warp hold nearly equal counts)
 __global__ void k_retile_hist(friq_devstate st, int *work)
 {
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < st.n) atomicAdd(&work[st.R[p]], 1);
+    if (p >= st.n) return;
+    const int r = st.R[p];
+    const unsigned peers = __match_any_sync(__activemask(), r);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&work[r], __popc(peers));
 }
 // exclusive prefix sums of the histogram in DESCENDING rule-count order (one block): work[r] = #agents with more than r rules
 __global__ void k_retile_scan(int *work, int cap)
@@ -969,33 +990,45 @@ __global__ void k_retile_assign(friq_devstate st, int *work, int by_rules)
 {
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= st.n) return;
-    work[st.cap + 1 + p] = by_rules ? atomicAdd(&work[st.R[p]], 1) : st.agent_of_slot[p];
+    if (!by_rules) { work[st.cap + 1 + p] = st.agent_of_slot[p]; return; }
+    const int r = st.R[p], lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(__activemask(), r);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&work[r], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    work[st.cap + 1 + p] = base + __popc(peers & ((1u << lane) - 1u));
 }
+// FRIQ_MOVE_SLICES threads per agent: slice 0 moves the scalars, every slice its share of the rules (blockDim.x = 32 agents, blockDim.y = slices)
+#define FRIQ_MOVE_SLICES 8
 __global__ void k_retile_move(friq_devstate a, friq_devstate b, const int *work)
 {
-    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long p = (long)blockIdx.x * FRIQ_TILE + threadIdx.x;
     if (p >= a.n) return;
     const long q = work[a.cap + 1 + p];
-    for (int k = 0; k < FRIQ_MAXK; k++) {
-        b.s[(size_t)k * b.n_pad + q] = a.s[(size_t)k * a.n_pad + p];
-        b.qs[(size_t)k * b.n_pad + q] = a.qs[(size_t)k * a.n_pad + p];
-        b.vo[(size_t)k * b.n_pad + q] = a.vo[(size_t)k * a.n_pad + p];
+    const int sl = threadIdx.y;
+    if (sl == 0) {
+        for (int k = 0; k < FRIQ_MAXK; k++) {
+            b.s[(size_t)k * b.n_pad + q] = a.s[(size_t)k * a.n_pad + p];
+            b.qs[(size_t)k * b.n_pad + q] = a.qs[(size_t)k * a.n_pad + p];
+            b.vo[(size_t)k * b.n_pad + q] = a.vo[(size_t)k * a.n_pad + p];
+        }
+        b.aidx[q] = a.aidx[p]; b.flags[q] = a.flags[p]; b.R[q] = a.R[p]; b.step_in_ep[q] = a.step_in_ep[p];
+        b.last_steps[q] = a.last_steps[p]; b.last_rules[q] = a.last_rules[p]; b.prev_steps[q] = a.prev_steps[p]; b.prev_numru[q] = a.prev_numru[p];
+        b.ep_num[q] = a.ep_num[p]; b.ep_return[q] = a.ep_return[p]; b.last_return[q] = a.last_return[p]; b.prev_reward[q] = a.prev_reward[p];
+        b.total_steps[q] = a.total_steps[p]; b.sum_rules[q] = a.sum_rules[p]; b.seed[q] = a.seed[p];
+        b.alpha[q] = a.alpha[p]; b.gamma[q] = a.gamma[p]; b.epsilon[q] = a.epsilon[p];
+        b.agent_of_slot[q] = a.agent_of_slot[p]; b.hitq[q] = a.hitq[p];
+        if (a.s0 && b.s0) for (int k = 0; k < FRIQ_MAXK; k++) b.s0[(size_t)k * b.n_pad + q] = a.s0[(size_t)k * a.n_pad + p];
     }
-    b.aidx[q] = a.aidx[p]; b.flags[q] = a.flags[p]; b.R[q] = a.R[p]; b.step_in_ep[q] = a.step_in_ep[p];
-    b.last_steps[q] = a.last_steps[p]; b.last_rules[q] = a.last_rules[p]; b.prev_steps[q] = a.prev_steps[p]; b.prev_numru[q] = a.prev_numru[p];
-    b.ep_num[q] = a.ep_num[p]; b.ep_return[q] = a.ep_return[p]; b.last_return[q] = a.last_return[p]; b.prev_reward[q] = a.prev_reward[p];
-    b.total_steps[q] = a.total_steps[p]; b.sum_rules[q] = a.sum_rules[p]; b.seed[q] = a.seed[p];
-    b.alpha[q] = a.alpha[p]; b.gamma[q] = a.gamma[p]; b.epsilon[q] = a.epsilon[p];
-    b.agent_of_slot[q] = a.agent_of_slot[p]; b.hitq[q] = a.hitq[p];
-    if (a.s0 && b.s0) for (int k = 0; k < FRIQ_MAXK; k++) b.s0[(size_t)k * b.n_pad + q] = a.s0[(size_t)k * a.n_pad + p];
     const size_t po = (size_t)(p >> 5) * a.cap * FRIQ_TILE + (p & 31), qo = (size_t)(q >> 5) * b.cap * FRIQ_TILE + (q & 31);
     const int R = a.R[p];
-    for (int i = 0; i < R; i++) {
+    const bool pv = a.prevq && b.prevq;
+    for (int i = sl; i < R; i += FRIQ_MOVE_SLICES) {
         b.rbw[qo + (size_t)i * FRIQ_TILE] = a.rbw[po + (size_t)i * FRIQ_TILE];
         b.rbq[qo + (size_t)i * FRIQ_TILE] = a.rbq[po + (size_t)i * FRIQ_TILE];
+        if (pv) b.prevq[qo + (size_t)i * FRIQ_TILE] = a.prevq[po + (size_t)i * FRIQ_TILE];
     }
-    if (a.prevq && b.prevq)
-        for (int i = 0; i < R; i++) b.prevq[qo + (size_t)i * FRIQ_TILE] = a.prevq[po + (size_t)i * FRIQ_TILE];
 }
 template <typename T>
 __global__ void k_unpermute(friq_devstate st, const T *src, T *dst)
@@ -1111,7 +1144,7 @@ int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules
         k_retile_scan<<<1, 256, 0, s>>>(d_work, src.cap);
     }
     k_retile_assign<<<g, FRIQ_BLOCK, 0, s>>>(src, d_work, by_rules);
-    k_retile_move<<<g, FRIQ_BLOCK, 0, s>>>(src, dst, d_work);
+    k_retile_move<<<dim3((unsigned)((src.n + FRIQ_TILE - 1) / FRIQ_TILE)), dim3(FRIQ_TILE, FRIQ_MOVE_SLICES), 0, s>>>(src, dst, d_work);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1165,7 +1198,10 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     const bool coop = variant == 2 && hp->hit_scan && hp->safe_range &&
                       ((hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) || (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)));
     const bool tab = coop && hp->wtab && st.rbc && st.idx_cells == hp->wcells;
-    if (tab) k_refresh_index<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st);
+    if (tab) {
+        CK(cudaMemsetAsync(st.cmap, 0, (size_t)((st.n + FRIQ_TILE - 1) / FRIQ_TILE) * st.idx_cells * FRIQ_TILE * sizeof(unsigned short), s));
+        k_refresh_index<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st);
+    }
 #define FRIQ_LAUNCH_STEP(S_, P_, A_, ACH_, ENV_, UNR_)                                                                   \
     do {                                                                                                              \
         if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
