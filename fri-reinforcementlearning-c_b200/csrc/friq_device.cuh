@@ -143,6 +143,28 @@ __device__ __forceinline__ int friq_vag_concl(const friq_devprob &pb, const uint
     return -1;
 }
 
+// The same as real calls, for the fused kernels' rare branches (a snapped point off the observation, an unknown exact-hit
+// rule after a per-call state change): inlined they put ~1000 instructions of library sqrt / x87 power / reciprocal into the
+// step loop, whose body then no longer fits the 32 KB instruction cache level (no_instruction stalls at 2 warps per scheduler).
+template <int K, int P>
+__device__ __noinline__ int friq_vag_concl_cold(const friq_devprob *pb, const uint32_t *rbw, const double *rbq, int R, const double *vo, double *conc)
+{
+    double v[K], c, ws;
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = vo[k];
+    const int hit = friq_vag_concl<K, P>(*pb, rbw, rbq, nullptr, R, v, c, ws);
+    *conc = c;
+    return hit;
+}
+template <int K>
+__device__ __noinline__ int friq_first_hit_cold(const friq_devprob *pb, const uint32_t *rbw, int R, const double *vo)
+{
+    double v[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = vo[k];
+    return friq_first_hit<K>(*pb, rbw, R, v);
+}
+
 // ---------------------------------------------------------------------------------------
 // frirl_get_best_action (frirl_get_best_action.c:31-341) + FIVEVagConcl_FRIRL_BestAct
 // (:56-301): all A actions in one pass over the rule base (ACH actions per sweep when A is
@@ -410,6 +432,13 @@ __device__ __forceinline__ void friq_q_cooperative(const friq_devprob &pb, const
 //   ci[k] >= 0   the observation is the grid value with that index (quantiser)
 //   ci[k] == -1  unknown: search the dictionary for the VE value (custom start states)
 //   ci[k] == -2  the default episode start state: the host has done the search (def_hit)
+// index of the dictionary entry with VE value v, -1 if none (rare: custom start states; out of line to keep the step loop small)
+__device__ __noinline__ int friq_dict_find(const double *ve, int n, double v)
+{
+    for (int t = 0; t < n; t++) if (ve[t] == v) return t;
+    return -1;
+}
+__device__ __noinline__ double friq_obs_ve_cold(const friq_devprob *pb, int k, double x) { return friq_obs_ve(*pb, k, x); }
 template <int S>
 __device__ __forceinline__ uint32_t friq_obs_word(const friq_devprob &pb, const double *vo, const int *ci)
 {
@@ -418,7 +447,7 @@ __device__ __forceinline__ uint32_t friq_obs_word(const friq_devprob &pb, const 
     for (int k = 0; k < S; k++) {
         int j = ci[k];
         if (j == -2) j = pb.def_hit[k];
-        else if (j < 0) { for (int t = 0; t < pb.dict_len[k]; t++) if (pb.dict_ve[k][t] == vo[k]) { j = t; break; } }
+        else if (j < 0) j = friq_dict_find(pb.dict_ve[k], pb.dict_len[k], vo[k]);
         ok = ok && j >= 0;
         word |= (uint32_t)(j & (FRIQ_MAXDICT - 1)) << (FRIQ_IDX_BITS * k);
     }
@@ -773,7 +802,7 @@ __device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, do
 //                 FIVE_vag_concl_weight, FIVEVagConclWeight.c:125-175, same point, same RB)
 //   qs[] / vo_q[] the antecedents (s,a) and their VE values.
 // ---------------------------------------------------------------------------------------
-template <int S, int P>
+template <int S, int P, bool COLD = false>
 __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
                                                  const double *qs, const int *qi, double reward, double qp, int hitq, double qnow, double ws,
                                                  double alpha, double gamma)
@@ -793,7 +822,8 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
             double vg[K], wsg;
 #pragma unroll
             for (int k = 0; k < K; k++) vg[k] = pb.dict_ve[k][gi[k]];
-            hitg = friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vg, qg, wsg);
+            if constexpr (COLD) hitg = friq_vag_concl_cold<K, P>(&pb, rbw, rbq, R, vg, &qg);
+            else hitg = friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vg, qg, wsg);
         }
         if (hitg < 0) {                                // no rule there: append (five_add_rule.c:47-95)
             flags |= FRIQ_F_INSERTED;

@@ -134,13 +134,16 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             if (initial) {                               // frirl_episode.c:46-82
 #pragma unroll
                 for (int k = 0; k < S; k++) {
-                    if (st.s0) { s[k] = qs[k] = st.s0[(size_t)k * st.n_pad + ag]; vo[k] = vc[k] = friq_obs_ve(pb, k, s[k]); ci[k] = -1; }
+                    if (st.s0) { s[k] = qs[k] = st.s0[(size_t)k * st.n_pad + ag]; vo[k] = vc[k] = friq_obs_ve_cold(&pb, k, s[k]); ci[k] = -1; }
                     else { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; ci[k] = -2; }   // -2: dictionary index known to the host (def_hit)
                     cur[k] = cq[k] = s[k]; qi[k] = -1;
                 }
                 ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
                 prev_numru = R;
-                if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
+                if (track) {
+#pragma unroll 1
+                    for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
+                }
             } else {                                     // frirl_episode.c:97-112
                 friq_env_step<ENV>(pb.act_val[aidx], s, cur);
                 friq_env_reward<ENV>(cur, reward, done);
@@ -157,7 +160,8 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         // there is none (-1) and its Shepard sums ride along in this pass as one more chain.  -2 = unknown
         // (state set through the per-call API, or act_ve != act_ve_eval): scan for it.
         const bool upd = act && !initial && learn;
-        if (upd && (hitq == -2 || !pb.qp_reuse)) hitq = friq_first_hit<K>(pb, rbw, R, vo);
+        const bool qp_reuse = tabmode || pb.qp_reuse;    // table mode is only launched for problems with qp_reuse
+        if (upd && (hitq == -2 || !qp_reuse)) hitq = friq_first_hit_cold<K>(&pb, rbw, R, vo);
         const bool needq = upd && hitq < 0;
         double actconc[A], vagq, wsq; int hidx[A];
         const unsigned qm = __ballot_sync(wmask, needq);
@@ -196,25 +200,25 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             }
         }
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
-        const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
+        const int next_hit = qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
         if (act) qw = (ow != FRIQ_NO_TARGET && pb.act_hit[a2] >= 0) ? (ow | ((uint32_t)pb.act_hit[a2] << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET;
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }
         if (act && !initial) {
             sum_rules += (unsigned long long)R;
             if (learn) {                                 // frirl_update_sarsa.c:348-385
                 double qp, qnow, ws = 0.0;
-                if (pb.qp_reuse) qp = friq_pick<A>(actconc, a2);      // Q(s',a') == actconc[a'] bit for bit
+                if (qp_reuse) qp = friq_pick<A>(actconc, a2);         // Q(s',a') == actconc[a'] bit for bit
                 else {
-                    double vq[K], wsd;
+                    double vq[K];
 #pragma unroll
                     for (int k = 0; k < S; k++) vq[k] = vc[k];
                     vq[S] = pb.act_ve_eval[a2];
-                    friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vq, qp, wsd);
+                    friq_vag_concl_cold<K, P>(&pb, rbw, rbq, R, vq, &qp);
                 }
                 if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
                 else { ws = wsq; qnow = __ddiv_rn(vagq, wsq); }                               // FIVEVagConcl.c:302
                 const int R0 = R;
-                friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma);
+                friq_sarsa_apply<S, P, true>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma);
                 hitq = next_hit;
                 if (R > R0 && tabmode) {                 // a rule was appended: keep the indexes current
                     const int cn = friq_cell<K>(pb, rbw[(size_t)R0 * FRIQ_TILE]);
