@@ -570,6 +570,10 @@ __device__ __forceinline__ void friq_tab_sums(const double *__restrict__ rowd, c
         pq += 2 * B * FRIQ_TILE; psw += 2 * B * FRIQ_TILE;
     }
 }
+// lane number of the n-th (0-based) set bit of mask: partial warps only (the last warp of a batch); __fns expands to ~220
+// instructions per use, so it lives out of line
+__device__ __noinline__ int friq_nth_lane(unsigned mask, int n) { return (int)__fns(mask, 0, n + 1); }
+
 // the computed sums of one pair, one rule at a time through the library-exact chain: the table-mode kernel's rare fall-back
 // (a point that is no dictionary cell: custom off-grid start states), kept out of line so that it costs the kernel no registers
 template <int K, int P>
@@ -632,17 +636,18 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
         const bool has = p < np && gi < per_round;
         const int ent = has ? plist[gi] : 0;
         const int c = ent >> 5, j = ent & 31;
-        // ---- the owner's point and rule count
+        // ---- the owner's point (table mode needs it only for the rare computed fall-back) and rule count
         double pt[K];
+        auto fetch_point = [&]() {
 #pragma unroll
-        for (int k = 0; k < S; k++) {
-            const double x = __shfl_sync(wmask, vo_obs[k], j), y = __shfl_sync(wmask, vo_q[k], j);
-            pt[k] = (c == A) ? y : x;
-        }
-        {
+            for (int k = 0; k < S; k++) {
+                const double x = __shfl_sync(wmask, vo_obs[k], j), y = __shfl_sync(wmask, vo_q[k], j);
+                pt[k] = (c == A) ? y : x;
+            }
             const double y = __shfl_sync(wmask, vo_q[S], j);
             pt[S] = (c == A) ? y : pb.act_ve[c < A ? c : 0];
-        }
+        };
+        if constexpr (!TAB) fetch_point();
         const int Rj = __shfl_sync(wmask, R, j);
         const bool isq = has && c == A;
         double vag = 0.0, ws = 0.0;
@@ -660,6 +665,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             }
             const bool slow = has && !tab;
             if (__any_sync(wmask, slow)) {
+                fetch_point();
                 if (slow) {
                     double out[2];
                     friq_pair_sums_slow<K, P>(&pb, tw + j, tq + j, tsw + j, Rj, isq ? 1 : 0, pt, out);
@@ -728,7 +734,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             const int e = ofs[t] + __popc(chm[t] & lt) - p0;         // my pair of channel t is entry e of this round (if I have one)
             const bool mine = ((chm[t] >> lane) & 1u) && e >= 0 && e < per_round;
             const int src = mine ? e * g : rank;                      // rank of the group's first lane
-            const int sl = (wmask == 0xffffffffu) ? src : __fns(wmask, 0, src + 1);
+            const int sl = (wmask == 0xffffffffu) ? src : friq_nth_lane(wmask, src);
             if (t < A) { const double r = __shfl_sync(wmask, res, sl); if (mine) conc[t < A ? t : 0] = r; }
             else { const double a1 = __shfl_sync(wmask, vag, sl), a2 = __shfl_sync(wmask, ws, sl); if (mine) { vagq = a1; wsq = a2; } }
         }
