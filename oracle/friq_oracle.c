@@ -184,6 +184,7 @@ fo_agent *fo_agent_new(const fo_problem *P, int capacity, uint64_t seed) {
     a->P = P; a->cap = capacity; a->seed = seed;
     a->rant = calloc((size_t)capacity * P->K, sizeof(double)); a->rve = calloc((size_t)capacity * P->K, sizeof(double));
     a->rconc = calloc(capacity, sizeof(double)); a->w = calloc(capacity, sizeof(double)); a->prev_rconc = calloc(capacity, sizeof(double));
+    a->weights = calloc(capacity, sizeof(double));              /* FIVEInit.c:334 mallocs it uncleared: fresh pages, zeros in practice */
     a->alpha = P->alpha; a->gamma = P->gamma; a->epsilon = P->epsilon; a->learning = 1;
     /* corner rules, binary-counter order, q = 0 (frirl_init_rb.c:99-126) */
     int n = 1 << P->K; double ant[FO_MAXK];
@@ -201,7 +202,7 @@ fo_agent *fo_agent_new(const fo_problem *P, int capacity, uint64_t seed) {
     a->prev_reward = -1; a->prev_steps = -1;
     return a;
 }
-void fo_agent_free(fo_agent *a) { if (a) { free(a->rant); free(a->rve); free(a->rconc); free(a->w); free(a->prev_rconc); free(a); } }
+void fo_agent_free(fo_agent *a) { if (a) { free(a->rant); free(a->rve); free(a->rconc); free(a->w); free(a->weights); free(a->prev_rconc); free(a); } }
 
 /* ------------------------------------------------------------- FIVE evaluation */
 
@@ -300,14 +301,14 @@ void fo_update_sarsa(fo_agent *a, const double *q_ant, double reward, const doub
         a->inserted = 0;
     }
     int rules = a->R - (a->inserted ? 1 : 0);
-    int hit = fo_vag_concl_weight(a, q_ant, a->w);              /* a->w now holds normalised weights */
+    int hit = fo_vag_concl_weight(a, q_ant, a->weights);        /* frb->weights (:39-40): untouched on an exact hit */
     if (hit >= 0) {
         if (P->skip_rules == 0 || hit < rules) a->rconc[hit] = qnow + qdiff;   /* :55 */
         return;                                                               /* :61-63 */
     }
     if (P->skip_rules == 0) { rules = a->R; a->inserted = 0; }
     for (int i = 0; i < rules; i++)
-        if (a->w[i] > P->wsig) a->rconc[i] = qnow + qdiff * a->w[i];          /* :106-107,138 */
+        if (a->weights[i] > P->wsig) a->rconc[i] = qnow + qdiff * a->weights[i];   /* :106-107,138 */
 }
 
 /* ---------------------------------------------------------------- environments */
@@ -444,6 +445,7 @@ static void agent_step(fo_agent *a) {
         int same = (a->prev_numru == a->R) && (a->prev_steps == a->ep_steps) &&
                    (a->ep_return > P->reward_good_above) && (a->prev_reward == a->ep_return);
         if (same && a->learning) {
+            a->epended = 1;                                                  /* :90 */
             int ok = 1;
             for (int i = 0; i < a->R; i++) if (fabs(a->rconc[i] - a->prev_rconc[i]) >= P->qdiff_final_tol) { ok = 0; break; }
             if (ok) a->converged = 1;
@@ -474,6 +476,70 @@ int fo_run_construct(fo_agent *a, double *ep_log, int max_log) {
         if (a->converged) break;
     }
     return episodes;
+}
+
+/* ------------------------------------------------------------ knowledge sharing
+ * The reference's experimental multi-agent mode (CMake option BUILD_OPENMP): frirl_omp_run, frirl_agent.c:294-385. */
+
+/* merge_rb (frirl_agent.c:58-117): every rule of the sender, in order, is folded into the receiver's rule base */
+void fo_merge_rb(fo_agent *r, int Rs, const double *srant, const double *srconc) {
+    const fo_problem *P = r->P; const int K = P->K;
+    for (int i = 0; i < Rs; i++) {
+        const double *sant = srant + (size_t)i * K; const double sq = srconc[i];
+        int rule_i = fo_vag_concl_weight(r, sant, r->weights);              /* :75-76: weights stay STALE on an exact hit */
+        double rc;
+        fo_vag_concl(r, sant, &rc);                                          /* :78-79 */
+        double qdiff = -rc + sq;                                             /* :84 */
+        if (qdiff > P->qdiff_pos || qdiff < P->qdiff_neg) {                  /* :92 */
+            double g[FO_MAXK], rconc = rc;
+            for (int k = 0; k < K; k++) g[k] = fo_snap(P, k, sant[k]);      /* CHECK_STATES, :96-99 + :19-45 */
+            rule_i = fo_vag_concl(r, g, &rconc);
+            if (rule_i < 0) { fo_add_rule(r, g, 0.5 * rconc + 0.5 * sq); continue; }   /* :100-103 */
+            r->rconc[rule_i] = 0.9 * rconc + 0.1 * sq;                       /* :105 */
+            continue;
+        }
+        const double q = 0.9 * rc + 0.1 * sq;                                /* :110 */
+        for (int w = 0; w < r->R; w++)                                       /* update_rules, :47-55: an ASSIGNMENT of q * weight */
+            if (r->weights[w] > P->wsig) r->rconc[w] = q * r->weights[w];
+    }
+}
+
+/* frirl_omp_run (frirl_agent.c:294-385) for W agents created by fo_agent_new: start states (gen_def_states, :120-138),
+ * chunks of FRIRL_AGENT_EPCHUNK - 1 = 9 episodes (frirl_sequential_run.c:51-65,159-161), then agent 0's rules into every
+ * other agent and every other agent's rules into agent 0, until agent 0 finds its rule base complete.
+ * log rows: (agent, steps, return, rules) per finished episode in per-agent order; returns the number of rows. */
+int fo_team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log) {
+    const fo_problem *P = ag[0]->P; const int K = P->K;
+    int n = 0;
+    if (W > 2) {
+        const int R0 = ag[0]->R, gap = R0 / (W - 2);
+        for (int id = 1; id < W; id++) {
+            double s0[FO_MAXK];
+            const int idx = (id - 1) * gap;                                 /* may run past the corner rules: zeros there */
+            for (int i = 0; i < P->S; i++) s0[i] = idx < R0 ? ag[id]->rant[(size_t)idx * K + i] : 0.0;
+            fo_agent_set_initial_state(ag[id], s0);
+        }
+    }
+    for (int round = 0; round < max_rounds; round++) {
+        int running0 = 1;
+        for (int id = 0; id < W; id++) {                                    /* "#pragma omp parallel for": independent */
+            fo_agent *a = ag[id];
+            a->epended = 0; a->converged = 0;
+            for (int epchunk = 1; epchunk < 10; epchunk++) {
+                do agent_step(a); while (!a->need_reset);
+                if (log && n < max_log) { log[4 * n] = id; log[4 * n + 1] = a->last_steps; log[4 * n + 2] = a->last_return; log[4 * n + 3] = a->last_rules; }
+                n++;
+                if (a->converged) { if (id == 0) running0 = 0; break; }
+            }
+            if (id == 0 && !a->converged && !(a->episode_num < (uint32_t)P->max_episodes)) running0 = 0;
+        }
+        if (!running0) break;
+        if (!ag[0]->epended)
+            for (int id = 1; id < W; id++) fo_merge_rb(ag[id], ag[0]->R, ag[0]->rant, ag[0]->rconc);
+        for (int id = 1; id < W; id++)
+            if (!ag[id]->epended) fo_merge_rb(ag[0], ag[id]->R, ag[id]->rant, ag[id]->rconc);
+    }
+    return n;
 }
 
 /* ------------------------------------------------- flat accessors for ctypes use */

@@ -47,6 +47,9 @@ typedef struct fo_agent {
     double *rve;     /* [cap][K] VE value of each antecedent (five_add_rule.c:71-84) */
     double *rconc;   /* [cap] */
     double *w;       /* [cap] scratch: wi */
+    double *weights; /* [cap] FIVERB.weights (FIVE.h:24-76): the normalised weights of the LAST FIVE_vag_concl_weight call that
+                      * found no exact hit - persistent state: merge_rb (frirl_agent.c:58-117) re-uses it STALE after exact hits */
+    int epended;     /* frirl_desc.epended: the "same as the previous episode" predicate held in this chunk (frirl_sequential_run.c:90) */
     double *prev_rconc;
     /* episode state (frirl_episode.c) */
     double s[FO_MAXK], qant[FO_MAXK];
@@ -78,6 +81,10 @@ int  fo_vag_concl_weight(fo_agent *a, const double *ant, double *weights);
 int  fo_get_best_action(fo_agent *a, const double *states, double *actconc);
 void fo_update_sarsa(fo_agent *a, const double *q_ant, double reward, const double *cur_q_ant);
 double fo_snap(const fo_problem *P, int k, double x);
+void fo_agent_set_initial_state(fo_agent *a, const double *s0);
+/* knowledge sharing: frirl_agent.c merge_rb / frirl_omp_run */
+void fo_merge_rb(fo_agent *rcvr, int Rs, const double *srant, const double *srconc);
+int  fo_team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log);
 
 /* environment */
 void fo_env_step(const fo_problem *P, double action, const double *s, double *snew);

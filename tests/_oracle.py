@@ -47,6 +47,8 @@ def lib():
         L.fo_env_step.argtypes = [C.c_void_p, C.c_double, dp, dp]
         L.fo_env_reward.argtypes = [C.c_void_p, dp, dp, C.POINTER(C.c_int)]
         L.fo_env_quantize.argtypes = [C.c_void_p, dp, dp]
+        L.fo_merge_rb.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.fo_team_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -129,6 +131,11 @@ class Agent:
         s0 = np.ascontiguousarray(s0, dtype=np.float64)
         lib().fo_agent_set_initial_state(self.h, _p(s0))
 
+    def merge_rb(self, rant, rconc):
+        """merge_rb (frirl_agent.c:58-117): fold the sender's rules into this agent's rule base"""
+        rant = np.ascontiguousarray(rant, dtype=np.float64); rconc = np.ascontiguousarray(rconc, dtype=np.float64)
+        lib().fo_merge_rb(self.h, len(rconc), _p(rant), _p(rconc))
+
     def run_steps(self, n, stop_on_converge=0):
         lib().fo_agent_run_steps(self.h, n, stop_on_converge)
 
@@ -144,3 +151,11 @@ class Agent:
                     converged=int(o[5]), total_steps=int(o[6]), sum_rules=o[7], inserted=int(o[8]), overflow=int(o[9]),
                     ep_return=o[10], ep_steps=int(o[11]), need_reset=int(o[12]), step_in_ep=int(o[13]),
                     s=o[16:16 + K - 1].copy(), qant=o[24:24 + K].copy())
+
+
+def team_run(agents, max_rounds=200, max_log=20000):
+    """frirl_omp_run (frirl_agent.c:294-385) over the given agents; rows (agent, steps, return, rules) per finished episode"""
+    hs = (C.c_void_p * len(agents))(*[a.h for a in agents])
+    log = np.zeros(4 * max_log)
+    n = lib().fo_team_run(hs, len(agents), max_rounds, _p(log), max_log)
+    return log[:4 * n].reshape(n, 4)
