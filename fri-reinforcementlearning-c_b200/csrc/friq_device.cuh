@@ -811,7 +811,7 @@ __device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, do
 template <int S, int P, bool COLD = false>
 __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
                                                  const double *qs, const int *qi, double reward, double qp, int hitq, double qnow, double ws,
-                                                 double alpha, double gamma)
+                                                 double alpha, double gamma, double *wref = nullptr)
 {   // qi[k] >= 0: qs[k] is known to BE the grid value dict_val[k][qi[k]] (snapping an on-grid value returns it)
     constexpr int K = S + 1;
     const double qdiff = __dmul_rn(alpha, __dsub_rn(__dadd_rn(reward, __dmul_rn(gamma, qp)), qnow));   // :358
@@ -844,6 +844,10 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
         if (pb.skip_rules == 0 || hitq < rules) rbq[(size_t)hitq * FRIQ_TILE] = __dadd_rn(qnow, qdiff);   // :55
         return;                                                                                          // :61-63
     }
+    if (wref) {                                        // FIVERB.weights as the reference leaves it (FIVEVagConclWeight.c:153-175)
+#pragma unroll 1
+        for (int i = 0; i < R; i++) wref[(size_t)i * FRIQ_TILE] = __ddiv_rn(sw[(size_t)i * FRIQ_TILE], ws);
+    }
     if (pb.skip_rules == 0) { rules = R; flags &= ~FRIQ_F_INSERTED; }
     // cheap superset of (wi/ws > wsig): only the few rules that pass it pay the division; four rules per trip, one branch
     const double pre = (pb.wsig >= 0.05) ? __dmul_rn(0.04, ws) : -1.0;
@@ -859,6 +863,65 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
                 const double wgt = __ddiv_rn(wi[u], ws);                                                         // A6
                 if (wgt > pb.wsig) rbq[(size_t)(i + u) * FRIQ_TILE] = __dadd_rn(qnow, __dmul_rn(qdiff, wgt));    // A7
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// merge_rb (frirl_agent.c:58-117, the reference's experimental knowledge-sharing mode): every rule of the sender, in order, is
+// folded into the receiver's rule base.  One thread per receiver; the sender is a list of packed rule words and consequents
+// with element stride `ss` (32 = a column of another agent's tile, 1 = a dense list).  wref is FIVERB.weights: written only
+// when FIVE_vag_concl_weight finds no exact hit (:75-76) and read - possibly STALE - by update_rules (:47-55, :110).
+// Library-exact chains; this is a per-chunk operation, not the hot loop.
+// ---------------------------------------------------------------------------------------
+template <int K, int P>
+__device__ __noinline__ void friq_merge_rb(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, double *wref, int cap, int &R, int &flags,
+                                           const uint32_t *sw_words, const double *sq_vals, int ss, int Rs)
+{
+    for (int r = 0; r < Rs; r++) {
+        const uint32_t word = sw_words[(size_t)r * ss];
+        const double sq = sq_vals[(size_t)r * ss];
+        double vo[K], ant[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int j = (word >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1);
+            vo[k] = pb.dict_ve[k][j]; ant[k] = pb.dict_val[k][j];
+        }
+        const int hit = friq_first_hit<K>(pb, rbw, R, vo);                       // FIVE_vag_concl_weight, :75-76
+        double rc;
+        if (hit >= 0) rc = rbq[(size_t)hit * FRIQ_TILE];                         // FIVE_vag_concl, :78-79
+        else {
+            double vagc, ws;
+            friq_shepard<K, P>(pb, rbw, rbq, sw, R, vo, vagc, ws);
+            rc = __ddiv_rn(vagc, ws);
+            for (int i = 0; i < R; i++) wref[(size_t)i * FRIQ_TILE] = __ddiv_rn(sw[(size_t)i * FRIQ_TILE], ws);
+        }
+        const double qdiff = __dadd_rn(-rc, sq);                                 // :84
+        if (qdiff > pb.qdiff_pos || qdiff < pb.qdiff_neg) {                      // :92
+            int gi[K]; bool same = true; uint32_t packed = 0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {                                        // CHECK_STATES, :96-99 + :19-45
+                gi[k] = friq_snap_index(pb, k, ant[k]);
+                same = same && (pb.dict_val[k][gi[k]] == ant[k]);
+                packed |= (uint32_t)gi[k] << (FRIQ_IDX_BITS * k);
+            }
+            int hitg = hit; double rcg = rc;
+            if (!same) {
+                double vg[K], wsg;
+#pragma unroll
+                for (int k = 0; k < K; k++) vg[k] = pb.dict_ve[k][gi[k]];
+                hitg = friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vg, rcg, wsg);
+            }
+            if (hitg < 0) {                                                      // :100-103
+                if (R < cap) { rbw[(size_t)R * FRIQ_TILE] = packed; rbq[(size_t)R * FRIQ_TILE] = __dadd_rn(__dmul_rn(0.5, rcg), __dmul_rn(0.5, sq)); R++; }
+                else flags |= FRIQ_F_OVERFLOW;
+            } else rbq[(size_t)hitg * FRIQ_TILE] = __dadd_rn(__dmul_rn(0.9, rcg), __dmul_rn(0.1, sq));   // :105
+            continue;
+        }
+        const double q = __dadd_rn(__dmul_rn(0.9, rc), __dmul_rn(0.1, sq));      // :110
+        for (int w = 0; w < R; w++) {                                            // update_rules, :47-55
+            const double wt = wref[(size_t)w * FRIQ_TILE];
+            if (wt > pb.wsig) rbq[(size_t)w * FRIQ_TILE] = __dmul_rn(q, wt);
         }
     }
 }

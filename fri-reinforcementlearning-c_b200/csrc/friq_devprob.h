@@ -33,9 +33,12 @@
 #endif
 
 /* per-agent flag bits */
-enum { FRIQ_F_NEED_RESET = 1, FRIQ_F_INSERTED = 2, FRIQ_F_CONVERGED = 4, FRIQ_F_OVERFLOW = 8 };
+enum { FRIQ_F_NEED_RESET = 1, FRIQ_F_INSERTED = 2, FRIQ_F_CONVERGED = 4, FRIQ_F_OVERFLOW = 8,
+       FRIQ_F_EPENDED = 16,     /* frirl_desc.epended: the "same as the previous episode" test held (frirl_sequential_run.c:90) */
+       FRIQ_F_TEAM_DONE = 32 }; /* knowledge sharing: this agent's team has finished (its leader found the rule base complete) */
 /* run mode bits */
-enum { FRIQ_M_LEARN = 1, FRIQ_M_TRACK = 2, FRIQ_M_STOP_ON_CONVERGE = 4, FRIQ_M_STOP_AT_EPISODE_END = 8, FRIQ_M_RETILE = 16 };
+enum { FRIQ_M_LEARN = 1, FRIQ_M_TRACK = 2, FRIQ_M_STOP_ON_CONVERGE = 4, FRIQ_M_STOP_AT_EPISODE_END = 8, FRIQ_M_RETILE = 16,
+       FRIQ_M_KEEP_WEIGHTS = 32 };   /* maintain FIVERB.weights (friq_devstate.wref) exactly as the reference does: merge_rb reads it stale */
 
 typedef struct friq_devprob {
     int S, K, A, U, p, env, skip_rules, no_random;
@@ -90,6 +93,9 @@ typedef struct friq_devstate {
     int *agent_of_slot;         /* [n_pad] which agent lives in slot p (identity unless re-tiled by rule count) */
     /* derived per-agent indexes of the fused kernel's table mode (friq_devprob.wtab); rebuilt from rbw before every launch
      * (k_refresh_index) and kept current by the kernel when it appends a rule; NULL when the problem has no table */
+    double *wref;               /* [tiles][cap][32] or NULL: FIVERB.weights (FIVE.h:24-76), the NORMALISED weights of the last
+                                 * FIVE_vag_concl_weight call without an exact hit (update_rules, frirl_update_sarsa.c:39-40; merge_rb,
+                                 * frirl_agent.c:75-76) - persistent, only kept under FRIQ_M_KEEP_WEIGHTS (knowledge sharing) */
     unsigned short *rbc;        /* [tiles][cap][32] dictionary cell of every rule (column of wtab) */
     unsigned short *cmap;       /* [tiles][idx_cells][32] 1 + index of the first rule in that cell, 0 = none: exact hits in O(1) */
     int idx_cells;              /* cells per agent in cmap (= friq_devprob.wcells when the arrays were sized) */
@@ -138,6 +144,10 @@ int friqd_rule_distance(const friq_devprob *hprob, const friq_devprob *dprob, fr
 int friqd_bestact_dists(const friq_devprob *hprob, friq_devstate st, const double *d_dists, double *d_conc, void *stream);
 unsigned long friqd_rbc_tile_slots(int cap);      /* u16 entries of friq_devstate.rbc per tile of 32 agents */
 int friqd_build_wtab(const friq_devprob *hprob, const friq_devprob *dprob, double *d_wtab);
+int friqd_merge_rb(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, long receiver, const unsigned int *d_words,
+                   const double *d_q, int Rs, void *stream);
+int friqd_team_merge(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, int team, int phase, void *stream);
+int friqd_team_ctl(friq_devstate st, int team, int op, int max_episodes, int *d_count, void *stream);
 int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream);
 int friqd_pow_x87(const double *d_x, double *d_out, long n, int p, int force_exact, void *stream);
 int friqd_fp64_peak(double *out_ginstr_per_s, int iters);

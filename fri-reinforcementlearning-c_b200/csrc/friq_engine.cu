@@ -83,6 +83,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 #endif
     FRIQ_SMEM_PROLOGUE();
     double *prevq = st.prevq ? st.prevq + tile_off : nullptr;
+    double *wref = ((mode & FRIQ_M_KEEP_WEIGHTS) && st.wref) ? st.wref + tile_off : nullptr;
 
     // ---- agent state -> registers
     double s[S], qs[K], vo[K];
@@ -218,7 +219,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
                 else { ws = wsq; qnow = __ddiv_rn(vagq, wsq); }                               // FIVEVagConcl.c:302
                 const int R0 = R;
-                friq_sarsa_apply<S, P, true>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma);
+                friq_sarsa_apply<S, P, true>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref);
                 hitq = next_hit;
                 if (R > R0 && tabmode) {                 // a rule was appended: keep the indexes current
                     const int cn = friq_cell<K>(pb, rbw[(size_t)R0 * FRIQ_TILE]);
@@ -243,6 +244,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             if (done || step_in_ep >= pb.max_steps) {
                 // "RB complete" predicate, frirl_sequential_run.c:83-150
                 if (learn && track && prev_numru == R && prev_steps == step_in_ep && ep_return > pb.reward_good_above && prev_reward == ep_return) {
+                    flags |= FRIQ_F_EPENDED;                                  // :90
                     bool ok = true;
                     for (int i = 0; i < R && ok; i++)
                         if (fabs(__dsub_rn(rbq[(size_t)i * FRIQ_TILE], prevq[(size_t)i * FRIQ_TILE])) >= pb.qdiff_final_tol) ok = false;
@@ -1041,6 +1043,64 @@ __global__ void k_unpermute(friq_devstate st, const T *src, T *dst)
     if (p < st.n) dst[st.agent_of_slot[p]] = src[p];
 }
 
+// ---- knowledge sharing (frirl_agent.c:58-117, 294-385)
+// one thread per receiver; receiver < 0: every agent.  The sender is a dense list (d_words, d_q).
+template <int S, int P>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
+k_merge_list(const friq_devprob *__restrict__ gprob, friq_devstate st, long receiver, const unsigned int *d_words, const double *d_q, int Rs)
+{
+    FRIQ_SMEM_PROLOGUE();
+    if (receiver >= 0 && ag != receiver) return;
+    int R = st.R[ag], flags = st.flags[ag];
+    friq_merge_rb<S + 1, P>(pb, rbw, rbq, sw, st.wref + tile_off, st.cap, R, flags, d_words, d_q, 1, Rs);
+    st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
+}
+// teams of `team` consecutive agents, member 0 = leader.  phase 0: the leader's rules into every other member (skipped when
+// the leader's chunk "pended", frirl_agent.c:338-349); phase 1: every other member's rules, in member order, into the leader
+// (each skipped when that member pended, :353-363).  Finished teams are left alone.
+template <int S, int P>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
+k_team_merge(const friq_devprob *__restrict__ gprob, friq_devstate st, int team, int phase)
+{
+    FRIQ_SMEM_PROLOGUE();
+    const long lead = ag - ag % team;
+    if (lead + team > st.n) return;                          // an incomplete trailing team takes no part
+    if (st.flags[lead] & FRIQ_F_TEAM_DONE) return;
+    int R = st.R[ag], flags = st.flags[ag];
+    double *wref = st.wref + tile_off;
+    if (phase == 0) {
+        if (ag == lead || (st.flags[lead] & FRIQ_F_EPENDED)) return;
+        const size_t so = (size_t)(lead >> 5) * st.cap * FRIQ_TILE + (lead & 31);
+        friq_merge_rb<S + 1, P>(pb, rbw, rbq, sw, wref, st.cap, R, flags, st.rbw + so, st.rbq + so, FRIQ_TILE, st.R[lead]);
+    } else {
+        if (ag != lead) return;
+        for (int id = 1; id < team; id++) {
+            const long m = lead + id;
+            if (st.flags[m] & FRIQ_F_EPENDED) continue;
+            const size_t so = (size_t)(m >> 5) * st.cap * FRIQ_TILE + (m & 31);
+            friq_merge_rb<S + 1, P>(pb, rbw, rbq, sw, wref, st.cap, R, flags, st.rbw + so, st.rbq + so, FRIQ_TILE, st.R[m]);
+        }
+    }
+    st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
+}
+// op 0, before a chunk: members of running teams forget "converged" / "pended" (frirl_sequential_run.c:34-36), members of finished
+// teams are frozen (converged, so FRIQ_M_STOP_ON_CONVERGE skips them).  op 1, after a chunk: a team whose leader found its rule base
+// complete (or ran out of episodes, :59-64) is finished; *count = teams still running.
+__global__ void k_team_ctl(friq_devstate st, int team, int op, int max_episodes, int *count)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n) return;
+    const long lead = ag - ag % team;
+    if (lead + team > st.n) { if (op == 0) st.flags[ag] |= FRIQ_F_CONVERGED | FRIQ_F_TEAM_DONE; return; }
+    if (op == 0) {
+        if (st.flags[lead] & FRIQ_F_TEAM_DONE) st.flags[ag] |= FRIQ_F_CONVERGED;
+        else st.flags[ag] &= ~(FRIQ_F_CONVERGED | FRIQ_F_EPENDED);
+    } else if (ag == lead && !(st.flags[ag] & FRIQ_F_TEAM_DONE)) {
+        if ((st.flags[ag] & FRIQ_F_CONVERGED) || st.ep_num[ag] >= (unsigned)max_episodes) st.flags[ag] |= FRIQ_F_TEAM_DONE;
+        else atomicAdd(count, 1);
+    }
+}
+
 // memoised Shepard weights (friq_devprob.wtab): wtab[q * cells + r] = 1 / d(q, r)^p for every pair of dictionary cells, through the
 // same device functions as a computed chain (friq_dist2 left-to-right over the dimensions, sqrt, x87 power, reciprocal)
 template <int K, int P>
@@ -1339,6 +1399,39 @@ int friqd_build_wtab(const friq_devprob *hp, const friq_devprob *dprob, double *
     else return (int)cudaErrorInvalidValue;
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
+    return 0;
+}
+int friqd_merge_rb(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long receiver, const unsigned int *d_words,
+                   const double *d_q, int Rs, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (!st.wref) return (int)cudaErrorInvalidValue;
+    if (hp->S == 2 && hp->p == 3) k_merge_list<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
+    else if (hp->S == 4 && hp->p == 5) k_merge_list<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
+    else if (hp->S == 1 && hp->p == 2) k_merge_list<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
+    else if (hp->S == 3 && hp->p == 4) k_merge_list<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_team_merge(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, int team, int phase, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (!st.wref || team < 2) return (int)cudaErrorInvalidValue;
+    if (hp->S == 2 && hp->p == 3) k_team_merge<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
+    else if (hp->S == 4 && hp->p == 5) k_team_merge<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
+    else if (hp->S == 1 && hp->p == 2) k_team_merge<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
+    else if (hp->S == 3 && hp->p == 4) k_team_merge<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_team_ctl(friq_devstate st, int team, int op, int max_episodes, int *d_count, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (op == 1) { CK(cudaMemsetAsync(d_count, 0, sizeof(int), s)); }
+    k_team_ctl<<<grid_for(st.n), FRIQ_BLOCK, 0, s>>>(st, team, op, max_episodes, d_count);
+    CK(cudaGetLastError());
     return 0;
 }
 int friqd_trig(const double *d_x, double *d_sin, double *d_cos, long n, void *stream)

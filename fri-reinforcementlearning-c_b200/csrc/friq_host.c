@@ -407,6 +407,7 @@ static void free_state(friq_devstate *st)
     friqd_free(st->rbw); friqd_free(st->rbq); if (st->prevq) friqd_free(st->prevq);
     if (st->rbc) friqd_free(st->rbc);
     if (st->cmap) friqd_free(st->cmap);
+    if (st->wref) friqd_free(st->wref);
     friqd_free(st->s);        /* slab base */
 }
 
@@ -415,7 +416,7 @@ static int retile(friq_batch *b, int by_rules, void *stream)
 {
     if (!by_rules && !b->permuted) return 0;
     if (!b->have_st2) {
-        b->st2 = b->st; b->st2.prevq = NULL; b->st2.s0 = NULL; b->st2.rbc = NULL; b->st2.cmap = NULL;
+        b->st2 = b->st; b->st2.prevq = NULL; b->st2.s0 = NULL; b->st2.rbc = NULL; b->st2.cmap = NULL; b->st2.wref = NULL;
         int rc = alloc_state(&b->st2, 0); if (rc) return rc;
         if (b->st.s0) DEV(friqd_malloc((void **)&b->st2.s0, 8 * FRIQ_MAXK * (size_t)b->st.n_pad));
         DEV(friqd_malloc((void **)&b->d_work, sizeof(int) * (FRIQ_MAXGROUPS * ((size_t)b->st.cap + 2 + FRIQ_TILE) + (size_t)b->st.n_pad)));
@@ -460,6 +461,14 @@ static int ensure_index(friq_batch *b)
     const int cells = b->P->hp.wtab ? b->P->hp.wcells : 0;
     int rc = ensure_index_one(&b->st, cells); if (rc) return rc;
     if (b->have_st2) { rc = ensure_index_one(&b->st2, cells); if (rc) return rc; }
+    return 0;
+}
+/* FIVERB.weights of every agent (friq_devstate.wref), zero like the reference's fresh allocation (FIVEInit.c:334) */
+static int ensure_wref(friq_batch *b)
+{
+    if (b->st.wref) return 0;
+    const size_t bytes = (size_t)b->st.n_pad * b->st.cap * 8;
+    DEV(friqd_malloc((void **)&b->st.wref, bytes)); DEV(friqd_memset(b->st.wref, 0, bytes));
     return 0;
 }
 #define IDENTITY(b) do { if ((b)->permuted) { DEV(friqd_device_sync()); int rc_ = retile((b), 0, NULL); if (rc_) return rc_; DEV(friqd_device_sync()); } } while (0)
@@ -692,6 +701,11 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         return 0;
     }
     { int rci = ensure_index(b); if (rci) return rci; }
+    if (mode & FRIQ_RUN_KEEP_WEIGHTS) {
+        if (mode & FRIQ_RUN_RETILE) FAIL(6, "friq_batch_run: FRIQ_RUN_KEEP_WEIGHTS cannot be combined with FRIQ_RUN_RETILE");
+        IDENTITY(b);
+        int rcw = ensure_wref(b); if (rcw) return rcw;
+    }
     if ((mode & FRIQ_RUN_TRACK_CONVERGENCE) && !b->st.prevq) {
         const size_t slots = (size_t)b->st.n_pad * b->st.cap;
         DEV(friqd_malloc((void **)&b->st.prevq, slots * 8)); DEV(friqd_memset(b->st.prevq, 0, slots * 8));
@@ -978,6 +992,134 @@ int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double 
     R++;
     DEV(friqd_h2d(b->st.R + agent, &R, sizeof(int)));
     { const int unknown = -2; DEV(friqd_h2d(b->st.hitq + agent, &unknown, sizeof(int))); }
+    return 0;
+}
+
+/* merge_rb (frirl_agent.c:58-117): the sender's rule list folded into one agent's rule base (agent < 0: into every agent's).
+ * The receivers' FIVERB.weights are the ones kept by runs with FRIQ_RUN_KEEP_WEIGHTS (zero before any such run). */
+int friq_batch_merge_rb(friq_batch *b, long agent, int Rs, const double *rant, const double *rconc)
+{
+    friq_problem *P = b->P; const int K = P->hp.K;
+    if (agent >= b->st.n) FAIL(5, "friq_batch_merge_rb: agent %ld out of range", agent);
+    if (Rs < 0) FAIL(5, "friq_batch_merge_rb: negative rule count");
+    if (Rs == 0) return 0;
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    unsigned int *w = (unsigned int *)malloc(sizeof(unsigned int) * Rs);
+    int grew = 0;
+    for (int i = 0; i < Rs; i++) {
+        unsigned int word = 0;
+        for (int k = 0; k < K; k++) {
+            const int before = P->hp.dict_len[k];
+            const int j = dict_find_or_add(P, k, rant[(size_t)i * K + k]);
+            if (j < 0) { free(w); FAIL(5, "friq_batch_merge_rb: more than %d distinct antecedent values in dimension %d", FRIQ_MAXDICT, k); }
+            grew |= (P->hp.dict_len[k] != before);
+            word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
+        }
+        w[i] = word;
+    }
+    int rc = 0;
+    if (grew) { refresh_hit_scan(P); rc = problem_publish(P); }
+    if (!rc) rc = ensure_wref(b);
+    unsigned int *dw = NULL; double *dq = NULL;
+    if (!rc) rc = friqd_malloc((void **)&dw, sizeof(unsigned int) * Rs);
+    if (!rc) rc = friqd_malloc((void **)&dq, sizeof(double) * Rs);
+    if (!rc) rc = friqd_h2d(dw, w, sizeof(unsigned int) * Rs);
+    if (!rc) rc = friqd_h2d(dq, rconc, sizeof(double) * Rs);
+    if (!rc) rc = friqd_merge_rb(&P->hp, P->dp, b->st, agent, dw, dq, Rs, NULL);
+    if (!rc) rc = friqd_device_sync();
+    if (dw) friqd_free(dw);
+    if (dq) friqd_free(dq);
+    free(w);
+    if (rc) FAIL(rc, "friq_batch_merge_rb: %s", friqd_error_string(rc));
+    return 0;
+}
+
+/* Knowledge-sharing run (the reference's experimental frirl_omp_run, frirl_agent.c:294-385) for a batch of TEAMS of
+ * `team` consecutive agents, all teams in parallel on the device:
+ *   member 0 (the leader) starts its episodes at values_def, member id >= 1 at the state part of corner rule (id - 1) * gap,
+ *   gap = corner rules / (team - 2) (gen_def_states, :120-138; past the last corner rule the reference reads zeros);
+ *   a round = every member learns a chunk of FRIRL_AGENT_EPCHUNK - 1 = 9 episodes (fewer when its "rule base complete" test fires,
+ *   frirl_sequential_run.c:51-65,152-161), then the leader's rules are merged into every other member and every other member's
+ *   rules into the leader (merge_rb, members that "pended" in the chunk are skipped, :338-363);
+ *   a team is finished when its leader finds its rule base complete (or runs out of episodes).
+ * log (optional): rows (agent, steps, return, rules) of every finished episode, in the order the reference prints them per agent;
+ * the caller sizes it (max_log rows), *n_log returns the rows that would have been written.  Returns 0; *rounds_out = rounds run. */
+int friq_team_run(friq_batch *b, int team, int max_rounds, double *log, long max_log, long *n_log, int *rounds_out)
+{
+    friq_problem *P = b->P; const friq_devprob *hp = &P->hp;
+    const long n = b->st.n; const int S = hp->S;
+    if (team < 3) FAIL(6, "friq_team_run: a team needs at least 3 agents (the reference divides by team - 2, frirl_agent.c:132)");
+    if (n < team) FAIL(6, "friq_team_run: the batch holds no complete team of %d agents", team);
+    if (hp->env == FRIQ_ENV_HOST_CALLBACKS) FAIL(6, "friq_team_run: the problem has no built-in environment");
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    {   /* start states */
+        double *s0 = (double *)calloc((size_t)n * S, sizeof(double));
+        const int gap = hp->ncorner / (team - 2);
+        for (long i = 0; i < n; i++) {
+            const int id = (int)(i % team);
+            for (int k = 0; k < S; k++) {
+                double v = hp->values_def[k];
+                if (id >= 1) {
+                    const int idx = (id - 1) * gap;
+                    v = idx < hp->ncorner ? hp->dict_val[k][(hp->corner[idx] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)] : 0.0;
+                }
+                s0[(size_t)i * S + k] = v;
+            }
+        }
+        int rc = friq_batch_set_initial_state(b, s0);
+        free(s0);
+        if (rc) return rc;
+    }
+    { int rc = ensure_wref(b); if (rc) return rc; }
+    int *d_count = NULL; DEV(friqd_malloc((void **)&d_count, sizeof(int)));
+    int *ep_before = NULL, *ep_after = NULL, *h_steps = NULL, *h_rules = NULL; double *h_ret = NULL;
+    if (log || n_log) {
+        ep_before = (int *)malloc(sizeof(int) * n); ep_after = (int *)malloc(sizeof(int) * n);
+        h_steps = (int *)malloc(sizeof(int) * n); h_rules = (int *)malloc(sizeof(int) * n); h_ret = (double *)malloc(sizeof(double) * n);
+    }
+    /* per-agent logs are kept in per-agent order: collect (round, episode) rows, then emit agent by agent */
+    long rows = 0, cap_rows = 0; double *tmp = NULL;
+    const int mode = FRIQ_RUN_LEARN | FRIQ_RUN_TRACK_CONVERGENCE | FRIQ_RUN_STOP_AT_EPISODE_END | FRIQ_RUN_STOP_ON_CONVERGE | FRIQ_RUN_KEEP_WEIGHTS;
+    int rounds = 0, rc = 0;
+    for (; rounds < max_rounds && !rc; rounds++) {
+        rc = friqd_team_ctl(b->st, team, 0, hp->max_episodes, d_count, NULL);
+        for (int e = 1; e < 10 && !rc; e++) {                                /* epchunk = 1 .. FRIRL_AGENT_EPCHUNK - 1 */
+            if (ep_before) rc = friqd_d2h(ep_before, b->st.ep_num, 4 * n);
+            if (!rc) rc = friq_batch_run(b, hp->max_steps, mode, NULL);
+            if (!rc && ep_before) {
+                rc = friqd_device_sync();
+                if (!rc) rc = friqd_d2h(ep_after, b->st.ep_num, 4 * n);
+                if (!rc) rc = friqd_d2h(h_steps, b->st.last_steps, 4 * n);
+                if (!rc) rc = friqd_d2h(h_rules, b->st.last_rules, 4 * n);
+                if (!rc) rc = friqd_d2h(h_ret, b->st.last_return, 8 * n);
+                for (long i = 0; i < n && !rc; i++) if (ep_after[i] != ep_before[i]) {
+                    if (rows == cap_rows) { cap_rows = cap_rows ? cap_rows * 2 : 4096; tmp = (double *)realloc(tmp, sizeof(double) * 4 * cap_rows); }
+                    tmp[4 * rows] = (double)i; tmp[4 * rows + 1] = h_steps[i]; tmp[4 * rows + 2] = h_ret[i]; tmp[4 * rows + 3] = h_rules[i];
+                    rows++;
+                }
+            }
+        }
+        int running = 0;
+        if (!rc) rc = friqd_team_ctl(b->st, team, 1, hp->max_episodes, d_count, NULL);
+        if (!rc) rc = friqd_device_sync();
+        if (!rc) rc = friqd_d2h(&running, d_count, sizeof(int));
+        if (rc || running == 0) { rounds++; break; }
+        rc = friqd_team_merge(hp, P->dp, b->st, team, 0, NULL);
+        if (!rc) rc = friqd_team_merge(hp, P->dp, b->st, team, 1, NULL);
+        if (!rc) rc = friqd_device_sync();
+    }
+    if (!rc && tmp) {                                                       /* stable sort by agent */
+        long o = 0;
+        for (long a = 0; a < n; a++)
+            for (long r = 0; r < rows; r++) if ((long)tmp[4 * r] == a) { if (log && o < max_log) memcpy(log + 4 * o, tmp + 4 * r, sizeof(double) * 4); o++; }
+    }
+    if (n_log) *n_log = rows;
+    if (rounds_out) *rounds_out = rounds;
+    free(tmp); free(ep_before); free(ep_after); free(h_steps); free(h_rules); free(h_ret);
+    friqd_free(d_count);
+    if (rc) FAIL(rc, "friq_team_run: %s", friqd_error_string(rc));
     return 0;
 }
 

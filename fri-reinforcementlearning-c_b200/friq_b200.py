@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("FRIQ_LIB") or os.path.join(HERE, "libfriq_b200.so")  
 
 ENV_MOUNTAINCAR, ENV_ACROBOT, ENV_CARTPOLE = 0, 1, 2
 ENV_ID = {"mountaincar": 0, "acrobot": 1, "cartpole": 2}
-RUN_LEARN, RUN_TRACK, RUN_STOP_ON_CONVERGE, RUN_STOP_AT_EPISODE_END, RUN_RETILE = 1, 2, 4, 8, 16
-F_NEED_RESET, F_INSERTED, F_CONVERGED, F_OVERFLOW = 1, 2, 4, 8
+RUN_LEARN, RUN_TRACK, RUN_STOP_ON_CONVERGE, RUN_STOP_AT_EPISODE_END, RUN_RETILE, RUN_KEEP_WEIGHTS = 1, 2, 4, 8, 16, 32
+F_NEED_RESET, F_INSERTED, F_CONVERGED, F_OVERFLOW, F_EPENDED, F_TEAM_DONE = 1, 2, 4, 8, 16, 32
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
@@ -72,6 +72,8 @@ SYMBOLS = {
     "friq_batch_bestact_from_dists": (C.c_int, [C.c_void_p, dp, dp]),
     "friq_batch_append_rule": (C.c_int, [C.c_void_p, C.c_long, dp, C.c_double]),
     "friq_batch_remove_rule": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
+    "friq_batch_merge_rb": (C.c_int, [C.c_void_p, C.c_long, C.c_int, dp, dp]),
+    "friq_team_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, dp, C.c_long, C.POINTER(C.c_long), ip]),
     "friq_batch_save_rb_files": (C.c_int, [C.c_void_p, C.c_long, C.c_long, C.c_char_p, C.c_int]),
     "friq_batch_load_rb_file": (C.c_int, [C.c_void_p, C.c_long, C.c_char_p]),
     "friq_batch_save_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -248,6 +250,17 @@ class Batch:
     def run_host(self, n_steps, mode, alpha_ptr, gamma_ptr, eps_ptr, ret_ptr, steps_ptr, rules_ptr, stream=None):
         """End-to-end call with HOST pointers (e.g. pinned torch tensors): H2D, run, D2H, sync."""
         _ck(lib().friq_batch_run_host(self.h, alpha_ptr, gamma_ptr, eps_ptr, int(n_steps), int(mode), ret_ptr, steps_ptr, rules_ptr, stream))
+
+    def merge_rb(self, rant, rconc, agent=-1):
+        """merge_rb (frirl_agent.c:58-117): fold a sender's rule list into one agent's (agent < 0: every agent's) rule base"""
+        rant, rconc = _f64(rant), _f64(rconc)
+        _ck(lib().friq_batch_merge_rb(self.h, agent, len(rconc), _p(rant), _p(rconc)))
+
+    def team_run(self, team, max_rounds=200, max_log=100000):
+        """frirl_omp_run (frirl_agent.c:294-385) for teams of `team` consecutive agents; returns (log rows, rounds)"""
+        log = np.zeros((max_log, 4)); n = C.c_long(0); rounds = C.c_int(0)
+        _ck(lib().friq_team_run(self.h, int(team), int(max_rounds), _p(log), max_log, C.byref(n), C.byref(rounds)))
+        return log[:min(n.value, max_log)].copy(), rounds.value
 
     # ---- per-call entry points
     def vag_concl(self, ant):

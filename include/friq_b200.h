@@ -34,6 +34,8 @@ extern "C" {
 #define FRIQ_RUN_STOP_ON_CONVERGE 4    /* converged agents stop stepping */
 #define FRIQ_RUN_STOP_AT_EPISODE_END 8 /* every agent stops after finishing its current episode (frirl_episode granularity) */
 #define FRIQ_RUN_RETILE 16             /* before the launch, re-assign agents to warps by rule count (results unaffected) */
+#define FRIQ_RUN_KEEP_WEIGHTS 32       /* maintain every agent's FIVERB.weights (FIVE.h:24-76) exactly as the reference leaves it after
+                                        * update_rules (frirl_update_sarsa.c:39-40): merge_rb reads it stale.  Not with FRIQ_RUN_RETILE. */
 
 /* One dimension of the problem; field for field struct frirl_dimension_desc
  * (src/frirl/frirl_types.h:34-44).  values / universe may be NULL, in which case
@@ -152,6 +154,21 @@ int friq_batch_remove_rule(friq_batch *b, long agent, int rule);
  * in order, which gives exactly the reference's sequential result.  verbose != 0 prints the reference's log lines. */
 int friq_reduce_rulebase(friq_problem *p, int device, int strategy, double reward_tolerance, int width,
                          int *R, double *rant, double *rconc, int verbose, int *episodes_run);
+
+/* ---- knowledge sharing between agents: the reference's experimental multi-agent mode (CMake option BUILD_OPENMP /
+ * BUILD_MPI, frirl_agent.c) on the device */
+/* merge_rb (frirl_agent.c:58-117): every rule of the sender list rant [Rs][K], rconc [Rs], in order, is folded into the rule base
+ * of one agent (agent < 0: of every agent): FIVE_vag_concl_weight + FIVE_vag_concl at the sender's antecedents, then either
+ * insertion / replacement at the snapped point (|difference| beyond the qdiff bounds) or the weighted assignment through the
+ * receiver's FIVERB.weights - which the reference leaves STALE after an exact hit; the engine keeps that array under
+ * FRIQ_RUN_KEEP_WEIGHTS.  The rule lists of agents on other GPUs travel by any transport (friq_dist.gather_rulebases: one
+ * all-gather) and are merged on every rank in the same order. */
+int friq_batch_merge_rb(friq_batch *b, long agent, int Rs, const double *rant, const double *rconc);
+/* frirl_omp_run (frirl_agent.c:294-385) for a batch of teams of `team` (>= 3) consecutive agents, all teams in parallel: chunks of
+ * 9 episodes per member (frirl_sequential_run.c:51-65), then leader -> members and members -> leader merges, until the team's
+ * leader (member 0) finds its rule base complete.  log (optional, max_log rows of 4 doubles): (agent, steps, return, rules) of
+ * every finished episode, agent by agent; *n_log = rows produced; *rounds_out = rounds run (<= max_rounds). */
+int friq_team_run(friq_batch *b, int team, int max_rounds, double *log, long max_log, long *n_log, int *rounds_out);
 
 /* ---- rule-base files, byte-compatible with frirl_utils.c:100-281 */
 int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double *rant, const double *rconc);

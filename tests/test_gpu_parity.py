@@ -301,6 +301,77 @@ def test_table_mode_equals_computed_chains(fq, name, monkeypatch):
         assert Ra == Rb and np.array_equal(ra, rb) and np.array_equal(qa, qb)
 
 
+@pytest.mark.parametrize("W", [3, 4])
+def test_team_run_reproduces_reference_openmp_build(fq, W):
+    """SURVEY 8f N3 on the GPU: knowledge sharing between agents (the reference's experimental frirl_omp_run + merge_rb,
+    frirl_agent.c, built here with BUILD_OPENMP and run with OMP_NUM_THREADS = W: tests/golden/mountaincar_omp<W>.*).  Three
+    teams of W agents side by side in one batch, every team must reproduce every agent's episode sequence (steps, return,
+    rules) and the leader's final rule base byte for byte - including merge_rb's use of STALE FIVERB.weights after exact
+    hits, which the fused kernel has to keep exactly as update_rules leaves them (FRIQ_RUN_KEEP_WEIGHTS)."""
+    import os
+    z = np.load(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.npz"))["episodes"]
+    want_txt = open(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.frirlrb.txt")).read()
+    P = fq.Problem("mountaincar")
+    teams = 3
+    b = fq.Batch(P, teams * W + 1, 256)                       # + 1: an incomplete trailing team is left alone
+    log, rounds = b.team_run(W)
+    assert rounds < 200
+    for t in range(teams):
+        for a in range(W):
+            want = z[z[:, 0] == a][:, 1:]; got = log[log[:, 0] == t * W + a][:, 1:]
+            assert np.array_equal(want, got), (t, a, len(want), len(got))
+        R, rant, rconc = b.get_rulebase(t * W)
+        txt = "".join("".join("%.18f " % v for v in rant[i]) + "%.18f \n" % rconc[i] for i in range(R))
+        assert txt == want_txt, t
+    assert len(log[log[:, 0] == teams * W]) == 0
+    b.close(); P.close()
+
+
+def test_merge_rb_per_call_matches_oracle(fq):
+    """merge_rb (frirl_agent.c:58-117) as a per-call entry point: agents that have learned with random exploration (their
+    FIVERB.weights kept by FRIQ_RUN_KEEP_WEIGHTS) receive a sender's rule list - the golden rule base with shifted
+    consequents, one antecedent moved OFF the grid (snapped before insertion, CHECK_STATES) - and must end with exactly the
+    oracle's rule bases; a second merge sees the weights the first one left behind."""
+    name = "mountaincar"
+    P = fq.Problem(name, no_random=0)
+    g = _golden.load(name)
+    rant, rconc = g["final"][1].copy(), g["final"][2].copy()
+    rng = np.random.default_rng(21)
+    rconc = rconc + rng.choice([0.0, 0.5, -3.0, 7.0, -40.0], len(rconc))
+    u = P.tables()["u"][0]
+    rant[11, 0] = u[17] + 0.25 * (u[18] - u[17])
+    n, first, steps = 40, 300, 600
+    alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.02, 0.1], n)
+    b = fq.Batch(P, n, 256, seed0=0x5EED0000, first_agent=first)
+    b.set_hyper(alpha, gamma, eps)
+    b.run(steps, fq.RUN_LEARN | fq.RUN_KEEP_WEIGHTS)
+    b.merge_rb(rant, rconc)
+    b.merge_rb(rant[::-1][:30], rconc[::-1][:30] * 0.5, agent=7)
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
+    for i in range(n):
+        a = _oracle.Agent(OP, 256, seed=0x5EED0000 + first + i)
+        a.set_hyper(alpha[i], gamma[i], eps[i])
+        a.run_steps(steps)
+        a.merge_rb(rant, rconc)
+        if i == 7:
+            a.merge_rb(rant[::-1][:30], rconc[::-1][:30] * 0.5)
+        R, brant, brconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(brant, orant) and np.array_equal(brconc, orconc), i
+    b.run(200, fq.RUN_LEARN | fq.RUN_KEEP_WEIGHTS)           # and learning goes on from the merged rule bases
+    for i in (0, 7, 39):
+        a = _oracle.Agent(OP, 256, seed=0x5EED0000 + first + i)
+        a.set_hyper(alpha[i], gamma[i], eps[i])
+        a.run_steps(steps); a.merge_rb(rant, rconc)
+        if i == 7:
+            a.merge_rb(rant[::-1][:30], rconc[::-1][:30] * 0.5)
+        a.run_steps(200)
+        R, brant, brconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(brant, orant) and np.array_equal(brconc, orconc), i
+    b.close(); P.close()
+
+
 def test_retiled_results_are_reported_in_agent_order(fq):
     """FRIQ_RUN_RETILE moves agents between warps (sorted by rule count); device-side gathers and the
     host-buffer end-to-end call must still report per-agent results in agent order."""
