@@ -40,6 +40,29 @@ def reduce_stats(dist, ret, rules, stats=None):
     return stats
 
 
+def gather_rulebases(dist, rant, rconc, cap):
+    """Knowledge sharing across ranks (the reference's MPI mode sends numofrules, rant and rconc point to point,
+    frirl_agent.c:427-461): every rank contributes ONE rule base - rant [R][K] float64, rconc [R] float64, R <= cap - and ONE
+    all-gather of a fixed-size record (R, antecedents, consequents padded to cap) gives every rank all of them.  Returns
+    [(rant_r, rconc_r) for r in range(world)]; each rank then folds them into its own agents in rank order with
+    friq_batch_merge_rb, so all ranks apply the same deterministic sequence."""
+    world = dist.get_world_size()
+    R, K = rant.shape
+    assert R <= cap and rconc.shape == (R,)
+    rec = torch.zeros(1 + cap * (K + 1), dtype=torch.float64, device=rant.device)
+    rec[0] = R
+    rec[1:1 + R * K] = rant.reshape(-1)
+    rec[1 + cap * K:1 + cap * K + R] = rconc
+    allrec = torch.empty(world * rec.numel(), dtype=torch.float64, device=rant.device)
+    dist.all_gather_into_tensor(allrec, rec)
+    out = []
+    for r in range(world):
+        v = allrec[r * rec.numel():(r + 1) * rec.numel()]
+        n = int(v[0].item())
+        out.append((v[1:1 + n * K].reshape(n, K).clone(), v[1 + cap * K:1 + cap * K + n].clone()))
+    return out
+
+
 class ResultExchange:
     """The path's ONE exchange per step, as ONE collective: per-agent (return f64, steps i32, rules i32) live in a single
     16 B/agent device buffer (three SoA segments; `ret`, `steps`, `rules` are views the engine writes into with
