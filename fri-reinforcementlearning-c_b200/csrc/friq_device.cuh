@@ -502,6 +502,13 @@ __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
 // ---- table mode: the per-agent list of rule cells (friq_devstate.rbc) is stored in blocks of FRIQ_CELL_VEC rules per lane,
 // [tile][slot / 8][lane][8] u16, so that a lane fetches the cells of 8 consecutive rules of a column with ONE 16-byte load;
 // the unused tail of the last block holds cell 0 (any valid column: those weights are loaded but never added).
+#ifndef FRIQ_TAB_PREFETCH
+#define FRIQ_TAB_PREFETCH 0     /* experiments: bit 0 prefetches the pair's table row, bit 1 the tile's consequent rows and cell blocks (both measured SLOWER: -3 .. -10 %) */
+#endif
+#ifndef FRIQ_TAB_PREFETCH_MAXCELLS
+#define FRIQ_TAB_PREFETCH_MAXCELLS 512
+#endif
+__device__ __forceinline__ void friq_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #ifndef FRIQ_CELL_VEC
 #define FRIQ_CELL_VEC 8         /* 8 (one 16-byte load per block) or 4 (8-byte loads, half the registers in flight) */
 #endif
@@ -511,7 +518,8 @@ __device__ __forceinline__ size_t friq_rbc_index(int i, int lane) { return ((siz
 typedef uint4 friq_cellvec;
 __device__ __forceinline__ friq_cellvec friq_cellvec_zero() { return make_uint4(0u, 0u, 0u, 0u); }
 __device__ __forceinline__ void friq_cellvec_unpack(const friq_cellvec c, unsigned (&cc)[8])
-{ cc[0] = c.x & 0xffffu; cc[1] = c.x >> 16; cc[2] = c.y & 0xffffu; cc[3] = c.y >> 16; cc[4] = c.z & 0xffffu; cc[5] = c.z >> 16; cc[6] = c.w & 0xffffu; cc[7] = c.w >> 16; }
+{ cc[0] = __byte_perm(c.x, 0, 0x4410); cc[1] = c.x >> 16; cc[2] = __byte_perm(c.y, 0, 0x4410); cc[3] = c.y >> 16;
+  cc[4] = __byte_perm(c.z, 0, 0x4410); cc[5] = c.z >> 16; cc[6] = __byte_perm(c.w, 0, 0x4410); cc[7] = c.w >> 16; }   // PRMT: no shift+mask pair folded into 64-bit address math
 #else
 typedef uint2 friq_cellvec;
 __device__ __forceinline__ friq_cellvec friq_cellvec_zero() { return make_uint2(0u, 0u); }
@@ -658,9 +666,27 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             const int ah = pb.act_hit[c < A ? c : 0];
             const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET);
             tab = has && pw != FRIQ_NO_TARGET;
+#if FRIQ_TAB_PREFETCH & 2
+            {   // the tile's rule data of this round (consequent rows, cell blocks) requested from L2 by all lanes at once
+                const int Rw = __reduce_max_sync(wmask, R);
+                const char *qb = reinterpret_cast<const char *>(tq), *cb = reinterpret_cast<const char *>(rbc);
+                for (int l = lane; l < 2 * Rw; l += 32) friq_prefetch_l1(qb + (size_t)l * 128);
+                for (int l = lane; l < ((Rw + FRIQ_CELL_VEC - 1) / FRIQ_CELL_VEC) * (FRIQ_CELL_VEC * 2 * FRIQ_TILE / 128); l += 32) friq_prefetch_l1(cb + (size_t)l * 128);
+            }
+#endif
             if (tab) {
                 const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wcells;
                 asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
+#if FRIQ_TAB_PREFETCH & 1
+                // the whole table row of the pair (1.8 KB for mountaincar) is requested up front: the loop's dependent lookups
+                // (cell -> weight) then find their lines in L1 instead of paying one L2 latency per block of 8 rules
+                if (pb.wcells <= FRIQ_TAB_PREFETCH_MAXCELLS) {
+                    const char *rb = reinterpret_cast<const char *>(rowd);
+                    const int bytes = pb.wcells * 8;
+#pragma unroll 1
+                    for (int o = 0; o < bytes; o += 128) friq_prefetch_l1(rb + o);
+                }
+#endif
                 friq_tab_sums(rowd, rbc, tq, tsw, j, Rj, isq, vag, ws);
             }
             const bool slow = has && !tab;

@@ -1254,6 +1254,16 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
     return 0;
 }
 
+// the table-mode kernel lives off L1 (rule rows, cell maps, table rows) and needs 10 KB of shared memory per CTA: ask for the
+// smallest shared-memory carve-out once per kernel (a hint; FRIQ_CARVEOUT_PCT < 0 leaves the driver's default)
+#ifndef FRIQ_CARVEOUT_PCT
+#define FRIQ_CARVEOUT_PCT (-1)   /* measured: 0 % starves the CTAs of shared memory (3.7e9), 25 % == default (5.0e9) */
+#endif
+#define FRIQ_CARVEOUT(kernel)                                                                                          \
+    do {                                                                                                              \
+        static bool done_ = false;                                                                                    \
+        if (!done_ && FRIQ_CARVEOUT_PCT >= 0) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FRIQ_CARVEOUT_PCT); done_ = true; } \
+    } while (0)
 int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, int variant, void *stream)
 {   // variant 0: one thread per agent, lock-step pass (+ hit sweep / cooperative sums when few pairs lack a hit);
     // 1: three warps per tile (k_run_steps_w3, A = 3 problems); 2: one thread per agent, hit sweep + cooperative sums only
@@ -1280,10 +1290,13 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     const int w3 = variant == 1;
     if (w3 && hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_W3(2, 3, FRIQ_ENV_MOUNTAINCAR);
     else if (w3 && hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_W3(4, 5, FRIQ_ENV_ACROBOT);
-    else if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR)
+    else if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR) {
+        FRIQ_CARVEOUT((k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2>));
         k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    else if (tab && hp->env == FRIQ_ENV_ACROBOT)
+    } else if (tab && hp->env == FRIQ_ENV_ACROBOT) {
+        FRIQ_CARVEOUT((k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2>));
         k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    }
     else if (coop && hp->env == FRIQ_ENV_MOUNTAINCAR)
         k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else if (coop && hp->env == FRIQ_ENV_ACROBOT)
