@@ -760,7 +760,7 @@ k_update_sarsa(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
     int qi[K];
 #pragma unroll
     for (int k = 0; k < K; k++) qi[k] = -1;
-    friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward[ag], qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
+    friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward[ag], qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag], st.wref ? st.wref + tile_off : nullptr);
     st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
 }
 
@@ -802,7 +802,7 @@ k_classic_step(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
         int qi[K];
 #pragma unroll
         for (int k = 0; k < K; k++) qi[k] = -1;
-        friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
+        friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag], st.wref ? st.wref + tile_off : nullptr);
         st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
     }
     o[0] = (double)a2; o[1] = (double)R; o[2] = (flags & FRIQ_F_INSERTED) ? 1.0 : 0.0; o[3] = (flags & FRIQ_F_OVERFLOW) ? 1.0 : 0.0;
@@ -869,7 +869,7 @@ k_classic_step_anyA(const friq_devprob *__restrict__ gprob, friq_devstate st, co
         int qi[K];
 #pragma unroll
         for (int k = 0; k < K; k++) qi[k] = -1;
-        friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag]);
+        friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, st.alpha[ag], st.gamma[ag], st.wref ? st.wref + tile_off : nullptr);
         st.R[ag] = R; st.flags[ag] = flags; st.hitq[ag] = -2;
     }
     o[0] = (double)a2; o[1] = (double)R; o[2] = (flags & FRIQ_F_INSERTED) ? 1.0 : 0.0; o[3] = (flags & FRIQ_F_OVERFLOW) ? 1.0 : 0.0;

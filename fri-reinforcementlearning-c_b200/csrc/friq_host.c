@@ -995,6 +995,15 @@ int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double 
     return 0;
 }
 
+/* From now on every entry point that runs update_rules for this batch (friq_batch_update_sarsa, friq_batch_classic_step, and
+ * friq_batch_run with FRIQ_RUN_KEEP_WEIGHTS) maintains FIVERB.weights the way the reference does (what merge_rb reads). */
+int friq_batch_keep_weights(friq_batch *b)
+{
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    return ensure_wref(b);
+}
+
 /* merge_rb (frirl_agent.c:58-117): the sender's rule list folded into one agent's rule base (agent < 0: into every agent's).
  * The receivers' FIVERB.weights are the ones kept by runs with FRIQ_RUN_KEEP_WEIGHTS (zero before any such run). */
 int friq_batch_merge_rb(friq_batch *b, long agent, int Rs, const double *rant, const double *rconc)

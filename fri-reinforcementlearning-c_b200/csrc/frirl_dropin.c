@@ -750,7 +750,74 @@ static void reduce_rule_base(struct frirl_desc *frirl)
     free(cand); free(cand_prev); free(removed);
 }
 
-void frirl_omp_run(struct frirl_desc *frirl) { (void)frirl; printf("Built without openmp support!\n"); }     /* frirl_agent.c:294-298 */
+/* Knowledge sharing between agents: frirl_omp_run (frirl_agent.c:294-385, the reference's experimental BUILD_OPENMP mode; its
+ * default build prints "Built without openmp support!").  World size = OMP_NUM_THREADS (as OpenMP would pick it), else the online
+ * CPUs.  Every agent is a full frirl_desc of its own (frirl_init on a copy: own tables, own one-agent device batch), started at
+ * gen_def_states' corner-rule states (:120-138); the agents learn their chunks one after the other (the reference's threads are
+ * independent between merges, so the order does not matter), merges run on the device (friq_batch_merge_rb). */
+static void merge_rule_base(struct frirl_desc *rcvr, int fromid, const struct FIVERB *sndr)              /* merge_rb, :58-117 */
+{
+    if (rcvr->verbose) printf("Synchronizing the rulebase from #%d to #%d\n", fromid, rcvr->agent_id);
+    dropin_engine *e = ENG(rcvr->fiverb);
+    sync_params(rcvr);
+    ENGINE(friq_batch_merge_rb(e->B, 0, sndr->numofrules, sndr->rant, sndr->rconc));
+    pull_rulebase(rcvr->fiverb);
+}
+void frirl_omp_run(struct frirl_desc *frirl)
+{
+    const char *nt = getenv("OMP_NUM_THREADS");
+    int world = nt ? atoi(nt) : (int)sysconf(_SC_NPROCESSORS_ONLN);
+    if (world < 1) world = 1;
+    if (world == 2) { printf("frirl_omp_run: FATAL ERROR: 2 agents divide by zero in gen_def_states (frirl_agent.c:132): use 1 or >= 3\n"); exit(1); }
+    frirl->agent_id = -1; frirl->agent_world_size = world;
+    const int S = frirl->statedims_len, K = frirl->numofantecedents;
+    struct frirl_desc *agent = (struct frirl_desc *)calloc(world, sizeof *agent);
+    for (int id = 0; id < world; id++) {                                                              /* omp_init, :145-263 */
+        printf("initializing thread %d\n", id);
+        struct frirl_desc *a = &agent[id];
+        memcpy(a, frirl, sizeof *a);
+        a->agent_id = id; a->agent_world_size = world; a->rbfile = NULL;
+        a->statedims = (struct frirl_dimension_desc *)malloc(sizeof(struct frirl_dimension_desc) * S);
+        memcpy(a->statedims, frirl->statedims, sizeof(struct frirl_dimension_desc) * S);
+        if (id != 0 && world >= 2) {                                                                  /* gen_def_states */
+            const struct FIVERB *mf = frirl->fiverb;
+            const int gap = mf->numofrules / (world - 2);
+            for (int i = 0; i < S; i++) {
+                const size_t at = (size_t)(id - 1) * gap * K + i;                                     /* past the corner rules: the buffer's zeros */
+                a->statedims[i].values_def = at < (size_t)mf->maxnumofrules * K ? mf->rant[at] : 0.0;
+            }
+        }
+        for (int i = 0; i < S; i++) printf("#%d sdim%d def:%f\n", id, i, a->statedims[i].values_def);
+        if (frirl_init(a) != 0) { printf("frirl_omp_run: FATAL ERROR: agent %d could not be initialised\n", id); exit(1); }
+        a->agent_id = id; a->agent_world_size = world; a->is_running = 1; a->reduction_state = 0;
+        a->episode_num = frirl->episode_num;
+        ENGINE(friq_batch_keep_weights(ENG(a->fiverb)->B));
+    }
+    for (;;) {
+        for (int id = 0; id < world; id++) frirl_sequential_run(&agent[id]);
+        if (agent[0].is_running == 0) break;
+        if (agent[0].epended == 0) {
+            for (int id = 1; id < world; id++) merge_rule_base(&agent[id], 0, agent[0].fiverb);
+        } else printf("#0 pended, skipping sync to master\n");
+        for (int id = 1; id < world; id++) {
+            if (agent[id].epended == 0) merge_rule_base(&agent[0], id, agent[id].fiverb);
+            else printf("#%d pended, skipping sync\n", id);
+        }
+    }
+    printf("moving rb from thread #0 to main process\n");
+    {   /* :370-378: the main process's rule base becomes agent 0's */
+        struct FIVERB *frb = frirl->fiverb, *src = agent[0].fiverb;
+        while (frb->numofrules > 0) five_remove_rule(frb, frb->numofrules - 1);
+        for (int i = 0; i < src->numofrules; i++) FIVE_add_rule(frb, src->rant + (size_t)i * K, src->rconc[i]);
+    }
+    for (int id = 0; id < world; id++) {
+        printf("deinitializing thread %d\n", id);
+        struct frirl_dimension_desc *sd = agent[id].statedims;
+        frirl_deinit(&agent[id]);
+        free(sd);
+    }
+    free(agent);
+}
 void frirl_mpi_run(struct frirl_desc *frirl) { (void)frirl; printf("Built without MPI support!\n"); }        /* frirl_agent.c:387-391 */
 
 void frirl_test_run(struct frirl_desc *frirl)                                    /* frirl_test_run.c:20-86 */

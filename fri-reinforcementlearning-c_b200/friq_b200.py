@@ -72,6 +72,7 @@ SYMBOLS = {
     "friq_batch_bestact_from_dists": (C.c_int, [C.c_void_p, dp, dp]),
     "friq_batch_append_rule": (C.c_int, [C.c_void_p, C.c_long, dp, C.c_double]),
     "friq_batch_remove_rule": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
+    "friq_batch_keep_weights": (C.c_int, [C.c_void_p]),
     "friq_batch_merge_rb": (C.c_int, [C.c_void_p, C.c_long, C.c_int, dp, dp]),
     "friq_team_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, dp, C.c_long, C.POINTER(C.c_long), ip]),
     "friq_batch_save_rb_files": (C.c_int, [C.c_void_p, C.c_long, C.c_long, C.c_char_p, C.c_int]),

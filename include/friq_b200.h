@@ -164,6 +164,9 @@ int friq_reduce_rulebase(friq_problem *p, int device, int strategy, double rewar
  * FRIQ_RUN_KEEP_WEIGHTS.  The rule lists of agents on other GPUs travel by any transport (friq_dist.gather_rulebases: one
  * all-gather) and are merged on every rank in the same order. */
 int friq_batch_merge_rb(friq_batch *b, long agent, int Rs, const double *rant, const double *rconc);
+/* allocate FIVERB.weights for the batch: the per-call update entry points (friq_batch_update_sarsa, friq_batch_classic_step) then
+ * keep it like the reference's update_rules does; friq_batch_run keeps it under FRIQ_RUN_KEEP_WEIGHTS */
+int friq_batch_keep_weights(friq_batch *b);
 /* frirl_omp_run (frirl_agent.c:294-385) for a batch of teams of `team` (>= 3) consecutive agents, all teams in parallel: chunks of
  * 9 episodes per member (frirl_sequential_run.c:51-65), then leader -> members and members -> leader merges, until the team's
  * leader (member 0) finds its rule base complete.  log (optional, max_log rows of 4 doubles): (agent, steps, return, rules) of

@@ -52,6 +52,28 @@ def test_shipped_mountaincar_rule_base_reduction(tmp_path):
     assert keep == open(os.path.join(_golden.GOLDEN, "mountaincar_reduction.log")).read().splitlines()
 
 
+@pytest.mark.parametrize("W", [3, 4])
+def test_reference_example_driver_in_omp_mode_reproduces_reference_openmp_build(W, tmp_path):
+    """`mountaincar -m omp` (frirl_run -> frirl_omp_run, frirl_agent.c:294-385): the reference needs its experimental CMake option
+    BUILD_OPENMP for this; oracle/Makefile built it that way and oracle/make_golden.py recorded runs with OMP_NUM_THREADS = 3 and
+    4.  The UNMODIFIED example driver on the drop-in API must print the same per-agent episode sequences and write the same
+    final rule base, byte for byte."""
+    import re
+    r = subprocess.run([_exe("dropin_mountaincar_crtrig"), "-m", "omp"], cwd=tmp_path, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, DROPIN_CONSTRUCT="1", OMP_NUM_THREADS=str(W)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    eps = {}
+    for l in r.stdout.splitlines():
+        m = re.match(r"#(\d+) Episode: (\d+)\tSteps: (\d+)\tReward: (?:\x1b\[[0-9;]*m)?(-?[0-9.]+)(?:\x1b\[[0-9;]*m)?\tRules: (\d+)", l)
+        if m:
+            eps.setdefault(int(m.group(1)), []).append((int(m.group(3)), float(m.group(4)), int(m.group(5))))
+    z = np.load(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.npz"))["episodes"]
+    for a in range(W):
+        want = [tuple(x) for x in z[z[:, 0] == a][:, 1:].tolist()]
+        assert [tuple(map(float, e)) for e in eps.get(a, [])] == want, a
+    assert open(tmp_path / "mountaincar.frirlrb.txt", "rb").read() == open(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.frirlrb.txt"), "rb").read()
+
+
 def test_test_mode_runs_one_greedy_episode(tmp_path):
     """-m test (frirl_test_run.c:20-86): one greedy episode without rule-base updates, exit code 0 on success."""
     rb = os.path.join(_golden.GOLDEN, "acrobot.frirlrb.bin")
