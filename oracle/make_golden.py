@@ -63,8 +63,8 @@ def main():
     # the reference's experimental knowledge-sharing mode (BUILD_OPENMP: frirl_omp_run + merge_rb, frirl_agent.c), mountaincar,
     # 3 and 4 agents: per-agent episode sequences (steps, return, rules) + agent 0's final rule base  
     import re
-    exe = os.path.join(HERE, "_ref", "ref_mountaincar_omp_crtrig")
-    for W in (3, 4):
+    for env, W in (("mountaincar", 3), ("mountaincar", 4), ("acrobot", 3), ("cartpole", 3)):
+        exe = os.path.join(HERE, "_ref", f"ref_{env}_omp_crtrig")
         with tempfile.TemporaryDirectory() as tmp:
             runs = []
             for _ in range(2):                       # thread scheduling must not matter: two runs, identical results
@@ -74,14 +74,14 @@ def main():
                     m = re.match(r"#(\d+) Episode: (\d+)\tSteps: (\d+)\tReward: (?:\x1b\[[0-9;]*m)?(-?[0-9.]+)(?:\x1b\[[0-9;]*m)?\tRules: (\d+)", l)
                     if m:
                         eps.setdefault(int(m.group(1)), []).append((int(m.group(3)), float(m.group(4)), int(m.group(5))))
-                runs.append((eps, open(os.path.join(tmp, "mountaincar.frirlrb.txt"), "rb").read()))
+                runs.append((eps, open(os.path.join(tmp, f"{env}.frirlrb.txt"), "rb").read()))
             if runs[0] != runs[1]:
-                sys.exit(f"omp W={W}: the reference run is not deterministic")
+                sys.exit(f"{env} omp W={W}: the reference run is not deterministic")
             eps, txt = runs[0]
             rows = np.array([(a, s_, r_, n_) for a in sorted(eps) for (s_, r_, n_) in eps[a]], dtype=np.float64)
-            np.savez_compressed(os.path.join(out, f"mountaincar_omp{W}.npz"), episodes=rows)
-            open(os.path.join(out, f"mountaincar_omp{W}.frirlrb.txt"), "wb").write(txt)
-            print(f"knowledge sharing, {W} agents: {len(rows)} episodes, agent 0 ends with {len(txt.splitlines())} rules")
+            np.savez_compressed(os.path.join(out, f"{env}_omp{W}.npz"), episodes=rows)
+            open(os.path.join(out, f"{env}_omp{W}.frirlrb.txt"), "wb").write(txt)
+            print(f"knowledge sharing, {env}, {W} agents: {len(rows)} episodes, agent 0 ends with {len(txt.splitlines())} rules")
     # a problem that is none of the examples (3 state dimensions, 5 actions, skip_rules = 0): tests/dropin/custom_problem.c, our own
     # program on the reference's public API, built against the reference by oracle/Makefile
     exe = os.path.join(HERE, "_ref", "custom_ref")

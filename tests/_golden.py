@@ -86,3 +86,10 @@ def rb_text(rant, rconc):
 
 def golden_text(env):
     return open(os.path.join(GOLDEN, f"{env}.frirlrb.txt"), "rb").read()
+
+
+def same_episode_rows(want, got):
+    """rows (steps, return, rules): the golden returns were parsed from the reference's "%f" printout (6 decimals)"""
+    if len(want) != len(got):
+        return False
+    return all(int(w[0]) == int(g[0]) and ("%f" % w[1]) == ("%f" % g[1]) and int(w[2]) == int(g[2]) for w, g in zip(want, got))

@@ -301,25 +301,25 @@ def test_table_mode_equals_computed_chains(fq, name, monkeypatch):
         assert Ra == Rb and np.array_equal(ra, rb) and np.array_equal(qa, qb)
 
 
-@pytest.mark.parametrize("W", [3, 4])
-def test_team_run_reproduces_reference_openmp_build(fq, W):
+@pytest.mark.parametrize("name,W", [("mountaincar", 3), ("mountaincar", 4), ("acrobot", 3), ("cartpole", 3)])
+def test_team_run_reproduces_reference_openmp_build(fq, name, W):
     """SURVEY 8f N3 on the GPU: knowledge sharing between agents (the reference's experimental frirl_omp_run + merge_rb,
-    frirl_agent.c, built here with BUILD_OPENMP and run with OMP_NUM_THREADS = W: tests/golden/mountaincar_omp<W>.*).  Three
+    frirl_agent.c, built here with BUILD_OPENMP and run with OMP_NUM_THREADS = W: tests/golden/<env>_omp<W>.*).  Three
     teams of W agents side by side in one batch, every team must reproduce every agent's episode sequence (steps, return,
     rules) and the leader's final rule base byte for byte - including merge_rb's use of STALE FIVERB.weights after exact
     hits, which the fused kernel has to keep exactly as update_rules leaves them (FRIQ_RUN_KEEP_WEIGHTS)."""
     import os
-    z = np.load(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.npz"))["episodes"]
-    want_txt = open(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.frirlrb.txt")).read()
-    P = fq.Problem("mountaincar")
+    z = np.load(os.path.join(_golden.GOLDEN, f"{name}_omp{W}.npz"))["episodes"]
+    want_txt = open(os.path.join(_golden.GOLDEN, f"{name}_omp{W}.frirlrb.txt")).read()
+    P = fq.Problem(name)
     teams = 3
-    b = fq.Batch(P, teams * W + 1, 256)                       # + 1: an incomplete trailing team is left alone
+    b = fq.Batch(P, teams * W + 1, {"mountaincar": 256, "acrobot": 768, "cartpole": 512}[name])   # + 1: an incomplete trailing team is left alone
     log, rounds = b.team_run(W)
     assert rounds < 200
     for t in range(teams):
         for a in range(W):
             want = z[z[:, 0] == a][:, 1:]; got = log[log[:, 0] == t * W + a][:, 1:]
-            assert np.array_equal(want, got), (t, a, len(want), len(got))
+            assert _golden.same_episode_rows(want, got), (t, a, len(want), len(got))
         R, rant, rconc = b.get_rulebase(t * W)
         txt = "".join("".join("%.18f " % v for v in rant[i]) + "%.18f \n" % rconc[i] for i in range(R))
         assert txt == want_txt, t

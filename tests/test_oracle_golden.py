@@ -127,19 +127,19 @@ def test_pow_x87_against_exact_integer_model():
             assert L.fo_pow_x87(float(d), p) == float(rne(acc, 53))
 
 
-@pytest.mark.parametrize("W", [3, 4])
-def test_knowledge_sharing_run_reproduces_reference_openmp_build(W):
+@pytest.mark.parametrize("env,W", [("mountaincar", 3), ("mountaincar", 4), ("acrobot", 3), ("cartpole", 3)])
+def test_knowledge_sharing_run_reproduces_reference_openmp_build(env, W):
     """the reference's experimental multi-agent mode (frirl_omp_run + merge_rb, frirl_agent.c; CMake option
     BUILD_OPENMP) was compiled and run here with OMP_NUM_THREADS = W (oracle/Makefile, oracle/make_golden.py).  The port must
     reproduce every agent's episode sequence (steps, return, rules) and agent 0's final rule base - which pins merge_rb
     including its use of STALE FIVERB.weights after exact hits."""
-    z = np.load(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.npz"))["episodes"]
-    P = _oracle.Problem(0, trig=1)
+    z = np.load(os.path.join(_golden.GOLDEN, f"{env}_omp{W}.npz"))["episodes"]
+    P = _oracle.Problem(_golden.ENV_ID[env], trig=1)
     agents = [_oracle.Agent(P, 4096) for _ in range(W)]
     log = _oracle.team_run(agents)
     for a in range(W):
         want = z[z[:, 0] == a][:, 1:]; got = log[log[:, 0] == a][:, 1:]
-        assert np.array_equal(want, got), (a, len(want), len(got))
+        assert _golden.same_episode_rows(want, got), (a, len(want), len(got))
     R, rant, rconc = agents[0].rb()
     txt = "".join("".join("%.18f " % v for v in rant[i]) + "%.18f \n" % rconc[i] for i in range(R))
-    assert txt == open(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.frirlrb.txt")).read()
+    assert txt == open(os.path.join(_golden.GOLDEN, f"{env}_omp{W}.frirlrb.txt")).read()
