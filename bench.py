@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.join(REPO, "fri-reinforcementlearning-c_b200"))
 
 METRIC = "agent_env_steps_per_sec"
 UNIT = "env-steps/s"
-WORKLOAD = "mountaincar FRIQ-learning, 65536 agents/GPU, eps-greedy 0.01 (Philox), learning from corner rule base"
+WORKLOAD = "mountaincar FRIQ-learning, %d agents/GPU, eps-greedy 0.01 (Philox), learning from corner rule base"
 # algorithmic work of one learning env step of mountaincar (S=2, K=p=3, A=3) with R rules
 F_ALG_PER_RULE = 82.0          # FP64 ops (sub/mul/add/cmp/sqrt/div = 1 each), reference's op count
 BYTES_ALG_PER_RULE = 19.0      # index-form rule base streamed once per step (K*1 + 8 read, 8 write back)
@@ -139,7 +139,7 @@ def main():
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "agents_per_gpu": args.agents, "env_steps_per_agent_per_step": args.chunk,
+            "config": {"workload": WORKLOAD % args.agents, "agents_per_gpu": args.agents, "env_steps_per_agent_per_step": args.chunk,
                        "reference_arm": "the unmodified reference (oracle/_ref, C + AVX2 inline asm, -O2 -mavx2) on all host cores: one process per "
                                         "core stepping independent single agents through frirl_episode(); a bounded sample of the workload "
                                         "(no_random = 1: the reference's libc rand() stream is unseedable)",
@@ -248,6 +248,20 @@ def main():
         traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))["k_run_steps"]["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
+    # what the dominant kernel EXECUTES (ncu --set full capture committed under profiles/), beside the nominal roofline fraction
+    executed = None
+    try:
+        import glob
+        mf = sorted(glob.glob(os.path.join(REPO, "profiles", "r1*_k_run_steps_metrics.json")))[-1]
+        ms_ = json.load(open(mf))
+        avg = lambda k: sum(float(m[k][0]) for m in ms_) / len(ms_)
+        executed = {"fp64_pipe_pct_of_active_cycles": avg("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "issue_slots_busy": avg("smsp__issue_active.avg.per_cycle_active"),
+                    "resident_warps_per_scheduler": avg("smsp__warps_active.avg.per_cycle_active"),
+                    "registers_per_thread": int(float(ms_[0]["launch__registers_per_thread"][0])),
+                    "source": os.path.relpath(mf, REPO) + " (ncu --set full, %d launches of the timed region)" % len(ms_)}
+    except (OSError, KeyError, ValueError, IndexError):
+        pass
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -257,7 +271,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "agents_per_gpu": n, "env_steps_per_agent_per_step": args.chunk,
+        "config": {"workload": WORKLOAD % args.agents, "agents_per_gpu": n, "env_steps_per_agent_per_step": args.chunk,
                    "rule_capacity": 192, "retile_interval_steps": args.retile, "mean_rules_in_timed_region": sumR / max(nsteps, 1),
                    "l2": "inputs larger than L2: rule bases + scratch = %.0f MB per GPU" % (n * 192 * 20 / 1e6),
                    "rng": "Philox4x32-10, key = 0x5EED0000 + agent id"},
@@ -272,12 +286,13 @@ def main():
                      "achieved": ach_tflops if frac_fp64 >= frac_hbm else ach_gbs,
                      "peak": fp64_peak_g / 1e3 if frac_fp64 >= frac_hbm else hbm_peak,
                      "unit": "TFLOP/s" if frac_fp64 >= frac_hbm else "GB/s",
-                     "frac": max(frac_fp64, frac_hbm), "traffic": traffic,
-                     "kernel": "k_run_steps<2,3,3,3,mountaincar>",
+                     "frac": max(frac_fp64, frac_hbm), "traffic": traffic, "executed": executed,
+                     "kernel": "k_run_steps<2,3,3,3,mountaincar> (table mode)",
                      "note": "algorithmic FP64 ops of the reference path (SURVEY 8d: 82*R per env step, sqrt and / counted as 1) over the "
                              "measured non-FMA FP64 issue rate of this GPU (friq_device_fp64_peak, DADD/DMUL lane-ops/s); the kernel "
                              "EXECUTES far fewer: exact hits short-cut the sums (as in the reference) and the Shepard weights are "
-                             "looked up in a memoised table, so this is nominal work per second, not pipe utilisation (ncu: profiles/); "
+                             "looked up in a memoised table, so this is nominal work per second - it can exceed 1 - not pipe utilisation: see "
+                             "`executed` (ncu: profiles/); "
                              "hbm view: %.1f GB/s algorithmic of %.0f GB/s measured = %.3f; achieved is over the whole timed step "
                              "(re-tiling + result gather included, k_run_steps is > 97 %% of it: profiles/)" % (ach_gbs, hbm_peak, frac_hbm)},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": frac_hbm, "traffic": traffic},
