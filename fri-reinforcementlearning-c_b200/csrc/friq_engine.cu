@@ -4,11 +4,19 @@
 //   k_run_steps      the fused persistent step kernel: for every agent, n env steps of
 //                    frirl_episode.c:86-186 (dynamics, reward, quantiser, best action over all
 //                    actions, epsilon-greedy, SARSA update / rule insertion), agent state in
-//                    registers, problem block staged to shared memory by TMA.
-//   k_vag_concl / k_best_action / k_update_sarsa
+//                    registers, problem block staged to shared memory by TMA.  COOP = 2 is its
+//                    TABLE MODE (mountaincar, acrobot): exact hits through a per-agent cell-to-rule
+//                    map, Shepard weights looked up in the problem's memoised table.
+//   k_build_wtab / k_refresh_index
+//                    the table (once per problem) and the per-agent indexes (before every launch).
+//   k_vag_concl / k_best_action / k_update_sarsa / k_classic_step / k_rule_distance / k_bestact_dists
 //                    one call of FIVE_vag_concl(_weight) / frirl_get_best_action /
-//                    frirl_update_sarsa per agent: the per-call boundary of the reference API
+//                    frirl_update_sarsa ... per agent: the per-call boundary of the reference API
 //                    (and the per-call parity tests); same device functions as the fused kernel.
+//   k_infer_shared   inference against ONE shared rule base streamed through shared memory by TMA.
+//   k_merge_list / k_team_merge / k_team_ctl
+//                    knowledge sharing: merge_rb and the team bookkeeping of frirl_omp_run (frirl_agent.c).
+//   k_retile_*       re-assignment of agents to warps by rule count (placement only).
 //   k_init_agents    corner-rule bases + episode bookkeeping (frirl_init_rb.c, frirl_init.c).
 // The extern "C" friqd_* functions are the thin C-ABI the ANSI-C host layer calls.
 #include <cuda_runtime.h>
