@@ -1390,8 +1390,8 @@ int friq_batch_save_checkpoint(friq_batch *b, const char *file_name)
     const int K = b->P->hp.K, cap = b->st.cap; const long n = b->st.n, chunk = 1024;
     FILE *f = fopen(file_name, "wb");
     if (!f) { perror("friq_batch_save_checkpoint: open()"); FAIL(-1, "cannot open %s", file_name); }
-    const long long n64 = n; const int32_t k32 = K, zero = 0;
-    fwrite("FRIQCKP1", 1, 8, f); fwrite(&n64, 8, 1, f); fwrite(&k32, 4, 1, f); fwrite(&zero, 4, 1, f);
+    const long long n64 = n; const int32_t k32 = K, flags32 = b->st.wref ? 1 : 0;   /* bit 0: a FIVERB.weights section follows the records */
+    fwrite("FRIQCKP1", 1, 8, f); fwrite(&n64, 8, 1, f); fwrite(&k32, 4, 1, f); fwrite(&flags32, 4, 1, f);
     int *R = (int *)malloc(sizeof(int) * chunk), *ins = (int *)malloc(sizeof(int) * n);
     double *rant = (double *)malloc(sizeof(double) * (size_t)chunk * cap * K), *rconc = (double *)malloc(sizeof(double) * (size_t)chunk * cap);
     int rc = friq_batch_get_inserted(b, ins);
@@ -1403,6 +1403,18 @@ int friq_batch_save_checkpoint(friq_batch *b, const char *file_name)
             fwrite(&r32, 4, 1, f); fwrite(&i32, 4, 1, f);
             for (int r = 0; r < R[i]; r++) { fwrite(rant + ((size_t)i * cap + r) * K, 8, K, f); fwrite(rconc + (size_t)i * cap + r, 8, 1, f); }
         }
+    }
+    if (!rc && b->st.wref) {          /* knowledge sharing: the persistent FIVERB.weights of every agent (cap doubles each), tile by tile */
+        const size_t tile_slots = (size_t)cap * FRIQ_TILE;
+        double *t = (double *)malloc(tile_slots * 8), *o = (double *)malloc(sizeof(double) * cap);
+        for (long tl = 0; tl * FRIQ_TILE < n && !rc; tl++) {
+            rc = friqd_d2h(t, b->st.wref + (size_t)tl * tile_slots, tile_slots * 8);
+            for (int l = 0; l < FRIQ_TILE && tl * FRIQ_TILE + l < n && !rc; l++) {
+                for (int i = 0; i < cap; i++) o[i] = t[(size_t)i * FRIQ_TILE + l];
+                fwrite(o, 8, cap, f);
+            }
+        }
+        free(t); free(o);
     }
     free(R); free(ins); free(rant); free(rconc);
     if (fclose(f) != 0 && !rc) FAIL(-1, "%s: write failed", file_name);
@@ -1431,6 +1443,19 @@ int friq_batch_load_checkpoint(friq_batch *b, const char *file_name)
         ins[a] = i32;
     }
     if (!rc) rc = friq_batch_set_inserted(b, ins);
+    if (!rc && (res & 1)) {           /* FIVERB.weights section */
+        rc = friq_batch_keep_weights(b);
+        const size_t tile_slots = (size_t)cap * FRIQ_TILE;
+        double *t = (double *)calloc(tile_slots, 8), *o = (double *)malloc(sizeof(double) * cap);
+        for (long tl = 0; tl * FRIQ_TILE < n && !rc; tl++) {
+            for (int l = 0; l < FRIQ_TILE && tl * FRIQ_TILE + l < n && !rc; l++) {
+                if (fread(o, 8, cap, f) != (size_t)cap) { snprintf(g_err, sizeof g_err, "%s: truncated weights section (checkpoint written with another rule capacity?)", file_name); rc = -1; break; }
+                for (int i = 0; i < cap; i++) t[(size_t)i * FRIQ_TILE + l] = o[i];
+            }
+            if (!rc) rc = friqd_h2d(b->st.wref + (size_t)tl * tile_slots, t, tile_slots * 8);
+        }
+        free(t); free(o);
+    }
     fclose(f); free(rant); free(rconc); free(ins);
     return rc;
 }

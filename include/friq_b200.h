@@ -183,7 +183,9 @@ int friq_load_rb_from_bin_file(const char *file_name, int K, int max_rules, int 
 int friq_batch_save_rb_files(friq_batch *b, long first, long count, const char *pattern, int text);
 /* warm start (`-f file`, frirl_app_helpers.c:53-62) of one agent, or of all agents when agent < 0 */
 int friq_batch_load_rb_file(friq_batch *b, long agent, const char *file_name);
-/* all rule bases + fus_is_rule_inserted flags of a batch in ONE file (per-agent records in the reference's binary layout) */
+/* all rule bases + fus_is_rule_inserted flags of a batch in ONE file (per-agent records in the reference's binary layout), and -
+ * when the batch keeps them (FRIQ_RUN_KEEP_WEIGHTS / friq_batch_keep_weights) - every agent's FIVERB.weights, so that a resumed
+ * knowledge-sharing run merges exactly like an uninterrupted one */
 int friq_batch_save_checkpoint(friq_batch *b, const char *file_name);
 int friq_batch_load_checkpoint(friq_batch *b, const char *file_name);
 

@@ -327,7 +327,7 @@ def test_team_run_reproduces_reference_openmp_build(fq, name, W):
     b.close(); P.close()
 
 
-def test_merge_rb_per_call_matches_oracle(fq):
+def test_merge_rb_per_call_matches_oracle(fq, tmp_path):
     """merge_rb (frirl_agent.c:58-117) as a per-call entry point: agents that have learned with random exploration (their
     FIVERB.weights kept by FRIQ_RUN_KEEP_WEIGHTS) receive a sender's rule list - the golden rule base with shifted
     consequents, one antecedent moved OFF the grid (snapped before insertion, CHECK_STATES) - and must end with exactly the
@@ -345,8 +345,19 @@ def test_merge_rb_per_call_matches_oracle(fq):
     b = fq.Batch(P, n, 256, seed0=0x5EED0000, first_agent=first)
     b.set_hyper(alpha, gamma, eps)
     b.run(steps, fq.RUN_LEARN | fq.RUN_KEEP_WEIGHTS)
+    ck = str(tmp_path / "team.ckp")
+    b.save_checkpoint(ck)                                    # rule bases + inserted flags + FIVERB.weights
     b.merge_rb(rant, rconc)
     b.merge_rb(rant[::-1][:30], rconc[::-1][:30] * 0.5, agent=7)
+    b2 = fq.Batch(P, n, 256, seed0=1, first_agent=0)         # a resumed batch must merge to the same rule bases
+    b2.load_checkpoint(ck)
+    b2.merge_rb(rant, rconc)
+    for i in (0, 7, 22, 39):
+        Ra, ra, qa = b.get_rulebase(i) if i != 7 else (None, None, None)
+        Rb, rb_, qb = b2.get_rulebase(i)
+        if i != 7:
+            assert Ra == Rb and np.array_equal(ra, rb_) and np.array_equal(qa, qb), i
+    b2.close()
     OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
     for i in range(n):
         a = _oracle.Agent(OP, 256, seed=0x5EED0000 + first + i)
