@@ -134,7 +134,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = run_reference(steps_per_agent)
+        cb = run_reference(steps_per_agent, float(os.environ.get("FRIQ_BENCH_REF_SECONDS", 15.0)))
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
