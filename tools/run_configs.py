@@ -56,7 +56,7 @@ def c4(n, R, steps):
     s0 = np.zeros((n, P.S)); s0[:, :2] = np.random.default_rng(4242).uniform(-np.pi / 2, np.pi / 2, size=(n, 2))
     b.set_initial_state(s0)
     sptr = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    b.run(20, 0, stream=sptr, sync=False)
+    b.run(int(os.environ.get("C4_WARM_STEPS", 20)), 0, stream=sptr, sync=False)      # (a short first launch is what tools capture under ncu)
     t = timed(lambda: b.run(steps, 0, stream=sptr, sync=False), 1)
     out = dict(config="C4 acrobot, shared rule base, inference", agents=n, rules=R, env_steps_per_s=n * steps / t,
                five_evals_per_s=n * steps * P.A / t, rule_evals_per_s=n * steps * P.A * R / t, seconds=t)
@@ -85,7 +85,11 @@ def c5(n, chunk, reps):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["C3a", "C3c", "C4", "C5"]
-    if "C3a" in which: print(json.dumps(learning("acrobot", 65536, 704, 100, 5, 5, 0.001)), flush=True)
-    if "C3c" in which: print(json.dumps(learning("cartpole", 16384, 2304, 50, 5, 5, 0.001)), flush=True)
-    if "C4" in which: print(json.dumps(c4(262144 // int(os.environ.get("C4_GPUS", 2)), 10240, 200)), flush=True)
+    if "C3a" in which:
+        for n_ac in [int(x) for x in os.environ.get("C3A_AGENTS", "65536").split(",")]:
+            print(json.dumps(learning("acrobot", n_ac, 704, 100, 5, 5, 0.001)), flush=True)
+    if "C3c" in which:
+        for n_cp in [int(x) for x in os.environ.get("C3C_AGENTS", "65536").split(",")]:    # 16,384 agents are only 128 CTAs: 20 of the 148 SMs idle
+            print(json.dumps(learning("cartpole", n_cp, 2304, 50, 5, 5, 0.001)), flush=True)
+    if "C4" in which: print(json.dumps(c4(int(os.environ.get("C4_AGENTS", 262144 // int(os.environ.get("C4_GPUS", 2)))), 10240, int(os.environ.get("C4_STEPS", 200)))), flush=True)
     if "C5" in which: print(json.dumps(c5(131072, 250, 6)), flush=True)
