@@ -834,6 +834,9 @@ __device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, do
 //                 FIVE_vag_concl_weight, FIVEVagConclWeight.c:125-175, same point, same RB)
 //   qs[] / vo_q[] the antecedents (s,a) and their VE values.
 // ---------------------------------------------------------------------------------------
+#ifndef FRIQ_WUPD_VEC
+#define FRIQ_WUPD_VEC 4         /* rules per trip of the weighted-update loop (loads in flight per L2 round trip) */
+#endif
 template <int S, int P, bool COLD = false>
 __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
                                                  const double *qs, const int *qi, double reward, double qp, int hitq, double qnow, double ws,
@@ -876,15 +879,17 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
     }
     if (pb.skip_rules == 0) { rules = R; flags &= ~FRIQ_F_INSERTED; }
     // cheap superset of (wi/ws > wsig): only the few rules that pass it pay the division; four rules per trip, one branch
+    // (the weights were stored by ANOTHER lane a moment ago and global stores do not stay in L1: every trip is one L2 round trip -
+    // FRIQ_WUPD_VEC rules share it.  ncu, acrobot: this loop holds 24 % of the kernel's samples at 4; 8 and 16 are next round's experiment)
     const double pre = (pb.wsig >= 0.05) ? __dmul_rn(0.04, ws) : -1.0;
 #pragma unroll 1
-    for (int i = 0; i < rules; i += 4) {
-        double wi[4]; bool any = false;
+    for (int i = 0; i < rules; i += FRIQ_WUPD_VEC) {
+        double wi[FRIQ_WUPD_VEC]; bool any = false;
 #pragma unroll
-        for (int u = 0; u < 4; u++) { wi[u] = (i + u < rules) ? sw[(size_t)(i + u) * FRIQ_TILE] : -2.0; any = any || (wi[u] > pre); }
+        for (int u = 0; u < FRIQ_WUPD_VEC; u++) { wi[u] = (i + u < rules) ? sw[(size_t)(i + u) * FRIQ_TILE] : -2.0; any = any || (wi[u] > pre); }
         if (!any) continue;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < FRIQ_WUPD_VEC; u++) {
             if (wi[u] > pre) {
                 const double wgt = __ddiv_rn(wi[u], ws);                                                         // A6
                 if (wgt > pb.wsig) rbq[(size_t)(i + u) * FRIQ_TILE] = __dadd_rn(qnow, __dmul_rn(qdiff, wgt));    // A7
