@@ -835,7 +835,7 @@ __device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, do
 //   qs[] / vo_q[] the antecedents (s,a) and their VE values.
 // ---------------------------------------------------------------------------------------
 #ifndef FRIQ_WUPD_VEC
-#define FRIQ_WUPD_VEC 4         /* rules per trip of the weighted-update loop (loads in flight per L2 round trip) */
+#define FRIQ_WUPD_VEC 4         /* rules per trip of the weighted-update loop (loads in flight per L2 round trip; 8 and 16 measured no better) */
 #endif
 template <int S, int P, bool COLD = false>
 __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
@@ -880,7 +880,7 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
     if (pb.skip_rules == 0) { rules = R; flags &= ~FRIQ_F_INSERTED; }
     // cheap superset of (wi/ws > wsig): only the few rules that pass it pay the division; four rules per trip, one branch
     // (the weights were stored by ANOTHER lane a moment ago and global stores do not stay in L1: every trip is one L2 round trip -
-    // FRIQ_WUPD_VEC rules share it.  ncu, acrobot: this loop holds 24 % of the kernel's samples at 4; 8 and 16 are next round's experiment)
+    // FRIQ_WUPD_VEC rules share it.  ncu, acrobot: this loop holds 24 % of the kernel's samples at 4; measured: 8 = no change, 16 = 19 % slower, profiles/README.md)
     const double pre = (pb.wsig >= 0.05) ? __dmul_rn(0.04, ws) : -1.0;
 #pragma unroll 1
     for (int i = 0; i < rules; i += FRIQ_WUPD_VEC) {
