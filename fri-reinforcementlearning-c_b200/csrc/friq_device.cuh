@@ -287,11 +287,9 @@ __device__ __forceinline__ void friq_best_action_pass(const friq_devprob &pb, co
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-per-action variant of the pass (k_run_steps_w3): the A = 3 actions of a 32-agent tile are
-// evaluated by three warps (lane = agent, warp = action), so an agent's critical path is one chain
-// per rule instead of A.  Each warp walks the whole rule base in rule order for its own action -
-// the sums are accumulated exactly as in friq_best_action_pass - with UNR rules (= UNR independent
-// sqrt / pow / rcp chains) per trip.
+// One action at a time (the per-call kernels for a run-time number of actions): the whole rule base
+// is walked in rule order for ONE action - the sums are accumulated exactly as in
+// friq_best_action_pass - with UNR rules (= UNR independent sqrt / pow / rcp chains) per trip.
 //   conc   Shepard conclusion of this action, or the consequent of the first rule at distance 0
 //   hidx   that rule's index, -1 if none (FIVEVagConcl_FRIRL_BestAct.c:89-93)
 // ---------------------------------------------------------------------------------------
@@ -345,32 +343,6 @@ __device__ __forceinline__ void friq_action_pass(const friq_devprob &pb, const u
     }
     hidx = (int)hi;
     conc = (hidx >= 0) ? rbq[(size_t)hidx * FRIQ_TILE] : __ddiv_rn(vagc, ws);               // :265
-}
-
-// Shepard weights wi of Q(s,a) at the previous antecedents vo_q[] (FIVEVagConcl.c:224-235) for the rules this warp
-// owns: blocks of UNR consecutive rules, dealt round-robin to the NW warps of the tile.  The weights go to sw[]; the
-// lead warp adds them up in rule order afterwards (and re-uses them for the weighted update).
-template <int K, int P, int UNR, int NW, bool SAFE>
-__device__ __forceinline__ void friq_q_weights(const friq_devprob &pb, const uint32_t *rbw, double *sw, int R, const double *vo_q,
-                                               bool needq, int wid)
-{
-#pragma unroll 1
-    for (int i = wid * UNR; i < R; i += NW * UNR) {
-        double wq[UNR], sq[UNR];
-        unsigned bad = 0;
-#pragma unroll
-        for (int u = 0; u < UNR; u++) {
-            const uint32_t w = (i + u < R) ? rbw[(size_t)(i + u) * FRIQ_TILE] : 0u;
-            sq[u] = friq_dist2<K>(pb, w, vo_q);
-            wq[u] = friq_shepard_weight_fast<P, SAFE>(sq[u], bad, needq && i + u < R && !friq_is_zero(sq[u]));
-        }
-        if (bad) {
-#pragma unroll
-            for (int u = 0; u < UNR; u++) wq[u] = friq_shepard_weight_slow<P>((friq_is_zero(sq[u]) || !needq) ? 1.0 : sq[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; u++) if (needq && i + u < R) sw[(size_t)(i + u) * FRIQ_TILE] = wq[u];
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -485,10 +457,6 @@ __device__ __forceinline__ void friq_hit_scan(const uint32_t *rbw, int R, const 
 // row, so these reads stay coalesced - and accumulates the sums sequentially in its own registers exactly like the
 // lock-step pass does (UNR rules = UNR independent chains per trip, friq_shepard_weights_n).  One round serves as many
 // pairs as the warp has lanes for the price of ONE chain per rule; the owners then pick their results up with a shuffle.  Bit-identical sums.
-#ifndef FRIQ_COMPACT_GMAX
-#define FRIQ_COMPACT_GMAX 1     /* lane groups per pair (2, 4, 8) measured SLOWER on B200 than one lane per pair: the segment shuffles of the
-                                * ordered sums cost more than the idle lanes save (gpurun_out/variants14.log); kept for experiments */
-#endif
 // dictionary cell of a packed word (row / column of the memoised weights pb.wtab)
 template <int K>
 __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
@@ -502,13 +470,6 @@ __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
 // ---- table mode: the per-agent list of rule cells (friq_devstate.rbc) is stored in blocks of FRIQ_CELL_VEC rules per lane,
 // [tile][slot / 8][lane][8] u16, so that a lane fetches the cells of 8 consecutive rules of a column with ONE 16-byte load;
 // the unused tail of the last block holds cell 0 (any valid column: those weights are loaded but never added).
-#ifndef FRIQ_TAB_PREFETCH
-#define FRIQ_TAB_PREFETCH 0     /* experiments: bit 0 prefetches the pair's table row, bit 1 the tile's consequent rows and cell blocks (both measured SLOWER: -3 .. -10 %) */
-#endif
-#ifndef FRIQ_TAB_PREFETCH_MAXCELLS
-#define FRIQ_TAB_PREFETCH_MAXCELLS 512
-#endif
-__device__ __forceinline__ void friq_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #ifndef FRIQ_CELL_VEC
 #define FRIQ_CELL_VEC 8         /* 8 (one 16-byte load per block) or 4 (8-byte loads, half the registers in flight) */
 #endif
@@ -623,16 +584,9 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
     for (int c = 0; c < C; c++) ofs[c + 1] = ofs[c] + __popc(chm[c]);
     const int np = ofs[C];
     vagq = 0.0; wsq = 0.0;
-    const int nw = __popc(wmask), rank = __popc(wmask & lt);          // the last warp of a batch may be partial
-    // Few pairs: every pair gets a GROUP of g lanes (g = 2, 4, 8).  The lanes of a group compute the weights of g consecutive
-    // blocks of UNR rules in parallel - the expensive part - and then all of them add the g * UNR weights up in rule order,
-    // fetching each other's values with segment shuffles, so the order of the sums is still the reference's.
-    int g = 1;
-    if (FRIQ_COMPACT_GMAX > 1 && wmask == 0xffffffffu) { if (np <= 4 && FRIQ_COMPACT_GMAX >= 8) g = 8; else if (np <= 8 && FRIQ_COMPACT_GMAX >= 4) g = 4; else if (np <= 16) g = 2; }
-    const int per_round = nw / g, gi = rank / g, gt = rank % g;
-    const unsigned gmask = (g == 1) ? (1u << lane) : (((g == 32 ? 0u : (1u << g)) - 1u) << (lane & ~(g - 1)));
+    const int per_round = __popc(wmask), rank = __popc(wmask & lt);   // the last warp of a batch may be partial
     for (int p0 = 0; p0 < np; p0 += per_round) {
-        // ---- which pair is my group's?  the owners post (lane, channel) of their pairs of this round, group gi reads entry gi
+        // ---- which pair is mine?  the owners post (lane, channel) of their pairs of this round, lane number `rank` reads entry `rank`
         __syncwarp(wmask);
 #pragma unroll
         for (int t = 0; t < C; t++) {
@@ -640,9 +594,8 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             if (((chm[t] >> lane) & 1u) && e >= 0 && e < per_round) plist[e] = (unsigned char)(lane | (t << 5));
         }
         __syncwarp(wmask);
-        const int p = p0 + gi;
-        const bool has = p < np && gi < per_round;
-        const int ent = has ? plist[gi] : 0;
+        const bool has = p0 + rank < np;
+        const int ent = has ? plist[rank] : 0;
         const int c = ent >> 5, j = ent & 31;
         // ---- the owner's point (table mode needs it only for the rare computed fall-back) and rule count
         double pt[K];
@@ -660,33 +613,14 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
         const bool isq = has && c == A;
         double vag = 0.0, ws = 0.0;
         // ---- table mode: a pair whose point is a dictionary cell looks the weight of every rule up (pb.wtab)
-        bool tab = false;
         if constexpr (TAB) {
             const uint32_t x = __shfl_sync(wmask, ow, j), y = __shfl_sync(wmask, qw, j);
             const int ah = pb.act_hit[c < A ? c : 0];
             const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET);
-            tab = has && pw != FRIQ_NO_TARGET;
-#if FRIQ_TAB_PREFETCH & 2
-            {   // the tile's rule data of this round (consequent rows, cell blocks) requested from L2 by all lanes at once
-                const int Rw = __reduce_max_sync(wmask, R);
-                const char *qb = reinterpret_cast<const char *>(tq), *cb = reinterpret_cast<const char *>(rbc);
-                for (int l = lane; l < 2 * Rw; l += 32) friq_prefetch_l1(qb + (size_t)l * 128);
-                for (int l = lane; l < ((Rw + FRIQ_CELL_VEC - 1) / FRIQ_CELL_VEC) * (FRIQ_CELL_VEC * 2 * FRIQ_TILE / 128); l += 32) friq_prefetch_l1(cb + (size_t)l * 128);
-            }
-#endif
+            const bool tab = has && pw != FRIQ_NO_TARGET;
             if (tab) {
                 const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wcells;
                 asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
-#if FRIQ_TAB_PREFETCH & 1
-                // the whole table row of the pair (1.8 KB for mountaincar) is requested up front: the loop's dependent lookups
-                // (cell -> weight) then find their lines in L1 instead of paying one L2 latency per block of 8 rules
-                if (pb.wcells <= FRIQ_TAB_PREFETCH_MAXCELLS) {
-                    const char *rb = reinterpret_cast<const char *>(rowd);
-                    const int bytes = pb.wcells * 8;
-#pragma unroll 1
-                    for (int o = 0; o < bytes; o += 128) friq_prefetch_l1(rb + o);
-                }
-#endif
                 friq_tab_sums(rowd, rbc, tq, tsw, j, Rj, isq, vag, ws);
             }
             const bool slow = has && !tab;
@@ -701,28 +635,25 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
         }
         if constexpr (!TAB) {
         const int Rp = has ? Rj : 0;
-        // ---- sequential Shepard sums over the owner's rules: g * UNR rules per trip, my block starts at i + gt * UNR
-        const int stride = g * UNR;
+        // ---- sequential Shepard sums over the owner's rules, UNR rules (= UNR independent chains) per trip
         uint32_t w[UNR]; double q[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-            const int r = gt * UNR + u;
             w[u] = 0; q[u] = 0.0;
-            if (r < Rp) { w[u] = tw[(size_t)r * FRIQ_TILE + j]; q[u] = tq[(size_t)r * FRIQ_TILE + j]; }
+            if (u < Rp) { w[u] = tw[(size_t)u * FRIQ_TILE + j]; q[u] = tq[(size_t)u * FRIQ_TILE + j]; }
         }
 #pragma unroll 1
-        for (int i = 0; i < Rp; i += stride) {
-            const int i0 = i + gt * UNR;                 // my block
+        for (int i = 0; i < Rp; i += UNR) {
             uint32_t wn[UNR]; double qn[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) {              // prefetch my block of the next trip
-                const int r = i0 + stride + u;
+            for (int u = 0; u < UNR; u++) {              // prefetch the next trip
+                const int r = i + UNR + u;
                 wn[u] = 0; qn[u] = 0.0;
                 if (r < Rp) { wn[u] = tw[(size_t)r * FRIQ_TILE + j]; qn[u] = tq[(size_t)r * FRIQ_TILE + j]; }
             }
             double sv[UNR], wv[UNR], wq[UNR], dv[UNR]; bool live[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) { sv[u] = friq_dist2<K>(pb, w[u], pt); live[u] = i0 + u < Rp; }   // != 0 for real rules: no exact hit
+            for (int u = 0; u < UNR; u++) { sv[u] = friq_dist2<K>(pb, w[u], pt); live[u] = i + u < Rp; }   // != 0 for real rules: no exact hit
             unsigned bad = 0;
             friq_shepard_weights_n<P, SAFE, UNR>(sv, wv, bad, live, dv);
             if (bad) {
@@ -733,33 +664,23 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
                 wq[u] = __dmul_rn(wv[u], q[u]);                                               // BestAct.c:216 / FIVEVagConcl.c:234, the product
-                if (isq && live[u]) tsw[(size_t)(i0 + u) * FRIQ_TILE + j] = wv[u];
+                if (isq && live[u]) tsw[(size_t)(i + u) * FRIQ_TILE + j] = wv[u];
             }
-            if (g == 1) {
 #pragma unroll
-                for (int u = 0; u < UNR; u++)
-                    if (u == 0 || i + u < Rp) { vag = __dadd_rn(vag, wq[u]); ws = __dadd_rn(ws, wv[u]); }   // :216-217 / :234-235
-            } else {
-                for (int tt = 0; tt < g; tt++) {         // blocks in rule order; every lane of the group adds the same values
-#pragma unroll
-                    for (int u = 0; u < UNR; u++) {
-                        const double a1 = __shfl_sync(gmask, wq[u], tt, g), a2 = __shfl_sync(gmask, wv[u], tt, g);
-                        if (i + tt * UNR + u < Rp) { vag = __dadd_rn(vag, a1); ws = __dadd_rn(ws, a2); }
-                    }
-                }
-            }
+            for (int u = 0; u < UNR; u++)
+                if (u == 0 || i + u < Rp) { vag = __dadd_rn(vag, wq[u]); ws = __dadd_rn(ws, wv[u]); }   // :216-217 / :234-235
 #pragma unroll
             for (int u = 0; u < UNR; u++) { w[u] = wn[u]; q[u] = qn[u]; }
         }
         }   // !TAB
         const double res = __ddiv_rn(vag, ws);                                               // BestAct.c:265
-        // ---- hand the results back to the owners (first lane of the pair's group)
+        // ---- hand the results back to the owners
         __syncwarp(wmask);
 #pragma unroll
         for (int t = 0; t < C; t++) {
             const int e = ofs[t] + __popc(chm[t] & lt) - p0;         // my pair of channel t is entry e of this round (if I have one)
             const bool mine = ((chm[t] >> lane) & 1u) && e >= 0 && e < per_round;
-            const int src = mine ? e * g : rank;                      // rank of the group's first lane
+            const int src = mine ? e : rank;                          // rank of the lane that summed it
             const int sl = (wmask == 0xffffffffu) ? src : friq_nth_lane(wmask, src);
             if (t < A) { const double r = __shfl_sync(wmask, res, sl); if (mine) conc[t < A ? t : 0] = r; }
             else { const double a1 = __shfl_sync(wmask, vag, sl), a2 = __shfl_sync(wmask, ws, sl); if (mine) { vagq = a1; wsq = a2; } }

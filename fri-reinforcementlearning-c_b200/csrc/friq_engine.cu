@@ -63,27 +63,6 @@ struct __align__(16) friq_smem_t {
     uint64_t mbar;
 };
 
-// Experiment (FRIQ_BLOCK_REMAP=1, OFF): after a re-tiling the CTAs of a launch are ordered by rule count, heaviest first, so the
-// first wave puts two HEAVY CTAs on every SM.  Pairing each of the 148 heaviest CTAs with one of the 148 lightest (to even out
-// the L1 working sets) measured 3-6 % SLOWER: the lightest CTAs then finish early next to the critical path and the middle ones
-// start late.  Placement only: results do not depend on it.
-#ifndef FRIQ_BLOCK_REMAP
-#define FRIQ_BLOCK_REMAP 0
-#endif
-#ifndef FRIQ_SM_COUNT
-#define FRIQ_SM_COUNT 148
-#endif
-__device__ __forceinline__ unsigned friq_logical_block(unsigned b, unsigned n)
-{
-#if FRIQ_BLOCK_REMAP
-    if (b < FRIQ_SM_COUNT || n <= FRIQ_SM_COUNT) return b;
-    const unsigned m = min(n - FRIQ_SM_COUNT, (unsigned)FRIQ_SM_COUNT);      // CTAs that become an SM's second one
-    if (b < FRIQ_SM_COUNT + m) return n - 1 - (b - FRIQ_SM_COUNT);          // ... the lightest
-    return b - m;                                                          // the middle, heaviest first
-#else
-    return b;
-#endif
-}
 #define FRIQ_SMEM_PROLOGUE_AT(BLOCK_INDEX)                                        \
     __shared__ friq_smem_t sm;                                                    \
     friq_stage_problem(gprob, sm.prob, &sm.mbar);                                 \
@@ -111,7 +90,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 #ifdef FRIQ_TIMELINE
     const unsigned long long tl_t0 = friq_globaltimer();
 #endif
-    FRIQ_SMEM_PROLOGUE_AT(friq_logical_block(blockIdx.x, gridDim.x));
+    FRIQ_SMEM_PROLOGUE();
     double *prevq = st.prevq ? st.prevq + tile_off : nullptr;
     double *wref = ((mode & FRIQ_M_KEEP_WEIGHTS) && st.wref) ? st.wref + tile_off : nullptr;
 
@@ -317,221 +296,6 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 }
 
 // ---------------------------------------------------------------------------------------
-// k_run_steps_w3: the fused step kernel with THREE warps per 32-agent tile (lane = agent, warp = action;
-// problems with A = 3).  The rule-count distribution of a learning batch is heavy-tailed, and with one thread
-// per agent the launch time is set by the serial time of the agents with the largest rule bases while most SMs
-// idle.  Here the three Shepard conclusions of an agent are evaluated concurrently, which cuts the per-agent
-// critical path of a step ~3x and triples the number of schedulable warps; every sum is still accumulated in
-// rule order by a single thread, so results stay bit-identical.
-//   warp 0 ("lead")  owns the agent state in registers and runs everything except the passes of actions 1, 2:
-//                    dynamics, reward, quantiser, its own pass, action selection, Q(s,a) sum, SARSA update.
-//   warps 1, 2       evaluate the conclusion of their action, and their share of the Shepard weights of Q(s,a).
-// Hand-off through shared memory, two CTA barriers per env step:
-//   B1  lead -> all : observation VE values, Q(s,a) antecedent VE values, rule count, needq, go
-//   B2  all -> lead : conclusion + first exact-hit rule per action (the weights of Q(s,a) are in sw[])
-// The lead is the only writer of the rule base and writes it only between B2 and the next B1.
-// ---------------------------------------------------------------------------------------
-#ifndef FRIQ_W3_MINB
-#define FRIQ_W3_MINB 3
-#endif
-#ifndef FRIQ_W3_UNR
-#define FRIQ_W3_UNR 6
-#endif
-template <int S>
-struct friq_w3_xch {
-    double vc[S][FRIQ_TILE];          // VE values of the quantised observation (lead -> all)
-    double vo[S + 1][FRIQ_TILE];      // VE values of the pending update's antecedents (s,a)
-    double actconc[3][FRIQ_TILE];     // all -> lead
-    int hidx[3][FRIQ_TILE];
-    int R[FRIQ_TILE];
-    unsigned needq_mask;
-    int go;
-};
-
-template <int S, int P, int ENV, int UNR, bool SAFE>
-__global__ void __launch_bounds__(3 * FRIQ_TILE, FRIQ_W3_MINB)
-k_run_steps_w3(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
-{
-    constexpr int K = S + 1, A = 3, NW = 3;
-    __shared__ friq_smem_t sm;
-    __shared__ friq_w3_xch<S> X;
-    friq_stage_problem(gprob, sm.prob, &sm.mbar);
-    const friq_devprob &pb = *reinterpret_cast<const friq_devprob *>(sm.prob);
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long ag = (long)blockIdx.x * FRIQ_TILE + lane;
-    const bool valid = ag < st.n;
-    const long ia = valid ? ag : (long)blockIdx.x * FRIQ_TILE;          // padding lanes shadow lane 0 and never store
-    const size_t tile_off = (size_t)blockIdx.x * st.cap * FRIQ_TILE + lane;
-    uint32_t *rbw = st.rbw + tile_off;
-    double *rbq = st.rbq + tile_off;
-    double *sw = st.sw + tile_off;
-
-    if (wid != 0) {                                      // ---- helper warps: one action each
-        const double ave = pb.act_ve[wid];
-        for (;;) {
-            __syncthreads();                             // B1
-            if (!X.go) break;
-            double vc[S], vo[K], conc; int hidx;
-#pragma unroll
-            for (int k = 0; k < S; k++) vc[k] = X.vc[k][lane];
-            const int R = X.R[lane];
-            const unsigned qm = X.needq_mask;
-            friq_action_pass<S, P, UNR, SAFE>(pb, rbw, rbq, R, vc, ave, conc, hidx);
-            if (qm) {
-#pragma unroll
-                for (int k = 0; k < K; k++) vo[k] = X.vo[k][lane];
-                friq_q_weights<K, P, UNR, NW, SAFE>(pb, rbw, sw, R, vo, (qm >> lane) & 1u, wid);
-            }
-            X.actconc[wid][lane] = conc; X.hidx[wid][lane] = hidx;
-            __syncthreads();                             // B2
-        }
-        return;
-    }
-
-    // ---- lead warp: agent state -> registers (as k_run_steps)
-    double *prevq = st.prevq ? st.prevq + tile_off : nullptr;
-    double s[S], qs[K], vo[K];
-#pragma unroll
-    for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ia];
-#pragma unroll
-    for (int k = 0; k < K; k++) { qs[k] = st.qs[(size_t)k * st.n_pad + ia]; vo[k] = st.vo[(size_t)k * st.n_pad + ia]; }
-    int aidx = st.aidx[ia], flags = st.flags[ia], R = st.R[ia], step_in_ep = st.step_in_ep[ia], hitq = st.hitq[ia];
-    uint32_t ep_num = st.ep_num[ia];
-    double ep_return = st.ep_return[ia];
-    double prev_reward = st.prev_reward[ia]; int prev_steps = st.prev_steps[ia], prev_numru = st.prev_numru[ia];
-    double last_return = st.last_return[ia]; int last_steps = st.last_steps[ia], last_rules = st.last_rules[ia];
-    unsigned long long total_steps = st.total_steps[ia], sum_rules = st.sum_rules[ia];
-    const unsigned long long seed = st.seed[ia];
-    const double alpha = st.alpha[ia], gamma = st.gamma[ia], epsilon = st.epsilon[ia];
-    const bool learn = mode & FRIQ_M_LEARN, track = (mode & FRIQ_M_TRACK) && prevq;
-    int qi[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        qi[k] = -1;
-        for (int j = 0; j < pb.grid_len[k]; j++) if (pb.dict_val[k][j] == qs[k]) { qi[k] = j; break; }
-    }
-    const double ave0 = pb.act_ve[0];
-    long done_steps = 0;
-    bool running = valid;
-    while (__any_sync(0xffffffffu, running && done_steps < n_steps)) {
-        const bool act = running && done_steps < n_steps && !((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED));
-        const bool initial = flags & FRIQ_F_NEED_RESET;
-        double cur[S], cq[S], vc[S], reward = 0.0; int done = 0, ci[S];
-        if (act) {
-            if (initial) {                               // frirl_episode.c:46-82
-#pragma unroll
-                for (int k = 0; k < S; k++) {
-                    if (st.s0) { s[k] = qs[k] = st.s0[(size_t)k * st.n_pad + ag]; vo[k] = vc[k] = friq_obs_ve(pb, k, s[k]); }
-                    else { s[k] = qs[k] = pb.values_def[k]; vo[k] = vc[k] = pb.ve_def[k]; }
-                    cur[k] = cq[k] = s[k]; qi[k] = ci[k] = -1;
-                }
-                ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
-                prev_numru = R;
-                if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
-            } else {                                     // frirl_episode.c:97-112
-                friq_env_step<ENV>(pb.act_val[aidx], s, cur);
-                friq_env_reward<ENV>(cur, reward, done);
-                ep_return = __dadd_rn(ep_return, reward);
-                friq_env_quantize<ENV, S>(pb, cur, cq, vc, ci);
-                step_in_ep++;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < S; k++) { cur[k] = s[k]; cq[k] = qs[k]; vc[k] = vo[k]; ci[k] = qi[k]; }
-            running = false;
-        }
-        const bool upd = act && !initial && learn;
-        if (upd && (hitq == -2 || !pb.qp_reuse)) hitq = friq_first_hit<K>(pb, rbw, R, vo);
-        const bool needq = upd && hitq < 0;
-        const unsigned qm = __ballot_sync(0xffffffffu, needq);
-        const int Reff = act ? R : 0;
-        // ---- B1: hand the step to the helper warps
-#pragma unroll
-        for (int k = 0; k < S; k++) X.vc[k][lane] = vc[k];
-        if (qm) {
-#pragma unroll
-            for (int k = 0; k < K; k++) X.vo[k][lane] = vo[k];
-        }
-        X.R[lane] = Reff;
-        if (lane == 0) { X.needq_mask = qm; X.go = 1; }
-        __syncthreads();
-        double actconc[A]; int hidx[A];
-        friq_action_pass<S, P, UNR, SAFE>(pb, rbw, rbq, Reff, vc, ave0, actconc[0], hidx[0]);
-        if (qm) friq_q_weights<K, P, UNR, NW, SAFE>(pb, rbw, sw, Reff, vo, needq, 0);
-        __syncthreads();                                 // ---- B2: conclusions of actions 1, 2 and the Q(s,a) weights are in
-#pragma unroll
-        for (int a = 1; a < A; a++) { actconc[a] = X.actconc[a][lane]; hidx[a] = X.hidx[a][lane]; }
-        const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
-        const int next_hit = pb.qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
-        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }
-        if (act && !initial) {
-            sum_rules += (unsigned long long)R;
-            if (learn) {                                 // frirl_update_sarsa.c:348-385
-                double qp, qnow, ws = 0.0;
-                if (pb.qp_reuse) qp = friq_pick<A>(actconc, a2);
-                else {
-                    double vq[K], wsd;
-#pragma unroll
-                    for (int k = 0; k < S; k++) vq[k] = vc[k];
-                    vq[S] = pb.act_ve_eval[a2];
-                    friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vq, qp, wsd);
-                }
-                if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
-                else {                                   // sequential Shepard sums of Q(s,a), FIVEVagConcl.c:224-235, :302
-                    double vagq = 0.0;
-                    for (int i = 0; i < R; i++) {
-                        const double wi = sw[(size_t)i * FRIQ_TILE];
-                        vagq = __dadd_rn(vagq, __dmul_rn(wi, rbq[(size_t)i * FRIQ_TILE]));
-                        ws = __dadd_rn(ws, wi);
-                    }
-                    qnow = __ddiv_rn(vagq, ws);
-                }
-                const int R0 = R;
-                friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma);
-                hitq = next_hit;
-                if (R > R0 && hitq == -1) {              // a rule was appended: is it at the next step's (s,a)?
-                    const uint32_t wnew = rbw[(size_t)R0 * FRIQ_TILE];
-                    bool same = pb.dict_ve[S][(wnew >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)] == pb.act_ve_eval[a2];
-#pragma unroll
-                    for (int k = 0; k < S; k++) same = same && (pb.dict_ve[k][(wnew >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)] == vc[k]);
-                    if (same) hitq = R0;
-                }
-            } else hitq = next_hit;
-#pragma unroll
-            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; qi[k] = ci[k]; }
-            aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2;
-            total_steps++; done_steps++;
-            if (done || step_in_ep >= pb.max_steps) {
-                if (learn && track && prev_numru == R && prev_steps == step_in_ep && ep_return > pb.reward_good_above && prev_reward == ep_return) {
-                    bool ok = true;
-                    for (int i = 0; i < R && ok; i++)
-                        if (fabs(__dsub_rn(rbq[(size_t)i * FRIQ_TILE], prevq[(size_t)i * FRIQ_TILE])) >= pb.qdiff_final_tol) ok = false;
-                    if (ok) flags |= FRIQ_F_CONVERGED;
-                }
-                last_return = ep_return; last_steps = step_in_ep; last_rules = R;
-                prev_reward = ep_return; prev_steps = step_in_ep;
-                ep_num++;
-                flags |= FRIQ_F_NEED_RESET;
-                if (mode & FRIQ_M_STOP_AT_EPISODE_END) running = false;
-            }
-        }
-        __syncwarp();
-    }
-    if (lane == 0) X.go = 0;
-    __syncthreads();                                     // releases the helper warps
-    if (!valid) return;
-#pragma unroll
-    for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
-#pragma unroll
-    for (int k = 0; k < K; k++) { st.qs[(size_t)k * st.n_pad + ag] = qs[k]; st.vo[(size_t)k * st.n_pad + ag] = vo[k]; }
-    st.aidx[ag] = aidx; st.flags[ag] = flags; st.R[ag] = R; st.step_in_ep[ag] = step_in_ep; st.hitq[ag] = hitq;
-    st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
-    st.prev_reward[ag] = prev_reward; st.prev_steps[ag] = prev_steps; st.prev_numru[ag] = prev_numru;
-    st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
-    st.total_steps[ag] = total_steps; st.sum_rules[ag] = sum_rules;
-}
-
-// ---------------------------------------------------------------------------------------
 // Shared-rule-base inference (BASELINE config 4: many agents, ONE large read-only rule base,
 // reduction_state = 1 semantics of frirl_test_run.c:65-69: greedy stepping, no rule-base writes).
 // The rule base is stored as rows of (VE value of each antecedent, consequent) = (K+1) f64 and streams
@@ -576,11 +340,11 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
     const bool valid = ag < st.n;
     const long ia = valid ? ag : 0;
 
-    double s[S], qs[K];
+    double s[S], qs[K], vo[K];                           // vo: VE values of qs[], kept like k_run_steps keeps them (a learning launch may follow)
 #pragma unroll
     for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ia];
 #pragma unroll
-    for (int k = 0; k < K; k++) qs[k] = st.qs[(size_t)k * st.n_pad + ia];
+    for (int k = 0; k < K; k++) { qs[k] = st.qs[(size_t)k * st.n_pad + ia]; vo[k] = st.vo[(size_t)k * st.n_pad + ia]; }
     int aidx = st.aidx[ia], flags = st.flags[ia], step_in_ep = st.step_in_ep[ia];
     uint32_t ep_num = st.ep_num[ia];
     double ep_return = st.ep_return[ia], last_return = st.last_return[ia];
@@ -684,12 +448,16 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
 #pragma unroll
         for (int a = 0; a < A; a++) actconc[a] = ((hitmask >> a) & 1u) ? hq[a] : __ddiv_rn(vagc[a], ws[a]);
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
-        if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; }
+        if (act && initial) {
+            aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
+#pragma unroll
+            for (int k = 0; k < S; k++) vo[k] = vc[k];
+        }
         if (act && !initial) {
             sum_rules += (unsigned long long)Rs;
 #pragma unroll
-            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; }
-            aidx = a2; qs[S] = pb.act_val[a2];
+            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; }
+            aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
             total_steps++; done_steps++;
             if (done || step_in_ep >= pb.max_steps) {
                 last_return = ep_return; last_steps = step_in_ep; last_rules = Rs;
@@ -703,7 +471,7 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
 #pragma unroll
     for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
 #pragma unroll
-    for (int k = 0; k < K; k++) st.qs[(size_t)k * st.n_pad + ag] = qs[k];
+    for (int k = 0; k < K; k++) { st.qs[(size_t)k * st.n_pad + ag] = qs[k]; st.vo[(size_t)k * st.n_pad + ag] = vo[k]; }
     st.aidx[ag] = aidx; st.flags[ag] = flags; st.step_in_ep[ag] = step_in_ep; st.hitq[ag] = -2;
     st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
     st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
@@ -1295,13 +1063,13 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
         if (!done_ && FRIQ_CARVEOUT_PCT >= 0) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FRIQ_CARVEOUT_PCT); done_ = true; } \
     } while (0)
 int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, int variant, void *stream)
-{   // variant 0: one thread per agent, lock-step pass (+ hit sweep / cooperative sums when few pairs lack a hit);
-    // 1: three warps per tile (k_run_steps_w3, A = 3 problems); 2: one thread per agent, hit sweep + cooperative sums only
+{   // evaluation policy (friq_batch_set_policy): 0 lock-step pass over all actions (+ hit sweep / compacted sums when few pairs lack
+    // a hit); 1 exact hits first + compacted Shepard chains only; 2 the same in table mode (memoised weights, per-agent indexes)
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
     // table mode (memoised weights + per-agent indexes) only where the COOP kernels run and the indexes are sized for this table
-    const bool coop = variant == 2 && hp->hit_scan && hp->safe_range &&
+    const bool coop = variant >= 1 && hp->hit_scan && hp->safe_range &&
                       ((hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) || (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)));
-    const bool tab = coop && hp->wtab && st.rbc && st.idx_cells == hp->wcells;
+    const bool tab = coop && variant == 2 && hp->wtab && st.rbc && st.idx_cells == hp->wcells;
     if (tab) {
         CK(cudaMemsetAsync(st.cmap, 0, (size_t)((st.n + FRIQ_TILE - 1) / FRIQ_TILE) * st.idx_cells * FRIQ_TILE * sizeof(unsigned short), s));
         k_refresh_index<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st);
@@ -1311,16 +1079,7 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
         if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
         else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
     } while (0)
-#define FRIQ_LAUNCH_W3(S_, P_, ENV_)                                                                                   \
-    do {                                                                                                              \
-        const dim3 g3((unsigned)((st.n + FRIQ_TILE - 1) / FRIQ_TILE));                                                 \
-        if (hp->safe_range) k_run_steps_w3<S_, P_, ENV_, FRIQ_W3_UNR, true><<<g3, 3 * FRIQ_TILE, 0, s>>>(dprob, st, n_steps, mode); \
-        else k_run_steps_w3<S_, P_, ENV_, FRIQ_W3_UNR, false><<<g3, 3 * FRIQ_TILE, 0, s>>>(dprob, st, n_steps, mode);   \
-    } while (0)
-    const int w3 = variant == 1;
-    if (w3 && hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_W3(2, 3, FRIQ_ENV_MOUNTAINCAR);
-    else if (w3 && hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_W3(4, 5, FRIQ_ENV_ACROBOT);
-    else if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR) {
+    if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR) {
         FRIQ_CARVEOUT((k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2>));
         k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     } else if (tab && hp->env == FRIQ_ENV_ACROBOT) {

@@ -44,9 +44,7 @@ struct friq_batch {
     double *d_srb; int shared_R;   /* shared read-only rule base: rows of (K VE values, consequent) */
     int groups;               /* independent agent groups pipelined on their own streams (hides launch tails) */
     void *gstream[FRIQ_MAXGROUPS], *gdone[FRIQ_MAXGROUPS], *gstart;
-    void *hstream[FRIQ_MAXGROUPS], *hfork[FRIQ_MAXGROUPS], *hjoin[FRIQ_MAXGROUPS];   /* side streams: the light tiles of a group */
-    int variant;              /* kernel of the un-tiled path: 0 one thread per agent, 1 three warps per tile (FRIQ_W3) */
-    int heavy_pct;            /* share of a group's tiles (largest rule bases first) stepped with three warps per tile */
+    int variant;              /* evaluation policy of the fused kernel (friq_batch_set_policy) */
     int *d_work;              /* re-tiling scratch */
     void *d_tmp8, *d_tmp4a, *d_tmp4b;   /* un-permuted result staging */
     int device;
@@ -312,15 +310,14 @@ int friq_problem_set_learning_params(friq_problem *P, double qdiff_pos, double q
  * pair is a constant of the problem: the fused kernel looks it up instead of running the sqrt -> x87 power -> reciprocal
  * chain per rule and pair.  The table is computed on the device by the same functions (friq_dist2, friq_shepard_weight).
  * Only for problems where exact hits are index equality (hit_scan) and Q(s',a') is actconc[a'] (qp_reuse), i.e. where the
- * fused kernel's policy 2 runs; FRIQ_NO_WTAB=1 disables it (experiments, parity tests of the computed path). */
+ * fused kernel's policy 2 runs (friq_batch_set_policy(b, 1) runs the computed chains instead: parity tests). */
 #define FRIQ_WTAB_MAX_BYTES (64ul << 20)
 static int problem_publish(friq_problem *P)
 {
     friq_devprob *hp = &P->hp;
     if (P->d_wtab) { DEV(friqd_device_sync()); DEV(friqd_free(P->d_wtab)); P->d_wtab = NULL; }
     hp->wtab = NULL; hp->wcells = 0;
-    const char *off = getenv("FRIQ_NO_WTAB");
-    if ((hp->env == FRIQ_ENV_MOUNTAINCAR || hp->env == FRIQ_ENV_ACROBOT) && hp->hit_scan && hp->qp_reuse && !(off && atoi(off))) {
+    if ((hp->env == FRIQ_ENV_MOUNTAINCAR || hp->env == FRIQ_ENV_ACROBOT) && hp->hit_scan && hp->qp_reuse) {
         unsigned long cells = 1; int ok = 1;
         for (int k = 0; k < hp->K; k++) { hp->wlin[k] = (int)cells; cells *= (unsigned long)hp->dict_len[k]; if (cells > 65535ul) { ok = 0; break; } }
         for (int a = 0; a < hp->A; a++) if (hp->act_hit[a] < 0) ok = 0;
@@ -481,28 +478,40 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     friq_batch *b = (friq_batch *)calloc(1, sizeof *b);
     b->P = P; b->device = device; b->seed0 = seed0; b->first_agent = first_agent;
     b->retile_interval = 125;
-    { const char *e = getenv("FRIQ_HEAVY_PCT"); b->heavy_pct = e ? atoi(e) : 0; if (b->heavy_pct < 0) b->heavy_pct = 0; if (b->heavy_pct > 100) b->heavy_pct = 100; }
     /* evaluation policy of the fused kernel (friqd_run_steps variant): mountaincar agents find an exact-hit rule for > 90 % of
-     * the (observation, action) pairs they visit, so the integer hit sweep + compacted Shepard sums win by a wide margin; for
+     * the (observation, action) pairs they visit, so exact hits first + compacted Shepard sums win by a wide margin; for
      * acrobot (13-53 % hits) they still measure 16 % faster than the lock-step pass; cartpole (A = 21, off-grid observations)
-     * keeps the lock-step pass.  FRIQ_POLICY=0|1|2 overrides (experiments). */
+     * keeps the lock-step pass.  friq_batch_set_policy() overrides. */
     b->variant = ((P->hp.env == FRIQ_ENV_MOUNTAINCAR || P->hp.env == FRIQ_ENV_ACROBOT) && P->hp.hit_scan) ? 2 : 0;
-    { const char *e = getenv("FRIQ_POLICY"); if (e) b->variant = atoi(e); }
-    {   /* groups of >= 8192 agents, tile aligned; FRIQ_GROUPS overrides (experiments) */
-        const char *e = getenv("FRIQ_GROUPS");
-        int g = e ? atoi(e) : (int)(n / 32768);
-        if (g < 1) g = 1;
-        if (g > FRIQ_MAXGROUPS) g = FRIQ_MAXGROUPS;
-        while (g > 1 && (n / g) < 1024) g--;
-        b->groups = g;
-    }
     friq_devstate *st = &b->st;
     st->n = n; st->n_pad = (n + FRIQ_TILE - 1) / FRIQ_TILE * FRIQ_TILE; st->cap = cap;
+    friq_batch_set_groups(b, 0);
     { int rc2 = alloc_state(st, 1); if (rc2) return rc2; }
     const size_t slots = (size_t)st->n_pad * cap;
     DEV(friqd_malloc((void **)&st->sw, slots * 8)); DEV(friqd_memset(st->sw, 0, slots * 8));
     *out = b;
     return friq_batch_reset(b);
+}
+
+/* evaluation policy of the fused kernel: 0 lock-step pass over all actions, 1 exact hits first + compacted Shepard chains,
+ * 2 the same with memoised weights (table mode).  A policy the problem does not qualify for falls back to the next lower one;
+ * results never depend on it (tests/test_gpu_parity.py compares all of them with the oracle). */
+int friq_batch_set_policy(friq_batch *b, int policy)
+{
+    if (policy < 0 || policy > 2) FAIL(4, "friq_batch_set_policy: policy %d (0, 1 or 2)", policy);
+    b->variant = policy;
+    return 0;
+}
+/* agent groups of a re-tiled run, each sorted and launched on its own stream; 0 = default (one per 32,768 agents, at most 8) */
+int friq_batch_set_groups(friq_batch *b, int groups)
+{
+    int g = groups > 0 ? groups : (int)(b->st.n ? b->st.n / 32768 : 1);
+    if (g < 1) g = 1;
+    if (g > FRIQ_MAXGROUPS) g = FRIQ_MAXGROUPS;
+    while (g > 1 && b->st.n && (b->st.n / g) < 1024) g--;
+    if (b->permuted) { DEV(friqd_set_device(b->device)); IDENTITY(b); }
+    b->groups = g;
+    return 0;
 }
 
 int friq_batch_reset(friq_batch *b)
@@ -522,7 +531,6 @@ void friq_batch_destroy(friq_batch *b)
     for (int g = 0; g < FRIQ_MAXGROUPS; g++) {
         if (b->gstream[g]) friqd_stream_destroy(b->gstream[g]);
         if (b->gdone[g]) friqd_event_destroy(b->gdone[g]);
-        if (b->hstream[g]) { friqd_stream_destroy(b->hstream[g]); friqd_event_destroy(b->hfork[g]); friqd_event_destroy(b->hjoin[g]); }
     }
     if (b->gstart) friqd_event_destroy(b->gstart);
     friqd_free(b->st.sw);
@@ -568,7 +576,7 @@ int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant
         }
         w[i] = word;
     }
-    if (grew) { refresh_hit_scan(P); int rcp_ = problem_publish(P); if (rcp_) return rcp_; }
+    if (grew) { refresh_hit_scan(P); int rcp_ = problem_publish(P); if (rcp_) { free(w); return rcp_; } }
     if (agent >= 0) {
         const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE);
         if (R) {
@@ -722,7 +730,6 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         if (!b->gstart) DEV(friqd_event_create(&b->gstart));
         for (int g = 0; g < G; g++) if (!b->gstream[g]) {
             DEV(friqd_stream_create(&b->gstream[g])); DEV(friqd_event_create(&b->gdone[g]));
-            DEV(friqd_stream_create(&b->hstream[g])); DEV(friqd_event_create(&b->hfork[g])); DEV(friqd_event_create(&b->hjoin[g]));
         }
         DEV(friqd_event_record(b->gstart, stream));
         const long tiles = b->st.n_pad / FRIQ_TILE, per = (tiles + G - 1) / G * FRIQ_TILE;
@@ -736,22 +743,7 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
                 if (cnt <= 0) continue;
                 friq_devstate src = state_view(&b->st, lo, cnt), dst = state_view(&b->st2, lo, cnt);
                 DEV(friqd_retile(src, dst, b->d_work + g * wstride, 1, b->gstream[g]));
-                /* The rule-count distribution is heavy-tailed and a launch lasts as long as its slowest warp: the tiles
-                 * with the largest rule bases (they come first after the sort) are stepped with three warps per tile,
-                 * which shortens their critical path ~2x; the bulk keeps the cheaper one-thread-per-agent kernel and
-                 * runs beside them on a side stream. */
-                long heavy = (b->P->hp.A == 3) ? (cnt / FRIQ_TILE * b->heavy_pct + 99) / 100 * FRIQ_TILE : 0;
-                if (heavy > cnt) heavy = cnt;
-                if (heavy > 0 && heavy < cnt) {
-                    friq_devstate hv = state_view(&b->st2, lo, heavy), lt = state_view(&b->st2, lo + heavy, cnt - heavy);
-                    DEV(friqd_event_record(b->hfork[g], b->gstream[g]));
-                    DEV(friqd_stream_wait_event(b->hstream[g], b->hfork[g]));
-                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, hv, m, mode, 1, b->gstream[g]));
-                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, lt, m, mode, b->variant == 1 ? 0 : b->variant, b->hstream[g]));
-                    DEV(friqd_event_record(b->hjoin[g], b->hstream[g]));
-                    DEV(friqd_stream_wait_event(b->gstream[g], b->hjoin[g]));
-                } else
-                    DEV(friqd_run_steps(&b->P->hp, b->P->dp, dst, m, mode, heavy > 0 ? 1 : b->variant, b->gstream[g]));
+                DEV(friqd_run_steps(&b->P->hp, b->P->dp, dst, m, mode, b->variant, b->gstream[g]));
             }
             friq_devstate t = b->st; b->st = b->st2; b->st2 = t;
             b->permuted = 1 + G;
@@ -1053,7 +1045,8 @@ int friq_batch_merge_rb(friq_batch *b, long agent, int Rs, const double *rant, c
  *   rules into the leader (merge_rb, members that "pended" in the chunk are skipped, :338-363);
  *   a team is finished when its leader finds its rule base complete (or runs out of episodes).
  * log (optional): rows (agent, steps, return, rules) of every finished episode, in the order the reference prints them per agent;
- * the caller sizes it (max_log rows), *n_log returns the rows that would have been written.  Returns 0; *rounds_out = rounds run. */
+ * the caller sizes it (max_log rows; rows beyond it are dropped), *n_log returns the number of finished episodes (= the rows a large
+ * enough log receives).  No per-episode device-to-host traffic when both are NULL.  Returns 0; *rounds_out = rounds run. */
 int friq_team_run(friq_batch *b, int team, int max_rounds, double *log, long max_log, long *n_log, int *rounds_out)
 {
     friq_problem *P = b->P; const friq_devprob *hp = &P->hp;
@@ -1119,10 +1112,15 @@ int friq_team_run(friq_batch *b, int team, int max_rounds, double *log, long max
         if (!rc) rc = friqd_team_merge(hp, P->dp, b->st, team, 1, NULL);
         if (!rc) rc = friqd_device_sync();
     }
-    if (!rc && tmp) {                                                       /* stable sort by agent */
-        long o = 0;
-        for (long a = 0; a < n; a++)
-            for (long r = 0; r < rows; r++) if ((long)tmp[4 * r] == a) { if (log && o < max_log) memcpy(log + 4 * o, tmp + 4 * r, sizeof(double) * 4); o++; }
+    if (!rc && tmp && log) {                                                /* stable counting sort by agent: O(rows + n) */
+        long *start = (long *)calloc((size_t)n + 1, sizeof(long));
+        for (long r = 0; r < rows; r++) start[(long)tmp[4 * r] + 1]++;
+        for (long a = 0; a < n; a++) start[a + 1] += start[a];
+        for (long r = 0; r < rows; r++) {
+            const long o = start[(long)tmp[4 * r]]++;
+            if (o < max_log) memcpy(log + 4 * o, tmp + 4 * r, sizeof(double) * 4);
+        }
+        free(start);
     }
     if (n_log) *n_log = rows;
     if (rounds_out) *rounds_out = rounds;
@@ -1280,7 +1278,8 @@ int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double 
         for (int k = 0; k < K; k++) fprintf(f, "%.18f ", rant[(size_t)i * K + k]);
         fprintf(f, "%.18f \n", rconc[i]);
     }
-    fclose(f);
+    const int werr = ferror(f);
+    if (fclose(f) != 0 || werr) FAIL(-1, "%s: write failed", file_name);
     return 0;
 }
 /* frirl_save_rb_to_bin_file (frirl_utils.c:151-203): int32 R, then per rule K doubles + Q, host endian */
@@ -1291,7 +1290,8 @@ int friq_save_rb_to_bin_file(const char *file_name, int K, int R, const double *
     int32_t n = R;
     fwrite(&n, sizeof n, 1, f);
     for (int i = 0; i < R; i++) { fwrite(rant + (size_t)i * K, sizeof(double), K, f); fwrite(rconc + i, sizeof(double), 1, f); }
-    fclose(f);
+    const int werr = ferror(f);
+    if (fclose(f) != 0 || werr) FAIL(-1, "%s: write failed", file_name);
     return 0;
 }
 /* frirl_load_rb_from_bin_file (frirl_utils.c:228-281) */
@@ -1382,16 +1382,20 @@ int friq_batch_load_rb_file(friq_batch *b, long agent, const char *file_name)
     return rc;
 }
 
-/* Checkpoint of a whole batch in ONE file: header {magic "FRIQCKP1", int64 n_agents, int32 K, int32 reserved}, then per agent
+/* Checkpoint of a whole batch in ONE file: header {magic "FRIQCKP2", int64 n_agents, int32 K, int32 flags (bit 0: a weights
+ * section follows), int32 rule_capacity at save time (= doubles per agent in the weights section), int32 0}, then per agent
  * {int32 R, int32 fus_is_rule_inserted, R x (K antecedents + consequent) f64} - the per-agent record is the reference's binary
- * rule-base format (frirl_utils.c:175-203) with the sticky flag in front.  Like the reference, no episode state is saved. */
+ * rule-base format (frirl_utils.c:175-203) with the sticky flag in front - then, with flag bit 0, every agent's FIVERB.weights
+ * (rule_capacity f64 each).  A batch with another capacity re-strides the weights on load (every R must fit); the file must
+ * end after the last section.  Like the reference, no episode state is saved. */
 int friq_batch_save_checkpoint(friq_batch *b, const char *file_name)
 {
     const int K = b->P->hp.K, cap = b->st.cap; const long n = b->st.n, chunk = 1024;
     FILE *f = fopen(file_name, "wb");
     if (!f) { perror("friq_batch_save_checkpoint: open()"); FAIL(-1, "cannot open %s", file_name); }
     const long long n64 = n; const int32_t k32 = K, flags32 = b->st.wref ? 1 : 0;   /* bit 0: a FIVERB.weights section follows the records */
-    fwrite("FRIQCKP1", 1, 8, f); fwrite(&n64, 8, 1, f); fwrite(&k32, 4, 1, f); fwrite(&flags32, 4, 1, f);
+    const int32_t cap32 = cap, zero32 = 0;            /* stride of the weights section: rule_capacity doubles per agent */
+    fwrite("FRIQCKP2", 1, 8, f); fwrite(&n64, 8, 1, f); fwrite(&k32, 4, 1, f); fwrite(&flags32, 4, 1, f); fwrite(&cap32, 4, 1, f); fwrite(&zero32, 4, 1, f);
     int *R = (int *)malloc(sizeof(int) * chunk), *ins = (int *)malloc(sizeof(int) * n);
     double *rant = (double *)malloc(sizeof(double) * (size_t)chunk * cap * K), *rconc = (double *)malloc(sizeof(double) * (size_t)chunk * cap);
     int rc = friq_batch_get_inserted(b, ins);
@@ -1417,7 +1421,8 @@ int friq_batch_save_checkpoint(friq_batch *b, const char *file_name)
         free(t); free(o);
     }
     free(R); free(ins); free(rant); free(rconc);
-    if (fclose(f) != 0 && !rc) FAIL(-1, "%s: write failed", file_name);
+    const int werr = ferror(f);
+    if ((fclose(f) != 0 || werr) && !rc) FAIL(-1, "%s: write failed", file_name);
     return rc;
 }
 
@@ -1426,9 +1431,10 @@ int friq_batch_load_checkpoint(friq_batch *b, const char *file_name)
     const int K = b->P->hp.K, cap = b->st.cap; const long n = b->st.n;
     FILE *f = fopen(file_name, "rb");
     if (!f) { perror("friq_batch_load_checkpoint: open()"); FAIL(-1, "cannot open %s", file_name); }
-    char magic[8]; long long n64 = 0; int32_t k32 = 0, res = 0;
-    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "FRIQCKP1", 8) || fread(&n64, 8, 1, f) != 1 || fread(&k32, 4, 1, f) != 1 || fread(&res, 4, 1, f) != 1) {
-        fclose(f); FAIL(-1, "%s: not a FRIQCKP1 checkpoint", file_name);
+    char magic[8]; long long n64 = 0; int32_t k32 = 0, res = 0, wstride = 0, pad32 = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "FRIQCKP2", 8) || fread(&n64, 8, 1, f) != 1 || fread(&k32, 4, 1, f) != 1 || fread(&res, 4, 1, f) != 1 ||
+        fread(&wstride, 4, 1, f) != 1 || fread(&pad32, 4, 1, f) != 1 || wstride < 0) {
+        fclose(f); FAIL(-1, "%s: not a FRIQCKP2 checkpoint", file_name);
     }
     if (n64 != n || k32 != K) { fclose(f); FAIL(-1, "%s: checkpoint of %lld agents / K = %d, batch has %ld / %d", file_name, n64, k32, n, K); }
     double *rant = (double *)malloc(sizeof(double) * (size_t)cap * K), *rconc = (double *)malloc(sizeof(double) * cap);
@@ -1443,19 +1449,23 @@ int friq_batch_load_checkpoint(friq_batch *b, const char *file_name)
         ins[a] = i32;
     }
     if (!rc) rc = friq_batch_set_inserted(b, ins);
-    if (!rc && (res & 1)) {           /* FIVERB.weights section */
+    if (!rc && (res & 1)) {           /* FIVERB.weights section: `wstride` doubles per agent as saved, re-strided to this batch's capacity
+                                       * (every agent's R <= cap was checked above, so min(wstride, cap) covers all live weights) */
         rc = friq_batch_keep_weights(b);
         const size_t tile_slots = (size_t)cap * FRIQ_TILE;
-        double *t = (double *)calloc(tile_slots, 8), *o = (double *)malloc(sizeof(double) * cap);
+        const int ncopy = wstride < cap ? wstride : cap;
+        double *t = (double *)malloc(tile_slots * 8), *o = (double *)malloc(sizeof(double) * (wstride ? wstride : 1));
         for (long tl = 0; tl * FRIQ_TILE < n && !rc; tl++) {
+            memset(t, 0, tile_slots * 8);
             for (int l = 0; l < FRIQ_TILE && tl * FRIQ_TILE + l < n && !rc; l++) {
-                if (fread(o, 8, cap, f) != (size_t)cap) { snprintf(g_err, sizeof g_err, "%s: truncated weights section (checkpoint written with another rule capacity?)", file_name); rc = -1; break; }
-                for (int i = 0; i < cap; i++) t[(size_t)i * FRIQ_TILE + l] = o[i];
+                if (fread(o, 8, wstride, f) != (size_t)wstride) { snprintf(g_err, sizeof g_err, "%s: truncated weights section", file_name); rc = -1; break; }
+                for (int i = 0; i < ncopy; i++) t[(size_t)i * FRIQ_TILE + l] = o[i];
             }
             if (!rc) rc = friqd_h2d(b->st.wref + (size_t)tl * tile_slots, t, tile_slots * 8);
         }
         free(t); free(o);
     }
+    if (!rc && fgetc(f) != EOF) { snprintf(g_err, sizeof g_err, "%s: trailing bytes after the last section (corrupt checkpoint)", file_name); rc = -1; }
     fclose(f); free(rant); free(rconc); free(ins);
     return rc;
 }

@@ -60,6 +60,8 @@ SYMBOLS = {
     "friq_batch_run": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
     "friq_batch_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "friq_batch_set_retile_interval": (C.c_int, [C.c_void_p, C.c_long]),
+    "friq_batch_set_policy": (C.c_int, [C.c_void_p, C.c_int]),
+    "friq_batch_set_groups": (C.c_int, [C.c_void_p, C.c_int]),
     "friq_batch_gather": (C.c_int, [C.c_void_p, dp, ip, ip, ip, ip, llp, llp]),
     "friq_batch_gather_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "friq_batch_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -231,6 +233,12 @@ class Batch:
 
     def set_retile_interval(self, steps):
         _ck(lib().friq_batch_set_retile_interval(self.h, int(steps)))
+
+    def set_policy(self, policy):
+        _ck(lib().friq_batch_set_policy(self.h, int(policy)))
+
+    def set_groups(self, groups):
+        _ck(lib().friq_batch_set_groups(self.h, int(groups)))
 
     def sync(self, stream=None):
         _ck(lib().friq_batch_sync(self.h, stream))

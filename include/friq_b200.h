@@ -111,6 +111,12 @@ int friq_batch_get_inserted(friq_batch *b, int *inserted);
  * (a cudaStream_t passed as void*, NULL = default stream). */
 int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream);
 int friq_batch_sync(friq_batch *b, void *stream);
+/* evaluation policy of the fused kernel: 0 lock-step pass over all actions, 1 exact hits first + compacted Shepard chains,
+ * 2 the same with memoised weights (table mode; the default where the problem qualifies).  Placement / evaluation strategy only:
+ * results are bit-identical under every policy. */
+int friq_batch_set_policy(friq_batch *b, int policy);
+/* agent groups of a re-tiled run (each sorted by rule count and launched on its own stream); 0 = default */
+int friq_batch_set_groups(friq_batch *b, int groups);
 /* with FRIQ_RUN_RETILE a run is split into launches of `steps` env steps with a re-tiling before each (default 125; 0 = once per run) */
 int friq_batch_set_retile_interval(friq_batch *b, long steps);
 /* results -> host arrays of n_agents (any pointer may be NULL): last finished episode's total reward /

@@ -149,7 +149,7 @@ def test_construct_run_reproduces_reference_golden(fq, env):
     b.close()
 
 
-@pytest.mark.parametrize("name", ["mountaincar", "acrobot"])
+@pytest.mark.parametrize("name", ["mountaincar", "acrobot", "cartpole"])
 def test_random_exploration_matches_oracle_port(fq, name):
     """epsilon-greedy with the Philox stream: per-agent seeds, per-agent hyper-parameters, chunked
     launches (state must survive kernel boundaries); every agent equals the oracle port bit for bit."""
@@ -159,7 +159,7 @@ def test_random_exploration_matches_oracle_port(fq, name):
     alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.01, 0.05, 0.2], n)
     b = fq.Batch(P, n, CAP[name], seed0=0x5EED0000, first_agent=first)
     b.set_hyper(alpha, gamma, eps)
-    steps = 1500 if name == "mountaincar" else 700
+    steps = {"mountaincar": 1500, "acrobot": 700, "cartpole": 900}[name]
     for chunk, mode in ((1, fq.RUN_LEARN), (7, fq.RUN_LEARN | fq.RUN_RETILE), (steps - 508, fq.RUN_LEARN),
                         (250, fq.RUN_LEARN | fq.RUN_RETILE), (250, fq.RUN_LEARN | fq.RUN_RETILE)):
         b.run(chunk, mode)                              # re-tiling by rule count must not change any agent's results
@@ -178,25 +178,29 @@ def test_random_exploration_matches_oracle_port(fq, name):
     b.close(); P.close()
 
 
-@pytest.mark.parametrize("name,policy", [("mountaincar", 0), ("mountaincar", 1), ("mountaincar", 2), ("acrobot", 1), ("acrobot", 2)])
-def test_every_evaluation_policy_matches_oracle(fq, name, policy, monkeypatch):
-    """The fused kernel has three evaluation policies (FRIQ_POLICY): 0 lock-step pass over all actions (+ hit sweep /
-    compacted sums when few pairs lack an exact hit), 1 three warps per tile, 2 hit sweep + compacted Shepard sums only
-    (mountaincar's default).  All of them must reproduce the oracle bit for bit - here on a hard mix: a partial last
+@pytest.mark.parametrize("name,policy", [("mountaincar", 0), ("mountaincar", 1), ("mountaincar", 2), ("acrobot", 0), ("acrobot", 1),
+                                         ("acrobot", 2), ("cartpole", 0)])
+def test_every_evaluation_policy_matches_oracle(fq, name, policy):
+    """The fused kernel has three evaluation policies (friq_batch_set_policy): 0 lock-step pass over all actions (+ hit sweep /
+    compacted sums when few pairs lack an exact hit; cartpole's A = 21 pass runs in 7 chunks of 3 actions with the Q(s,a) chain
+    in chunk 0 or served cooperatively), 1 exact hits first + compacted Shepard chains, 2 the same with memoised weights
+    (mountaincar's and acrobot's default).  All of them must reproduce the oracle bit for bit - here on a hard mix: a partial last
     warp (70 agents), random OFF-GRID episode start states (no exact hit possible at episode start: every pair needs its
-    Shepard sums), heavy exploration, per-agent hyper-parameters, chunked and re-tiled launches."""
-    monkeypatch.setenv("FRIQ_POLICY", str(policy))
+    Shepard sums), heavy exploration (divergent lanes, different rule counts per lane, partial Q(s,a) masks), per-agent
+    hyper-parameters, chunked and re-tiled launches.  Reference: frirl_get_best_action.c:212-281 (the loop over actions),
+    examples/cartpole/cartpole.c:114-168 (the off-grid quantiser)."""
     P = fq.Problem(name, no_random=0)
     n, first = 70, 7
     rng = np.random.default_rng(100 + policy)
     alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.02, 0.1, 0.3], n)
-    lo = {"mountaincar": [-1.2, -0.05], "acrobot": [-1.0, -1.0, -0.5, -0.5]}[name]
-    hi = {"mountaincar": [0.3, 0.05], "acrobot": [1.0, 1.0, 0.5, 0.5]}[name]
+    lo = {"mountaincar": [-1.2, -0.05], "acrobot": [-1.0, -1.0, -0.5, -0.5], "cartpole": [-1.0, -0.6, -0.12, -0.6]}[name]
+    hi = {"mountaincar": [0.3, 0.05], "acrobot": [1.0, 1.0, 0.5, 0.5], "cartpole": [1.0, 0.6, 0.12, 0.6]}[name]
     s0 = rng.uniform(lo, hi, size=(n, P.S))
     b = fq.Batch(P, n, CAP[name], seed0=0x5EED0000, first_agent=first)
+    b.set_policy(policy)
     b.set_hyper(alpha, gamma, eps)
     b.set_initial_state(s0)
-    steps = 900 if name == "mountaincar" else 400
+    steps = {"mountaincar": 900, "acrobot": 400, "cartpole": 600}[name]
     for chunk, mode in ((3, fq.RUN_LEARN), (steps - 303, fq.RUN_LEARN | fq.RUN_RETILE), (300, fq.RUN_LEARN | fq.RUN_RETILE)):
         b.run(chunk, mode)
     o = b.gather()
@@ -275,18 +279,18 @@ def test_table_mode_survives_dictionary_growth_and_odd_capacity(fq):
 
 
 @pytest.mark.parametrize("name", ["mountaincar", "acrobot"])
-def test_table_mode_equals_computed_chains(fq, name, monkeypatch):
+def test_table_mode_equals_computed_chains(fq, name):
     """The looked-up weights ARE the computed ones: a larger batch than the oracle comparisons afford, run once in table
-    mode (default) and once with the table disabled (FRIQ_NO_WTAB=1: integer hit sweep + computed sqrt / x87 power /
-    reciprocal chains); every rule base, return and step count must be identical."""
+    mode (policy 2, the default) and once with policy 1 (integer hit sweep + computed sqrt / x87 power / reciprocal chains);
+    every rule base, return and step count must be identical."""
     n, steps = 4096 + 17, 1200 if name == "mountaincar" else 500
     rng = np.random.default_rng(8)
     alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.01, 0.05, 0.2], n)
     res = []
-    for off in ("0", "1"):
-        monkeypatch.setenv("FRIQ_NO_WTAB", off)
+    for policy in (2, 1):
         P = fq.Problem(name, no_random=0)
         b = fq.Batch(P, n, CAP[name], seed0=4242, first_agent=0)
+        b.set_policy(policy)
         b.set_hyper(alpha, gamma, eps)
         for chunk in (steps // 3, steps - steps // 3):
             b.run(chunk, fq.RUN_LEARN | fq.RUN_RETILE)
@@ -358,6 +362,25 @@ def test_merge_rb_per_call_matches_oracle(fq, tmp_path):
         if i != 7:
             assert Ra == Rb and np.array_equal(ra, rb_) and np.array_equal(qa, qb), i
     b2.close()
+    # a batch with ANOTHER rule capacity re-strides the saved FIVERB.weights (the header carries the capacity at save time);
+    # a batch too small for a saved rule base and a file with trailing bytes are rejected
+    b3 = fq.Batch(P, n, 301, seed0=1, first_agent=0)
+    b3.load_checkpoint(ck)
+    b3.merge_rb(rant, rconc)
+    for i in (0, 22, 39):
+        Ra, ra, qa = b.get_rulebase(i); Rb, rb_, qb = b3.get_rulebase(i)
+        assert Ra == Rb and np.array_equal(ra, rb_) and np.array_equal(qa, qb), i
+    b3.close()
+    b4 = fq.Batch(P, n, 12, seed0=1, first_agent=0)
+    with pytest.raises(fq.FriqError):
+        b4.load_checkpoint(ck)
+    b4.close()
+    with open(ck, "ab") as f:
+        f.write(b"\0" * 8)
+    b5 = fq.Batch(P, n, 256, seed0=1, first_agent=0)
+    with pytest.raises(fq.FriqError):
+        b5.load_checkpoint(ck)
+    b5.close()
     OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
     for i in range(n):
         a = _oracle.Agent(OP, 256, seed=0x5EED0000 + first + i)
@@ -572,6 +595,35 @@ def test_full_size_batch_properties(fq):
     for x in (whole, lo, hi):
         x.close()
     P.close()
+
+
+def test_bench_workload_matches_oracle_on_sampled_agents(fq):
+    """The bench workload itself (bench.py, BASELINE configs[2]): 65,536 mountaincar agents, eps = 0.01 (Philox), learning from the
+    corner rule base for 6,250 env steps (25 bench steps x 250), re-tiled every 125 steps in two stream groups - exactly the
+    driver's `--steps 20 --warmup 5` run.  48 randomly chosen agents (plus the first and the last) must end with the oracle
+    port's rule base, return, step and rule-sum counters bit for bit."""
+    n, chunk, nchunks = 65536, 250, 25
+    P = fq.Problem("mountaincar", no_random=0)
+    b = fq.Batch(P, n, 192, seed0=0x5EED0000, first_agent=0)
+    b.set_retile_interval(125)
+    for _ in range(nchunks):
+        b.run(chunk, fq.RUN_LEARN | fq.RUN_RETILE)
+    o = b.gather()
+    assert int(o["total_steps"].sum()) == n * chunk * nchunks
+    assert not np.any(o["flags"] & fq.F_OVERFLOW)
+    rng = np.random.default_rng(20261019)
+    picks = sorted(set([0, n - 1] + [int(x) for x in rng.integers(0, n, 48)]))
+    OP = _oracle.Problem(0, trig=1); OP.set_no_random(0)
+    for i in picks:
+        a = _oracle.Agent(OP, 192, seed=0x5EED0000 + i)
+        a.run_steps(chunk * nchunks)
+        sm = a.summary()
+        R, rant, rconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(rant, orant) and np.array_equal(rconc, orconc), i
+        assert (o["episodes"][i], o["last_steps"][i], o["last_return"][i], o["total_steps"][i], o["sum_rules"][i]) == \
+            (sm["episode_num"] - 1, sm["last_steps"], sm["last_return"], sm["total_steps"], sm["sum_rules"]), i
+    b.close(); P.close()
 
 
 def test_shared_rule_base_at_config4_size_matches_oracle_samples(fq):

@@ -2,10 +2,10 @@
 # run bench.py for every engine variant built by tools/build_variants.sh (on the GPU box); one line per variant / setting
 cd "$(dirname "$0")/.."
 for so in fri-reinforcementlearning-c_b200/build/variants/friq_*.so; do
-  for g in ${GROUPS_LIST:-2}; do
-   for hp in ${HEAVY_LIST:-20}; do
-    r=$(FRIQ_HEAVY_PCT=$hp FRIQ_GROUPS=$g FRIQ_LIB=$PWD/$so python bench.py --steps ${STEPS:-6} --warmup 3 --no-cpu-baseline ${BENCH_ARGS} 2>&1 | tail -1)
-    echo "$(basename $so) groups=$g heavy=$hp $(echo "$r" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("value=%.4g e2e=%.4g frac=%.3f meanR=%.1f" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["config"]["mean_rules_in_timed_region"]))' 2>&1 | tail -1)"
-   done
+  for g in ${GROUPS_LIST:-0}; do
+   {
+    r=$(FRIQ_LIB=$PWD/$so python bench.py --steps ${STEPS:-6} --warmup 3 --no-cpu-baseline --groups $g ${BENCH_ARGS} 2>&1 | tail -1)
+    echo "$(basename $so) groups=$g $(echo "$r" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("value=%.4g e2e=%.4g frac=%.3f meanR=%.1f" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["config"]["mean_rules_in_timed_region"]))' 2>&1 | tail -1)"
+   }
   done
 done

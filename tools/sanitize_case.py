@@ -11,10 +11,10 @@ for name, cap, steps in (("mountaincar", 192, 260), ("acrobot", 704, 120), ("car
     for policy in (0, 1, 2):
         if name == "cartpole" and policy:
             continue
-        os.environ["FRIQ_POLICY"] = str(policy)
         P = fq.Problem(name, no_random=0)
         n = 70
         b = fq.Batch(P, n, cap, seed0=3)
+        b.set_policy(policy)
         b.set_hyper(np.full(n, 0.5), np.ones(n), np.full(n, 0.1))
         b.run(steps, fq.RUN_LEARN | fq.RUN_RETILE)
         b.run(37, fq.RUN_LEARN)
@@ -22,7 +22,6 @@ for name, cap, steps in (("mountaincar", 192, 260), ("acrobot", 704, 120), ("car
         st = np.zeros((n, P.S)); hit, conc = b.vag_concl(np.zeros((n, P.K))); best, ac = b.best_action(st)
         print(name, policy, "rules", o["rules"].min(), o["rules"].max(), "steps", int(o["total_steps"].sum()))
         b.close(); P.close()
-del os.environ["FRIQ_POLICY"]
 P = fq.Problem("mountaincar")
 b = fq.Batch(P, 40, 192)
 b.run(2000, fq.RUN_LEARN | fq.RUN_STOP_AT_EPISODE_END)
