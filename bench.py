@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--agents", type=int, default=65536, help="agents per GPU")
     ap.add_argument("--chunk", type=int, default=250, help="env steps per agent per bench step (one kernel launch)")
     ap.add_argument("--retile", type=int, default=125, help="env steps between re-tilings by rule count inside a step (0 = once per step)")
+    ap.add_argument("--groups", type=int, default=0, help="agent groups on their own streams (0 = the engine's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -167,7 +168,9 @@ def main():
     b = fq.Batch(P, n, 192, device=local, seed0=0x5EED0000, first_agent=first_agent)
     b.set_retile_interval(args.retile)
     launches_per_step = (-(-args.chunk // args.retile) if args.retile > 0 else 1)
-    groups = int(os.environ.get("FRIQ_GROUPS", 0)) or min(8, max(1, n // 32768))     # friq_batch_create: agent groups on their own streams
+    groups = args.groups or min(8, max(1, n // 32768))     # friq_batch_create: agent groups on their own streams
+    if args.groups:
+        b.set_groups(args.groups)
     mode = fq.RUN_LEARN | fq.RUN_RETILE      # agents are re-assigned to warps by rule count before every launch
 
     # the path's only exchange: per-agent (return f64, steps i32, rules i32) + rule-base statistics, ONE all-gather per step
@@ -280,7 +283,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         # per group and launch: 4 re-tiling kernels (histogram, scan, assign, move) + k_refresh_index (table mode) + k_run_steps;
         # per step: 3 result un-permute kernels
-        "gpu_launches": args.steps * ((5 if os.environ.get("FRIQ_NO_WTAB", "0") not in ("", "0") else 6) * launches_per_step * groups + 3),
+        "gpu_launches": args.steps * (6 * launches_per_step * groups + 3),
         "clocks": clocks,
         "roofline": {"bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",
                      "achieved": ach_tflops if frac_fp64 >= frac_hbm else ach_gbs,

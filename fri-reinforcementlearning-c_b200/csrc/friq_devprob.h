@@ -118,6 +118,7 @@ int friqd_h2d_async(void *dst, const void *src, unsigned long bytes, void *strea
 int friqd_d2h_async(void *dst, const void *src, unsigned long bytes, void *stream);
 int friqd_device_count(int *count);
 int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const double *d_q, int R, void *stream);
+int friqd_set_s0(friq_devstate st, const double *d_s0, int S, void *stream);
 int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules, void *stream);
 int friqd_unpermute(friq_devstate st, const void *src, void *dst, int elem_bytes, void *stream);
 int friqd_stream_create(void **s);
@@ -133,6 +134,10 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
                       double alpha, double gamma, double epsilon, void *stream);
 int friqd_run_steps(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, int variant, void *stream);
 int friqd_run_shared(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, long n_steps, int mode, void *stream);
+int friqd_shared_memo_build(const friq_devprob *hprob, const friq_devprob *dprob, const double *d_srb, int Rs, double *d_memo, int cells, void *stream);
+int friqd_shared_start(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, double *d_start, void *stream);
+int friqd_run_shared_memo(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_memo, const double *d_start,
+                          int Rs, long n_steps, int mode, void *stream);
 int friqd_vag_concl(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_conc, int *d_hit,
                     double *d_weights, void *stream);
 int friqd_best_action(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_states, double *d_actconc,

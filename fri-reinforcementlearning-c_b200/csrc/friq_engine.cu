@@ -321,25 +321,105 @@ __device__ __forceinline__ void friq_mbar_wait(uint64_t *mbar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
 
+// One pass of every thread's observation (VE values vc[]) over the shared rule base: conclusions of all A actions
+// (FIVEVagConcl_FRIRL_BestAct.c:89-93, :212-217, :265).  CTA-wide: every thread of the CTA must call it (threads without an
+// agent pass any finite vc[]); `parity` carries the ring's mbarrier phases from call to call.
+template <int S, int P, int A, int UNR, bool SAFE>
+__device__ __forceinline__ void friq_shared_pass(double (*tile)[FRIQ_SRB_TILE * (S + 2)], uint64_t *full, uint32_t &parity,
+                                                 const double *__restrict__ srb, int Rs, const double *vc, const double *ave, double *actconc)
+{
+    constexpr int K = S + 1, RW = K + 1;
+    const int ntiles = (Rs + FRIQ_SRB_TILE - 1) / FRIQ_SRB_TILE;
+    double vagc[A], ws[A], hq[A];
+    unsigned hitmask = 0;
+#pragma unroll
+    for (int a = 0; a < A; a++) { vagc[a] = 0.0; ws[a] = 0.0; hq[a] = 0.0; }
+    if (threadIdx.x == 0)
+        for (int t = 0; t < 2 && t < ntiles; t++) {
+            const int cnt = min(FRIQ_SRB_TILE, Rs - t * FRIQ_SRB_TILE);
+            friq_tma_load(tile[t], srb + (size_t)t * FRIQ_SRB_TILE * RW, (uint32_t)(cnt * RW * sizeof(double)), &full[t]);
+        }
+    for (int t = 0; t < ntiles; t++) {
+        const int bsel = t & 1, cnt = min(FRIQ_SRB_TILE, Rs - t * FRIQ_SRB_TILE);
+        friq_mbar_wait(&full[bsel], (parity >> bsel) & 1u);
+        parity ^= 1u << bsel;
+        const double *tb = tile[bsel];
+#pragma unroll 1
+        for (int i = 0; i < cnt; i += UNR) {
+            constexpr int NC = UNR * A;              // all chains of the trip, evaluated stage by stage
+            double sv[NC], wv[NC], dv[NC], q[UNR]; bool live[NC];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const double *r = tb + (size_t)min(i + u, cnt - 1) * RW;
+                double ssum = 0.0;
+#pragma unroll
+                for (int k = 0; k < S; k++) {
+                    const double d = __dsub_rn(vc[k], r[k]);
+                    const double d2 = __dmul_rn(d, d);
+                    ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);
+                }
+                q[u] = r[K];
+#pragma unroll
+                for (int a = 0; a < A; a++) {
+                    const double da = __dsub_rn(ave[a], r[S]);
+                    sv[u * A + a] = __dadd_rn(__dmul_rn(da, da), ssum);
+                    live[u * A + a] = !friq_is_zero(sv[u * A + a]);
+                }
+            }
+            unsigned bad = 0;
+            friq_shepard_weights_n<P, SAFE, NC>(sv, wv, bad, live, dv);
+            if (bad) {
+#pragma unroll
+                for (int n = 0; n < NC; n++)
+                    if ((bad >> n) & 1u) wv[n] = SAFE ? friq_shepard_weight_from_sqrt<P>(dv[n]) : friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                if (u == 0 || i + u < cnt) {
+#pragma unroll
+                    for (int a = 0; a < A; a++) {
+                        if (!live[u * A + a] && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q[u]; }
+                        vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u * A + a], q[u]));
+                        ws[a] = __dadd_rn(ws[a], wv[u * A + a]);
+                    }
+                }
+            }
+        }
+        __syncthreads();                             // everyone is done with tile[bsel]
+        if (threadIdx.x == 0 && t + 2 < ntiles) {
+            const int c2 = min(FRIQ_SRB_TILE, Rs - (t + 2) * FRIQ_SRB_TILE);
+            friq_tma_load(tile[bsel], srb + (size_t)(t + 2) * FRIQ_SRB_TILE * RW, (uint32_t)(c2 * RW * sizeof(double)), &full[bsel]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < A; a++) actconc[a] = ((hitmask >> a) & 1u) ? hq[a] : __ddiv_rn(vagc[a], ws[a]);
+}
+
+#define FRIQ_SHARED_PROLOGUE()                                                                                          \
+    __shared__ friq_smem_t sm;                                                                                        \
+    __shared__ __align__(16) double tile[2][FRIQ_SRB_TILE * (S + 2)];                                                 \
+    __shared__ uint64_t full[2];                                                                                      \
+    friq_stage_problem(gprob, sm.prob, &sm.mbar);                                                                     \
+    const friq_devprob &pb = *reinterpret_cast<const friq_devprob *>(sm.prob);                                        \
+    if (threadIdx.x == 0) {                                                                                           \
+        for (int j = 0; j < 2; j++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full[j]))); \
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                                            \
+    }                                                                                                                 \
+    __syncthreads();                                                                                                  \
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;                                                      \
+    const bool valid = ag < st.n;                                                                                     \
+    const long ia = valid ? ag : 0;                                                                                   \
+    uint32_t parity = 0;                                 /* bit j = phase of full[j] */
+
+// The general stepping kernel: one full pass over the shared rule base per env step (policy 0).  Since the quantised
+// observations of the built-in environments live on the grid, the default is k_infer_memo below; this kernel stays as the
+// reference it is compared with (tests/test_gpu_parity.py) and for the roofline of the streaming pass itself.
 template <int S, int P, int A, int ENV, int UNR, bool SAFE>
 __global__ void __launch_bounds__(FRIQ_BLOCK, 2)
 k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ srb, int Rs, long n_steps, int mode)
 {
-    constexpr int K = S + 1, RW = K + 1;
-    __shared__ friq_smem_t sm;
-    __shared__ __align__(16) double tile[2][FRIQ_SRB_TILE * RW];
-    __shared__ uint64_t full[2];
-    friq_stage_problem(gprob, sm.prob, &sm.mbar);
-    const friq_devprob &pb = *reinterpret_cast<const friq_devprob *>(sm.prob);
-    if (threadIdx.x == 0) {
-        for (int j = 0; j < 2; j++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full[j])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = ag < st.n;
-    const long ia = valid ? ag : 0;
-
+    constexpr int K = S + 1;
+    FRIQ_SHARED_PROLOGUE();
     double s[S], qs[K], vo[K];                           // vo: VE values of qs[], kept like k_run_steps keeps them (a learning launch may follow)
 #pragma unroll
     for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ia];
@@ -352,8 +432,9 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
     unsigned long long total_steps = st.total_steps[ia], sum_rules = st.sum_rules[ia];
     const unsigned long long seed = st.seed[ia];
     const double epsilon = st.epsilon[ia];
-    const int ntiles = (Rs + FRIQ_SRB_TILE - 1) / FRIQ_SRB_TILE;
-    uint32_t parity = 0;                                 // bit j = phase of full[j]
+    double ave[A];
+#pragma unroll
+    for (int a = 0; a < A; a++) ave[a] = pb.act_ve[a];
 
     long done_steps = 0;
     bool running = valid;
@@ -382,71 +463,8 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
             for (int k = 0; k < S; k++) { cur[k] = s[k]; cq[k] = qs[k]; vc[k] = 0.0; }
             running = false;
         }
-        // ---- one pass over the shared rule base: all A actions, UNR rules per trip
-        double vagc[A], ws[A], hq[A], ave[A];
-        unsigned hitmask = 0;
-#pragma unroll
-        for (int a = 0; a < A; a++) { vagc[a] = 0.0; ws[a] = 0.0; hq[a] = 0.0; ave[a] = pb.act_ve[a]; }
-        if (threadIdx.x == 0)
-            for (int t = 0; t < 2 && t < ntiles; t++) {
-                const int cnt = min(FRIQ_SRB_TILE, Rs - t * FRIQ_SRB_TILE);
-                friq_tma_load(tile[t], srb + (size_t)t * FRIQ_SRB_TILE * RW, (uint32_t)(cnt * RW * sizeof(double)), &full[t]);
-            }
-        for (int t = 0; t < ntiles; t++) {
-            const int bsel = t & 1, cnt = min(FRIQ_SRB_TILE, Rs - t * FRIQ_SRB_TILE);
-            friq_mbar_wait(&full[bsel], (parity >> bsel) & 1u);
-            parity ^= 1u << bsel;
-            const double *tb = tile[bsel];
-#pragma unroll 1
-            for (int i = 0; i < cnt; i += UNR) {
-                constexpr int NC = UNR * A;              // all chains of the trip, evaluated stage by stage
-                double sv[NC], wv[NC], dv[NC], q[UNR]; bool live[NC];
-#pragma unroll
-                for (int u = 0; u < UNR; u++) {
-                    const double *r = tb + (size_t)min(i + u, cnt - 1) * RW;
-                    double ssum = 0.0;
-#pragma unroll
-                    for (int k = 0; k < S; k++) {
-                        const double d = __dsub_rn(vc[k], r[k]);
-                        const double d2 = __dmul_rn(d, d);
-                        ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);
-                    }
-                    q[u] = r[K];
-#pragma unroll
-                    for (int a = 0; a < A; a++) {
-                        const double da = __dsub_rn(ave[a], r[S]);
-                        sv[u * A + a] = __dadd_rn(__dmul_rn(da, da), ssum);
-                        live[u * A + a] = !friq_is_zero(sv[u * A + a]);
-                    }
-                }
-                unsigned bad = 0;
-                friq_shepard_weights_n<P, SAFE, NC>(sv, wv, bad, live, dv);
-                if (bad) {
-#pragma unroll
-                    for (int n = 0; n < NC; n++)
-                        if ((bad >> n) & 1u) wv[n] = SAFE ? friq_shepard_weight_from_sqrt<P>(dv[n]) : friq_shepard_weight_slow<P>(live[n] ? sv[n] : 1.0);
-                }
-#pragma unroll
-                for (int u = 0; u < UNR; u++) {
-                    if (u == 0 || i + u < cnt) {
-#pragma unroll
-                        for (int a = 0; a < A; a++) {
-                            if (!live[u * A + a] && !((hitmask >> a) & 1u)) { hitmask |= 1u << a; hq[a] = q[u]; }
-                            vagc[a] = __dadd_rn(vagc[a], __dmul_rn(wv[u * A + a], q[u]));
-                            ws[a] = __dadd_rn(ws[a], wv[u * A + a]);
-                        }
-                    }
-                }
-            }
-            __syncthreads();                             // everyone is done with tile[bsel]
-            if (threadIdx.x == 0 && t + 2 < ntiles) {
-                const int c2 = min(FRIQ_SRB_TILE, Rs - (t + 2) * FRIQ_SRB_TILE);
-                friq_tma_load(tile[bsel], srb + (size_t)(t + 2) * FRIQ_SRB_TILE * RW, (uint32_t)(c2 * RW * sizeof(double)), &full[bsel]);
-            }
-        }
         double actconc[A];
-#pragma unroll
-        for (int a = 0; a < A; a++) actconc[a] = ((hitmask >> a) & 1u) ? hq[a] : __ddiv_rn(vagc[a], ws[a]);
+        friq_shared_pass<S, P, A, UNR, SAFE>(tile, full, parity, srb, Rs, vc, ave, actconc);
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         if (act && initial) {
             aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
@@ -468,6 +486,156 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
         }
     }
     if (!valid) return;
+#pragma unroll
+    for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
+#pragma unroll
+    for (int k = 0; k < K; k++) { st.qs[(size_t)k * st.n_pad + ag] = qs[k]; st.vo[(size_t)k * st.n_pad + ag] = vo[k]; }
+    st.aidx[ag] = aidx; st.flags[ag] = flags; st.step_in_ep[ag] = step_in_ep; st.hitq[ag] = -2;
+    st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
+    st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
+    st.total_steps[ag] = total_steps; st.sum_rules[ag] = sum_rules;
+}
+
+// ---- Memoised conclusions (BASELINE config 4).  The shared rule base is read-only and, after the first step of an episode, an
+// agent's observation is a GRID point (the quantisers of mountaincar.c:98-125 / acrobot.c:165-192 return values[where]): the
+// conclusion of (observation cell, action) against the whole rule base is a constant of the batch.  k_shared_memo_build
+// evaluates it once per cell and action - same chains, same rule order, so bit for bit what k_infer_shared computes on every
+// step - and k_shared_start does the one pass left per agent: the conclusions at its (off-grid) episode start state.
+// Stepping (k_infer_memo) is then dynamics + A table reads.
+//
+// memo[cell * A + a], cell = sum_k grid_index_k * stride_k (stride_0 = 1).  One WARP per (cell, action): the 32 lanes evaluate
+// the weights of 32 consecutive rules in parallel (library-exact chain), then the sums are added in rule order (every lane adds
+// the same shuffled values), stopping at the first rule at distance 0.
+template <int S, int P>
+__global__ void __launch_bounds__(128)
+k_shared_memo_build(const friq_devprob *__restrict__ gprob, const double *__restrict__ srb, int Rs, double *__restrict__ memo, int cells, int A)
+{
+    constexpr int K = S + 1, RW = K + 1;
+    const int lane = threadIdx.x & 31;
+    const long wi = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wi >= (long)cells * A) return;
+    int cell = (int)(wi / A); const int a = (int)(wi % A);
+    double vc[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) { const int n = gprob->grid_len[k]; vc[k] = gprob->dict_ve[k][cell % n]; cell /= n; }
+    const double ave = gprob->act_ve[a];
+    double vag = 0.0, ws = 0.0, hq = 0.0; bool hit = false;
+    for (int base = 0; base < Rs && !hit; base += 32) {
+        const int i = base + lane; const bool in = i < Rs;
+        const double *r = srb + (size_t)(in ? i : Rs - 1) * RW;
+        double ssum = 0.0;
+#pragma unroll
+        for (int k = 0; k < S; k++) {
+            const double d = __dsub_rn(vc[k], r[k]);
+            const double d2 = __dmul_rn(d, d);
+            ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);
+        }
+        const double da = __dsub_rn(ave, r[S]);
+        const double sv = __dadd_rn(__dmul_rn(da, da), ssum);
+        const double q = r[K];
+        const bool zero = in && friq_is_zero(sv);
+        const double w = zero ? 0.0 : friq_shepard_weight<P>(sv);
+        const double wq = __dmul_rn(w, q);
+        const unsigned zm = __ballot_sync(0xffffffffu, zero);
+        if (zm) { hit = true; hq = __shfl_sync(0xffffffffu, q, __ffs(zm) - 1); break; }      // BestAct.c:89-93: first rule at distance 0
+        const int cnt = min(32, Rs - base);
+        for (int j = 0; j < cnt; j++) {
+            vag = __dadd_rn(vag, __shfl_sync(0xffffffffu, wq, j));                             // :216
+            ws = __dadd_rn(ws, __shfl_sync(0xffffffffu, w, j));                                // :217
+        }
+    }
+    if (lane == 0) memo[wi] = hit ? hq : __ddiv_rn(vag, ws);                                   // :265
+}
+
+// conclusions of all actions at every agent's episode start state (frirl_episode.c:46-48, :78: the first action is chosen from
+// the RAW start state): start[a * n_pad + agent]
+template <int S, int P, int A, int UNR, bool SAFE>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 2)
+k_shared_start(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ srb, int Rs, double *__restrict__ start)
+{
+    FRIQ_SHARED_PROLOGUE();
+    double vc[S], ave[A], actconc[A];
+#pragma unroll
+    for (int k = 0; k < S; k++) vc[k] = st.s0 ? friq_obs_ve(pb, k, st.s0[(size_t)k * st.n_pad + ia]) : pb.ve_def[k];
+#pragma unroll
+    for (int a = 0; a < A; a++) ave[a] = pb.act_ve[a];
+    friq_shared_pass<S, P, A, UNR, SAFE>(tile, full, parity, srb, Rs, vc, ave, actconc);
+    if (!valid) return;
+#pragma unroll
+    for (int a = 0; a < A; a++) start[(size_t)a * st.n_pad + ag] = actconc[a];
+}
+
+// greedy / epsilon-greedy stepping on memoised conclusions: per env step the dynamics, the quantiser and A table reads
+template <int S, int A, int ENV>
+__global__ void __launch_bounds__(FRIQ_BLOCK)
+k_infer_memo(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ memo, const double *__restrict__ start,
+             int Rs, long n_steps, int mode)
+{
+    constexpr int K = S + 1;
+    FRIQ_SMEM_PROLOGUE();
+    (void)rbw; (void)rbq; (void)sw;
+    double s[S], qs[K], vo[K];
+#pragma unroll
+    for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ag];
+#pragma unroll
+    for (int k = 0; k < K; k++) { qs[k] = st.qs[(size_t)k * st.n_pad + ag]; vo[k] = st.vo[(size_t)k * st.n_pad + ag]; }
+    int aidx = st.aidx[ag], flags = st.flags[ag], step_in_ep = st.step_in_ep[ag];
+    uint32_t ep_num = st.ep_num[ag];
+    double ep_return = st.ep_return[ag], last_return = st.last_return[ag];
+    int last_steps = st.last_steps[ag], last_rules = st.last_rules[ag];
+    unsigned long long total_steps = st.total_steps[ag], sum_rules = st.sum_rules[ag];
+    const unsigned long long seed = st.seed[ag];
+    const double epsilon = st.epsilon[ag];
+    int stride[S];
+    { int m = 1;
+#pragma unroll
+      for (int k = 0; k < S; k++) { stride[k] = m; m *= pb.grid_len[k]; } }
+    long done_steps = 0;
+    bool running = true;
+    while (running && done_steps < n_steps) {
+        const bool initial = flags & FRIQ_F_NEED_RESET;
+        double cur[S], cq[S], vc[S], actconc[A], reward = 0.0; int done = 0, ci[S];
+        if (initial) {                                   // frirl_episode.c:46-82
+#pragma unroll
+            for (int k = 0; k < S; k++) {
+                s[k] = qs[k] = st.s0 ? st.s0[(size_t)k * st.n_pad + ag] : pb.values_def[k];
+                vc[k] = st.s0 ? friq_obs_ve_cold(&pb, k, s[k]) : pb.ve_def[k];
+                cur[k] = cq[k] = s[k];
+            }
+#pragma unroll
+            for (int a = 0; a < A; a++) actconc[a] = start[(size_t)a * st.n_pad + ag];
+            ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
+        } else {                                         // frirl_episode.c:97-112
+            friq_env_step<ENV>(pb.act_val[aidx], s, cur);
+            friq_env_reward<ENV>(cur, reward, done);
+            ep_return = __dadd_rn(ep_return, reward);
+            friq_env_quantize<ENV, S>(pb, cur, cq, vc, ci);
+            step_in_ep++;
+            int cell = 0;
+#pragma unroll
+            for (int k = 0; k < S; k++) cell += ci[k] * stride[k];
+#pragma unroll
+            for (int a = 0; a < A; a++) actconc[a] = __ldg(memo + (size_t)cell * A + a);
+        }
+        const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
+#pragma unroll
+        for (int k = 0; k < S; k++) vo[k] = vc[k];
+        vo[S] = pb.act_ve_eval[a2];
+        if (initial) { aidx = a2; qs[S] = pb.act_val[a2]; }
+        else {
+            sum_rules += (unsigned long long)Rs;
+#pragma unroll
+            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; }
+            aidx = a2; qs[S] = pb.act_val[a2];
+            total_steps++; done_steps++;
+            if (done || step_in_ep >= pb.max_steps) {
+                last_return = ep_return; last_steps = step_in_ep; last_rules = Rs;
+                ep_num++;
+                flags |= FRIQ_F_NEED_RESET;
+                if (mode & FRIQ_M_STOP_AT_EPISODE_END) running = false;
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
 #pragma unroll
@@ -749,6 +917,14 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
     }
 }
 
+// per-agent episode start states from a device array [n][S] (agent-major, as a caller holds them) into the engine's [k][n_pad] rows
+__global__ void k_set_s0(friq_devstate st, const double *__restrict__ src, int S)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n) return;
+    for (int k = 0; k < S; k++) st.s0[(size_t)k * st.n_pad + ag] = src[(size_t)ag * S + k];
+}
+
 __global__ void k_broadcast_rb(friq_devstate st, const unsigned int *__restrict__ words, const double *__restrict__ q, int R)
 {
     const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -996,6 +1172,12 @@ int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const doub
     CK(cudaGetLastError());
     return 0;
 }
+int friqd_set_s0(friq_devstate st, const double *d_s0, int S, void *stream)
+{
+    k_set_s0<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(st, d_s0, S);
+    CK(cudaGetLastError());
+    return 0;
+}
 int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
@@ -1108,6 +1290,42 @@ int friqd_run_shared(const friq_devprob *hp, const friq_devprob *dprob, friq_dev
     } while (0)
     if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_SHARED(2, 3, 3, FRIQ_ENV_MOUNTAINCAR, 3);
     else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_SHARED(4, 5, 3, FRIQ_ENV_ACROBOT, 2);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+// memoised conclusions of a shared rule base (k_shared_memo_build / k_shared_start / k_infer_memo)
+int friqd_shared_memo_build(const friq_devprob *hp, const friq_devprob *dprob, const double *d_srb, int Rs, double *d_memo, int cells, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const long warps = (long)cells * hp->A;
+    const unsigned g = (unsigned)((warps * 32 + 127) / 128);
+    if (FRIQ_SHAPE_MC(hp)) k_shared_memo_build<2, 3><<<g, 128, 0, s>>>(dprob, d_srb, Rs, d_memo, cells, hp->A);
+    else if (FRIQ_SHAPE_AC(hp)) k_shared_memo_build<4, 5><<<g, 128, 0, s>>>(dprob, d_srb, Rs, d_memo, cells, hp->A);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_shared_start(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, double *d_start, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+#define FRIQ_LAUNCH_START(S_, P_, A_, UNR_)                                                                            \
+    do {                                                                                                              \
+        if (hp->safe_range) k_shared_start<S_, P_, A_, UNR_, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, d_start); \
+        else k_shared_start<S_, P_, A_, UNR_, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, d_start);               \
+    } while (0)
+    if (FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_START(2, 3, 3, 3);
+    else if (FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_START(4, 5, 3, 2);
+    else return FRIQ_ERR_SHAPE;
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_run_shared_memo(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_memo, const double *d_start,
+                          int Rs, long n_steps, int mode, void *stream)
+{
+    const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) k_infer_memo<2, 3, FRIQ_ENV_MOUNTAINCAR><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_memo, d_start, Rs, n_steps, mode);
+    else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) k_infer_memo<4, 3, FRIQ_ENV_ACROBOT><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_memo, d_start, Rs, n_steps, mode);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;

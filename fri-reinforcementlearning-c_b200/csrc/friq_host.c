@@ -42,6 +42,8 @@ struct friq_batch {
     int have_st2, permuted;
     long retile_interval;     /* env steps between re-tilings inside one friq_batch_run (FRIQ_RUN_RETILE) */
     double *d_srb; int shared_R;   /* shared read-only rule base: rows of (K VE values, consequent) */
+    double *d_memo; int memo_cells;   /* its memoised conclusions per (observation grid cell, action), or NULL */
+    double *d_start; int start_dirty; /* its conclusions at every agent's episode start state [A][n_pad]; dirty = recompute before the next run */
     int groups;               /* independent agent groups pipelined on their own streams (hides launch tails) */
     void *gstream[FRIQ_MAXGROUPS], *gdone[FRIQ_MAXGROUPS], *gstart;
     int variant;              /* evaluation policy of the fused kernel (friq_batch_set_policy) */
@@ -535,6 +537,8 @@ void friq_batch_destroy(friq_batch *b)
     if (b->gstart) friqd_event_destroy(b->gstart);
     friqd_free(b->st.sw);
     if (b->d_srb) friqd_free(b->d_srb);
+    if (b->d_memo) friqd_free(b->d_memo);
+    if (b->d_start) friqd_free(b->d_start);
     if (b->st.s0) friqd_free(b->st.s0);
     if (b->have_st2 && b->st2.s0) friqd_free(b->st2.s0);
     free_state(&b->st);
@@ -604,7 +608,8 @@ int friq_batch_set_shared_rulebase(friq_batch *b, int R, const double *rant, con
     DEV(friqd_set_device(b->device));
     DEV(friqd_device_sync());
     if (b->d_srb) { friqd_free(b->d_srb); b->d_srb = NULL; }
-    b->shared_R = 0;
+    if (b->d_memo) { friqd_free(b->d_memo); b->d_memo = NULL; }
+    b->shared_R = 0; b->memo_cells = 0; b->start_dirty = 1;
     if (R <= 0) return 0;
     double *rows = (double *)malloc(sizeof(double) * (size_t)R * (K + 1));
     for (int i = 0; i < R; i++) {
@@ -617,6 +622,20 @@ int friq_batch_set_shared_rulebase(friq_batch *b, int R, const double *rant, con
     free(rows);
     if (rc) FAIL(rc, "friq_batch_set_shared_rulebase: %s", friqd_error_string(rc));
     b->shared_R = R;
+    /* memoised conclusions: one entry per (observation grid cell, action) - the built-in quantisers return grid points, so after the
+     * first step of an episode every conclusion an agent needs is one of these (k_shared_memo_build, k_infer_memo) */
+    if (P->hp.env == FRIQ_ENV_MOUNTAINCAR || P->hp.env == FRIQ_ENV_ACROBOT) {
+        unsigned long cells = 1;
+        for (int k = 0; k < P->hp.S; k++) cells *= (unsigned long)P->hp.grid_len[k];
+        if (cells * (unsigned long)P->hp.A * 8ul <= (64ul << 20)) {
+            DEV(friqd_malloc((void **)&b->d_memo, cells * (unsigned long)P->hp.A * 8ul));
+            int rcm = friqd_shared_memo_build(&P->hp, P->dp, b->d_srb, R, b->d_memo, (int)cells, NULL);
+            if (!rcm) rcm = friqd_device_sync();
+            if (rcm == 9001) { friqd_free(b->d_memo); b->d_memo = NULL; }           /* no memo kernel for this shape: the streaming pass serves it */
+            else if (rcm) FAIL(rcm, "friq_batch_set_shared_rulebase: %s", friqd_error_string(rcm));
+            else b->memo_cells = (int)cells;
+        }
+    }
     return 0;
 }
 
@@ -626,6 +645,7 @@ int friq_batch_set_initial_state(friq_batch *b, const double *s0)
     const long n = b->st.n; const size_t np = (size_t)b->st.n_pad; const int S = b->P->hp.S;
     DEV(friqd_set_device(b->device));
     IDENTITY(b);
+    b->start_dirty = 1;
     if (!s0) { if (b->st.s0) { friqd_free(b->st.s0); b->st.s0 = NULL; } if (b->have_st2 && b->st2.s0) { friqd_free(b->st2.s0); b->st2.s0 = NULL; } return 0; }
     double *t = (double *)calloc(FRIQ_MAXK * np, sizeof(double));
     for (long i = 0; i < n; i++) for (int k = 0; k < S; k++) t[(size_t)k * np + i] = s0[(size_t)i * S + k];
@@ -635,6 +655,20 @@ int friq_batch_set_initial_state(friq_batch *b, const double *s0)
     if (!rc) rc = friqd_h2d(b->st.s0, t, 8 * FRIQ_MAXK * np);
     free(t);
     if (rc) FAIL(rc, "friq_batch_set_initial_state: %s", friqd_error_string(rc));
+    return 0;
+}
+
+/* the same from a DEVICE array d_s0 [n][S] (e.g. a tensor the caller already holds in HBM), asynchronous on `stream` */
+int friq_batch_set_initial_state_device(friq_batch *b, const void *d_s0, void *stream)
+{
+    const size_t np = (size_t)b->st.n_pad;
+    if (!d_s0) FAIL(5, "friq_batch_set_initial_state_device: NULL (use friq_batch_set_initial_state(b, NULL) to restore values_def)");
+    DEV(friqd_set_device(b->device));
+    IDENTITY(b);
+    b->start_dirty = 1;
+    if (!b->st.s0) { DEV(friqd_malloc((void **)&b->st.s0, 8 * FRIQ_MAXK * np)); DEV(friqd_memset(b->st.s0, 0, 8 * FRIQ_MAXK * np)); }
+    if (b->have_st2 && !b->st2.s0) DEV(friqd_malloc((void **)&b->st2.s0, 8 * FRIQ_MAXK * np));
+    DEV(friqd_set_s0(b->st, (const double *)d_s0, b->P->hp.S, stream));
     return 0;
 }
 
@@ -705,6 +739,12 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
     if (b->shared_R > 0) {
         if (mode & FRIQ_RUN_LEARN) FAIL(6, "friq_batch_run: a shared rule base is read-only (clear it or drop FRIQ_RUN_LEARN)");
         IDENTITY(b);
+        if (b->d_memo && b->variant != 0) {          /* memoised conclusions (default); policy 0 = one full pass per env step */
+            if (!b->d_start) DEV(friqd_malloc((void **)&b->d_start, 8ul * (unsigned long)b->P->hp.A * (unsigned long)b->st.n_pad));
+            if (b->start_dirty) { DEV(friqd_shared_start(&b->P->hp, b->P->dp, b->st, b->d_srb, b->shared_R, b->d_start, stream)); b->start_dirty = 0; }
+            DEV(friqd_run_shared_memo(&b->P->hp, b->P->dp, b->st, b->d_memo, b->d_start, b->shared_R, n_steps, mode, stream));
+            return 0;
+        }
         DEV(friqd_run_shared(&b->P->hp, b->P->dp, b->st, b->d_srb, b->shared_R, n_steps, mode, stream));
         return 0;
     }

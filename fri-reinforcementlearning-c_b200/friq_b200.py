@@ -54,6 +54,7 @@ SYMBOLS = {
     "friq_batch_get_rulebase": (C.c_int, [C.c_void_p, C.c_long, ip, dp, dp]),
     "friq_batch_set_shared_rulebase": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
     "friq_batch_set_initial_state": (C.c_int, [C.c_void_p, dp]),
+    "friq_batch_set_initial_state_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "friq_batch_get_state": (C.c_int, [C.c_void_p, dp, ip]),
     "friq_batch_set_inserted": (C.c_int, [C.c_void_p, ip]),
     "friq_batch_get_inserted": (C.c_int, [C.c_void_p, ip]),
@@ -193,6 +194,9 @@ class Batch:
     def set_initial_state(self, s0):
         s0 = None if s0 is None else _f64(s0).reshape(self.n, self.P.S)
         _ck(lib().friq_batch_set_initial_state(self.h, _p(s0)))
+
+    def set_initial_state_device(self, ptr, stream=None):
+        _ck(lib().friq_batch_set_initial_state_device(self.h, ptr, stream))
 
     def get_rulebase(self, agent=0):
         R = C.c_int(0)

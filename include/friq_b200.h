@@ -97,10 +97,14 @@ int friq_batch_set_hyper(friq_batch *b, const double *alpha, const double *gamma
 int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant, const double *rconc);
 int friq_batch_get_rulebase(friq_batch *b, long agent, int *R, double *rant, double *rconc);
 /* ONE read-only rule base shared by all agents (inference only: reduction_state = 1, frirl_test_run.c:65-69);
- * it streams through shared memory by TMA; R = 0 returns to the private rule bases */
+ * R = 0 returns to the private rule bases.  Default evaluation: the conclusions are memoised per (observation grid cell,
+ * action) once, plus one pass over the rule base (streamed through shared memory by TMA) per agent for its off-grid episode
+ * start state; friq_batch_set_policy(b, 0) runs the full pass on every env step instead (same results) */
 int friq_batch_set_shared_rulebase(friq_batch *b, int R, const double *rant, const double *rconc);
 /* per-agent episode start state s0 [n][S] instead of values_def (frirl_episode.c:46-48); NULL restores it */
 int friq_batch_set_initial_state(friq_batch *b, const double *s0);
+/* the same from a device array [n][S] (a cudaMalloc'ed buffer / torch tensor already in HBM), asynchronous on `stream` */
+int friq_batch_set_initial_state_device(friq_batch *b, const void *d_s0, void *stream);
 /* current raw state s [n][S] (fep_ant) and action index [n] of every agent */
 int friq_batch_get_state(friq_batch *b, double *s, int *action_index);
 int friq_batch_set_inserted(friq_batch *b, const int *inserted);   /* fus_is_rule_inserted, frirl_types.h:153 */

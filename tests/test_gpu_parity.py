@@ -453,12 +453,15 @@ def test_inference_mode_leaves_rule_base_untouched(fq):
     b.close(); P.close()
 
 
+@pytest.mark.parametrize("policy", [0, 2])
 @pytest.mark.parametrize("name,R,n,steps", [("mountaincar", 0, 200, 400), ("acrobot", 700, 150, 120), ("acrobot", 513, 40, 30)])
-def test_shared_rule_base_inference_matches_oracle(fq, name, R, n, steps):
-    """BASELINE config 4 in miniature: many agents, ONE read-only rule base streamed through shared memory by
-    TMA, randomised start states, greedy stepping.  R = 0: the learned golden rule base; else a synthetic
-    rule base of R distinct rules on universe points.  Final raw states, actions and episode
-    results of every agent must equal the oracle port's bit for bit."""
+def test_shared_rule_base_inference_matches_oracle(fq, name, R, n, steps, policy):
+    """BASELINE config 4 in miniature: many agents, ONE read-only rule base, randomised start states, greedy stepping.
+    policy 0: one full pass over the rule base per env step (streamed through shared memory by TMA); policy 2 (default):
+    conclusions memoised per (observation grid cell, action) + one pass per agent at its off-grid start state.
+    R = 0: the learned golden rule base (mountaincar episodes END and restart inside the run); else a synthetic rule base of R
+    distinct rules on universe points.  Final raw states, actions and episode results of every agent must
+    equal the oracle port's bit for bit."""
     rng = np.random.default_rng(1234)
     P = fq.Problem(name)
     OP = _oracle.Problem(_golden.ENV_ID[name], trig=1)
@@ -475,6 +478,7 @@ def test_shared_rule_base_inference_matches_oracle(fq, name, R, n, steps):
     hi = {"mountaincar": [0.3, 0.05], "acrobot": [np.pi / 2, np.pi / 2, 0, 0]}[name]
     s0 = rng.uniform(lo, hi, size=(n, P.S))
     b = fq.Batch(P, n, max(len(rconc), P.ncorner))
+    b.set_policy(policy)
     b.set_shared_rulebase(rant, rconc)
     b.set_initial_state(s0)
     with pytest.raises(fq.FriqError):
@@ -645,6 +649,12 @@ def test_shared_rule_base_at_config4_size_matches_oracle_samples(fq):
         b.run(steps, 0)
         res.append(b.get_state()); b.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    m = 8192                                            # the memoised path (default, above) == one full pass per step (policy 0)
+    b = fq.Batch(P, m, P.ncorner); b.set_policy(0)
+    b.set_shared_rulebase(rant, rconc); b.set_initial_state(s0[:m])
+    b.run(steps, 0)
+    s_full, a_full = b.get_state(); b.close()
+    assert np.array_equal(s_full, res[0][0][:m]) and np.array_equal(a_full, res[0][1][:m])
     OP = _oracle.Problem(1, trig=1)
     for i in (0, 65535, n - 1):
         ag = _oracle.Agent(OP, R + 8); ag.set_rb(rant, rconc); ag.set_learning(0); ag.set_initial_state(s0[i])
