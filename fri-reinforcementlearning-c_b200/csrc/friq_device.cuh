@@ -567,7 +567,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
                                                      const double *vo_obs, const double *vo_q, uint32_t ow, uint32_t qw,
                                                      unsigned wmask, const unsigned (&nm)[A], unsigned qm,
                                                      unsigned char *plist /* 32 bytes of shared memory per warp */,
-                                                     double (&conc)[A], double &vagq, double &wsq)
+                                                     double (&conc)[A], double &vagq, double &wsq, unsigned &n_tab, unsigned &n_chain)
 {
     constexpr int K = S + 1, C = A + 1;
     const int lane = threadIdx.x & 31;
@@ -622,6 +622,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
                 const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wcells;
                 asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
                 friq_tab_sums(rowd, rbc, tq, tsw, j, Rj, isq, vag, ws);
+                n_tab += (unsigned)Rj;
             }
             const bool slow = has && !tab;
             if (__any_sync(wmask, slow)) {
@@ -629,12 +630,13 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
                 if (slow) {
                     double out[2];
                     friq_pair_sums_slow<K, P>(&pb, tw + j, tq + j, tsw + j, Rj, isq ? 1 : 0, pt, out);
-                    vag = out[0]; ws = out[1];
+                    vag = out[0]; ws = out[1]; n_chain += (unsigned)Rj;
                 }
             }
         }
         if constexpr (!TAB) {
         const int Rp = has ? Rj : 0;
+        n_chain += (unsigned)Rp;
         // ---- sequential Shepard sums over the owner's rules, UNR rules (= UNR independent chains) per trip
         uint32_t w[UNR]; double q[UNR];
 #pragma unroll
@@ -761,7 +763,7 @@ __device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, do
 template <int S, int P, bool COLD = false>
 __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
                                                  const double *qs, const int *qi, double reward, double qp, int hitq, double qnow, double ws,
-                                                 double alpha, double gamma, double *wref = nullptr)
+                                                 double alpha, double gamma, double *wref = nullptr, unsigned *n_wupd = nullptr)
 {   // qi[k] >= 0: qs[k] is known to BE the grid value dict_val[k][qi[k]] (snapping an on-grid value returns it)
     constexpr int K = S + 1;
     const double qdiff = __dmul_rn(alpha, __dsub_rn(__dadd_rn(reward, __dmul_rn(gamma, qp)), qnow));   // :358
@@ -803,6 +805,7 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
     // (the weights were stored by ANOTHER lane a moment ago and global stores do not stay in L1: every trip is one L2 round trip -
     // FRIQ_WUPD_VEC rules share it.  ncu, acrobot: this loop holds 24 % of the kernel's samples at 4; measured: 8 = no change, 16 = 19 % slower, profiles/README.md)
     const double pre = (pb.wsig >= 0.05) ? __dmul_rn(0.04, ws) : -1.0;
+    if (n_wupd) *n_wupd += (unsigned)rules;
 #pragma unroll 1
     for (int i = 0; i < rules; i += FRIQ_WUPD_VEC) {
         double wi[FRIQ_WUPD_VEC]; bool any = false;

@@ -99,7 +99,17 @@ typedef struct friq_devstate {
     unsigned short *rbc;        /* [tiles][cap][32] dictionary cell of every rule (column of wtab) */
     unsigned short *cmap;       /* [tiles][idx_cells][32] 1 + index of the first rule in that cell, 0 = none: exact hits in O(1) */
     int idx_cells;              /* cells per agent in cmap (= friq_devprob.wcells when the arrays were sized) */
+    unsigned long long *ctr;    /* [FRIQ_NCTR] executed-work counters of the fused kernels, summed over all agents and launches (one atomic per warp
+                                 * and counter at kernel exit): what bench.py reports as the EXECUTED work beside the nominal roofline */
 } friq_devstate;
+enum { FRIQ_CTR_PAIRS = 0,      /* (agent, channel) pairs without an exact-hit rule: conclusions that needed their Shepard sums */
+       FRIQ_CTR_TAB_RULES = 1,  /* rules summed with a looked-up weight (table mode: 1 DMUL + 2 DADD each) */
+       FRIQ_CTR_CHAIN_RULES = 2,/* rules summed with a computed weight (sqrt -> x87 power -> reciprocal chain) */
+       FRIQ_CTR_HIT_PAIRS = 3,  /* (agent, channel) pairs answered by an exact-hit rule */
+       FRIQ_CTR_APPENDED = 4,   /* rules appended */
+       FRIQ_CTR_WUPD_RULES = 5, /* rules scanned by weighted updates */
+       FRIQ_CTR_STEPS = 6,      /* env steps executed */
+       FRIQ_NCTR = 8 };
 
 #ifdef __cplusplus
 extern "C" {
@@ -118,6 +128,9 @@ int friqd_h2d_async(void *dst, const void *src, unsigned long bytes, void *strea
 int friqd_d2h_async(void *dst, const void *src, unsigned long bytes, void *stream);
 int friqd_device_count(int *count);
 int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const double *d_q, int R, void *stream);
+int friqd_permute_in3(friq_devstate st, const double *s0, double *d0, const double *s1, double *d1, const double *s2, double *d2, void *stream);
+int friqd_new_episodes(friq_devstate st, void *stream);
+int friqd_result_stats(const double *d_ret, const int *d_rules, long n, double *d_out3, void *stream);
 int friqd_set_s0(friq_devstate st, const double *d_s0, int S, void *stream);
 int friqd_retile(friq_devstate src, friq_devstate dst, int *d_work, int by_rules, void *stream);
 int friqd_unpermute(friq_devstate st, const void *src, void *dst, int elem_bytes, void *stream);
@@ -135,7 +148,8 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
 int friqd_run_steps(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, int variant, void *stream);
 int friqd_run_shared(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, long n_steps, int mode, void *stream);
 int friqd_shared_memo_build(const friq_devprob *hprob, const friq_devprob *dprob, const double *d_srb, int Rs, double *d_memo, int cells, void *stream);
-int friqd_shared_start(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, double *d_start, void *stream);
+unsigned long friqd_shared_start_scratch_bytes(long n_pad, int A);
+int friqd_shared_start(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, double *d_start, void *d_scratch, void *stream);
 int friqd_run_shared_memo(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_memo, const double *d_start,
                           int Rs, long n_steps, int mode, void *stream);
 int friqd_vag_concl(const friq_devprob *hprob, const friq_devprob *dprob, friq_devstate st, const double *d_ant, double *d_conc, int *d_hit,

@@ -136,6 +136,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     const unsigned wmask = __activemask();
     long done_steps = 0;
     bool running = true;
+    unsigned c_pairs = 0, c_tab = 0, c_chain = 0, c_hit = 0, c_app = 0, c_wupd = 0;    // executed-work counters (friq_devstate.ctr)
     while (__any_sync(wmask, running && done_steps < n_steps)) {
         const bool act = running && done_steps < n_steps && !((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED));
         const bool initial = flags & FRIQ_F_NEED_RESET;
@@ -192,16 +193,19 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             } else
                 friq_hit_scan<A>(rbw, act ? R : 0, tgt, hidx);
 #pragma unroll
-            for (int a = 0; a < A; a++) { nm[a] = __ballot_sync(wmask, act && hidx[a] < 0); pairs += __popc(nm[a]); }
+            for (int a = 0; a < A; a++) { nm[a] = __ballot_sync(wmask, act && hidx[a] < 0); pairs += __popc(nm[a]); if (act) { if (hidx[a] < 0) c_pairs++; else c_hit++; } }
+            if (needq) c_pairs++; else if (upd) c_hit++;
             if (COOP || pairs <= FRIQ_COOP_MAXPAIRS) {
                 lockstep = false;
 #pragma unroll
                 for (int a = 0; a < A; a++) actconc[a] = (hidx[a] >= 0) ? rbq[(size_t)hidx[a] * FRIQ_TILE] : 0.0;
                 vagq = 0.0; wsq = 0.0;
-                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq);
+                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq, c_tab, c_chain);
             }
         }
         if (!COOP && lockstep) {
+            if (act) { c_chain += (unsigned)(R * A); if (!(COOP || A == ACH) || !pb.hit_scan) { c_pairs += A + (needq ? 1 : 0); } }
+            if (needq) c_chain += (unsigned)R;
             if (__popc(qm) >= FRIQ_QCOOP_MAX)            // many lanes need Q(s,a): its chain rides in the pass
                 friq_best_action_pass<S, P, A, ACH, true, UNR, SAFE>(pb, rbw, rbq, sw, act ? R : 0, vc, actconc, hidx, vo, needq, vagq, wsq);
             else {                                       // none or a few: the warp serves them one by one
@@ -228,8 +232,9 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
                 else { ws = wsq; qnow = __ddiv_rn(vagq, wsq); }                               // FIVEVagConcl.c:302
                 const int R0 = R;
-                friq_sarsa_apply<S, P, true>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref);
+                friq_sarsa_apply<S, P, true>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref, &c_wupd);
                 hitq = next_hit;
+                c_app += (unsigned)(R - R0);
                 if (R > R0 && tabmode) {                 // a rule was appended: keep the indexes current
                     const int cn = friq_cell<K>(pb, rbw[(size_t)R0 * FRIQ_TILE]);
                     unsigned short *e = rbc + friq_rbc_index(R0, (int)(ag & 31));
@@ -269,6 +274,16 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         __syncwarp(wmask);
     }
 
+    // ---- executed-work counters: one atomic per warp and counter
+    if (st.ctr) {
+        const unsigned v[7] = { c_pairs, c_tab, c_chain, c_hit, c_app, c_wupd, (unsigned)done_steps };
+        const int lead = __ffs(wmask) - 1;
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            const unsigned t = __reduce_add_sync(wmask, v[c]);
+            if ((int)(threadIdx.x & 31) == lead && t) atomicAdd(st.ctr + c, (unsigned long long)t);
+        }
+    }
     // ---- registers -> agent state
 #pragma unroll
     for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
@@ -506,21 +521,14 @@ k_infer_shared(const friq_devprob *__restrict__ gprob, friq_devstate st, const d
 // memo[cell * A + a], cell = sum_k grid_index_k * stride_k (stride_0 = 1).  One WARP per (cell, action): the 32 lanes evaluate
 // the weights of 32 consecutive rules in parallel (library-exact chain), then the sums are added in rule order (every lane adds
 // the same shuffled values), stopping at the first rule at distance 0.
+// conclusion of ONE (point, action) against the shared rule base, computed by a whole warp: every lane returns the value
 template <int S, int P>
-__global__ void __launch_bounds__(128)
-k_shared_memo_build(const friq_devprob *__restrict__ gprob, const double *__restrict__ srb, int Rs, double *__restrict__ memo, int cells, int A)
+__device__ __forceinline__ double friq_warp_conclusion(const double *__restrict__ srb, int Rs, const double *vc, double ave)
 {
     constexpr int K = S + 1, RW = K + 1;
     const int lane = threadIdx.x & 31;
-    const long wi = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wi >= (long)cells * A) return;
-    int cell = (int)(wi / A); const int a = (int)(wi % A);
-    double vc[S];
-#pragma unroll
-    for (int k = 0; k < S; k++) { const int n = gprob->grid_len[k]; vc[k] = gprob->dict_ve[k][cell % n]; cell /= n; }
-    const double ave = gprob->act_ve[a];
-    double vag = 0.0, ws = 0.0, hq = 0.0; bool hit = false;
-    for (int base = 0; base < Rs && !hit; base += 32) {
+    double vag = 0.0, ws = 0.0;
+    for (int base = 0; base < Rs; base += 32) {
         const int i = base + lane; const bool in = i < Rs;
         const double *r = srb + (size_t)(in ? i : Rs - 1) * RW;
         double ssum = 0.0;
@@ -537,22 +545,102 @@ k_shared_memo_build(const friq_devprob *__restrict__ gprob, const double *__rest
         const double w = zero ? 0.0 : friq_shepard_weight<P>(sv);
         const double wq = __dmul_rn(w, q);
         const unsigned zm = __ballot_sync(0xffffffffu, zero);
-        if (zm) { hit = true; hq = __shfl_sync(0xffffffffu, q, __ffs(zm) - 1); break; }      // BestAct.c:89-93: first rule at distance 0
+        if (zm) return __shfl_sync(0xffffffffu, q, __ffs(zm) - 1);                             // BestAct.c:89-93: first rule at distance 0
         const int cnt = min(32, Rs - base);
         for (int j = 0; j < cnt; j++) {
             vag = __dadd_rn(vag, __shfl_sync(0xffffffffu, wq, j));                             // :216
             ws = __dadd_rn(ws, __shfl_sync(0xffffffffu, w, j));                                // :217
         }
     }
-    if (lane == 0) memo[wi] = hit ? hq : __ddiv_rn(vag, ws);                                   // :265
+    return __ddiv_rn(vag, ws);                                                                 // :265
+}
+template <int S, int P>
+__global__ void __launch_bounds__(128)
+k_shared_memo_build(const friq_devprob *__restrict__ gprob, const double *__restrict__ srb, int Rs, double *__restrict__ memo, int cells, int A)
+{
+    const long wi = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wi >= (long)cells * A) return;
+    int cell = (int)(wi / A); const int a = (int)(wi % A);
+    double vc[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) { const int n = gprob->grid_len[k]; vc[k] = gprob->dict_ve[k][cell % n]; cell /= n; }
+    const double c = friq_warp_conclusion<S, P>(srb, Rs, vc, gprob->act_ve[a]);
+    if ((threadIdx.x & 31) == 0) memo[wi] = c;
+}
+
+// ---- Episode start states, de-duplicated.  The conclusions at a start state depend on it only through the nearest universe
+// index of every dimension (five_rule_distance.c:75: VE_k[idx(x_k)]), and a universe has few points (41 for acrobot): a batch of
+// 262,144 random start states holds at most 41 x 41 distinct index tuples in the two dimensions config 4 randomises.  Agents
+// insert their tuple into a hash table (k_start_keys), the distinct tuples are numbered (k_start_compact), ONE warp per (tuple,
+// action) evaluates the conclusion (k_start_unique) and every agent copies its tuple's values (k_start_scatter).  When more than
+// n / FRIQ_START_DEDUPE_DIV tuples are distinct, the thread-per-agent streaming pass (k_shared_start) is cheaper and runs instead;
+// both kernels read the count on the device and the wrong one leaves at once, so the host never waits for it.
+#define FRIQ_START_DEDUPE_DIV 8
+#define FRIQ_KEY_EMPTY 0xffffffffffffffffull
+__device__ __forceinline__ unsigned long long friq_mix64(unsigned long long x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+__global__ void k_start_keys(const friq_devprob *__restrict__ gprob, friq_devstate st, unsigned long long *table, unsigned tmask, int *slot_of_agent)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n) return;
+    const int S = gprob->S;
+    unsigned long long key = 0;
+    for (int k = 0; k < S; k++) {
+        const double x = st.s0 ? st.s0[(size_t)k * st.n_pad + ag] : gprob->values_def[k];
+        key |= (unsigned long long)friq_nearest_index(*gprob, k, x, gprob->U) << (16 * k);
+    }
+    unsigned h = (unsigned)friq_mix64(key) & tmask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(table + h, FRIQ_KEY_EMPTY, key);
+        if (old == FRIQ_KEY_EMPTY || old == key) break;
+        h = (h + 1) & tmask;
+    }
+    slot_of_agent[ag] = (int)h;
+}
+__global__ void k_start_compact(const unsigned long long *__restrict__ table, unsigned tsize, int *rank_of_slot, int *slot_of_rank, int *count)
+{
+    const unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= tsize || table[h] == FRIQ_KEY_EMPTY) return;
+    const int r = atomicAdd(count, 1);
+    rank_of_slot[h] = r; slot_of_rank[r] = (int)h;
+}
+template <int S, int P>
+__global__ void __launch_bounds__(128)
+k_start_unique(const friq_devprob *__restrict__ gprob, const double *__restrict__ srb, int Rs, const unsigned long long *__restrict__ table,
+               const int *__restrict__ slot_of_rank, const int *__restrict__ count, long n, double *__restrict__ uconc, int A)
+{
+    const int nu = *count;
+    if ((long)nu * FRIQ_START_DEDUPE_DIV > n) return;                    // too many distinct tuples: k_shared_start serves this batch
+    const long wi = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wi >= (long)nu * A) return;
+    const int u = (int)(wi / A), a = (int)(wi % A);
+    const unsigned long long key = table[slot_of_rank[u]];
+    double vc[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) vc[k] = __ldg(gprob->ve + (size_t)k * gprob->U + (int)((key >> (16 * k)) & 0xffffu));
+    const double c = friq_warp_conclusion<S, P>(srb, Rs, vc, gprob->act_ve[a]);
+    if ((threadIdx.x & 31) == 0) uconc[wi] = c;
+}
+__global__ void k_start_scatter(friq_devstate st, const int *__restrict__ slot_of_agent, const int *__restrict__ rank_of_slot, const int *__restrict__ count,
+                                const double *__restrict__ uconc, double *__restrict__ start, int A)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag >= st.n || (long)(*count) * FRIQ_START_DEDUPE_DIV > st.n) return;
+    const int u = rank_of_slot[slot_of_agent[ag]];
+    for (int a = 0; a < A; a++) start[(size_t)a * st.n_pad + ag] = uconc[(size_t)u * A + a];
 }
 
 // conclusions of all actions at every agent's episode start state (frirl_episode.c:46-48, :78: the first action is chosen from
 // the RAW start state): start[a * n_pad + agent]
 template <int S, int P, int A, int UNR, bool SAFE>
 __global__ void __launch_bounds__(FRIQ_BLOCK, 2)
-k_shared_start(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ srb, int Rs, double *__restrict__ start)
+k_shared_start(const friq_devprob *__restrict__ gprob, friq_devstate st, const double *__restrict__ srb, int Rs, double *__restrict__ start,
+               const int *__restrict__ uniq_count)
 {
+    if (uniq_count && (long)(*uniq_count) * FRIQ_START_DEDUPE_DIV <= st.n) return;     // the de-duplicated path serves this batch
     FRIQ_SHARED_PROLOGUE();
     double vc[S], ave[A], actconc[A];
 #pragma unroll
@@ -917,6 +1005,27 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
     }
 }
 
+// every agent abandons its current episode and starts a new one at its next step (rule bases, counters and RNG keys untouched)
+__global__ void k_new_episodes(friq_devstate st)
+{
+    const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ag < st.n) st.flags[ag] |= FRIQ_F_NEED_RESET;
+}
+// per-agent result statistics of a gathered result set: out[0] = sum of rules, out[1] = sum of returns, out[2] = max rules.
+// ONE block, fixed summation tree: deterministic for a given n.
+__global__ void __launch_bounds__(1024) k_result_stats(const double *__restrict__ ret, const int *__restrict__ rules, long n, double *__restrict__ out)
+{
+    __shared__ double s_ret[1024], s_rules[1024]; __shared__ int s_max[1024];
+    double a = 0.0, r = 0.0; int m = 0;
+    for (long i = threadIdx.x; i < n; i += 1024) { a += ret[i]; r += (double)rules[i]; m = max(m, rules[i]); }
+    s_ret[threadIdx.x] = a; s_rules[threadIdx.x] = r; s_max[threadIdx.x] = m;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) { s_ret[threadIdx.x] += s_ret[threadIdx.x + w]; s_rules[threadIdx.x] += s_rules[threadIdx.x + w]; s_max[threadIdx.x] = max(s_max[threadIdx.x], s_max[threadIdx.x + w]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = s_rules[0]; out[1] = s_ret[0]; out[2] = (double)s_max[0]; }
+}
 // per-agent episode start states from a device array [n][S] (agent-major, as a caller holds them) into the engine's [k][n_pad] rows
 __global__ void k_set_s0(friq_devstate st, const double *__restrict__ src, int S)
 {
@@ -1015,6 +1124,16 @@ __global__ void k_unpermute(friq_devstate st, const T *src, T *dst)
 {
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < st.n) dst[st.agent_of_slot[p]] = src[p];
+}
+// the other direction: per-agent inputs in AGENT order (src0..2, any may be NULL) into the slots the agents live in
+__global__ void k_permute_in3(friq_devstate st, const double *src0, double *dst0, const double *src1, double *dst1, const double *src2, double *dst2)
+{
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= st.n) return;
+    const int a = st.agent_of_slot[p];
+    if (src0) dst0[p] = src0[a];
+    if (src1) dst1[p] = src1[a];
+    if (src2) dst2[p] = src2[a];
 }
 
 // ---- knowledge sharing (frirl_agent.c:58-117, 294-385)
@@ -1172,6 +1291,24 @@ int friqd_broadcast_rb(friq_devstate st, const unsigned int *d_words, const doub
     CK(cudaGetLastError());
     return 0;
 }
+int friqd_permute_in3(friq_devstate st, const double *s0, double *d0, const double *s1, double *d1, const double *s2, double *d2, void *stream)
+{
+    k_permute_in3<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(st, s0, d0, s1, d1, s2, d2);
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_new_episodes(friq_devstate st, void *stream)
+{
+    k_new_episodes<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(st);
+    CK(cudaGetLastError());
+    return 0;
+}
+int friqd_result_stats(const double *d_ret, const int *d_rules, long n, double *d_out3, void *stream)
+{
+    k_result_stats<<<1, 1024, 0, (cudaStream_t)stream>>>(d_ret, d_rules, n, d_out3);
+    CK(cudaGetLastError());
+    return 0;
+}
 int friqd_set_s0(friq_devstate st, const double *d_s0, int S, void *stream)
 {
     k_set_s0<<<grid_for(st.n), FRIQ_BLOCK, 0, (cudaStream_t)stream>>>(st, d_s0, S);
@@ -1306,13 +1443,38 @@ int friqd_shared_memo_build(const friq_devprob *hp, const friq_devprob *dprob, c
     CK(cudaGetLastError());
     return 0;
 }
-int friqd_shared_start(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, double *d_start, void *stream)
+// scratch of the de-duplication, one allocation: table u64[T] | slot_of_agent i32[n_pad] | rank_of_slot i32[T] | slot_of_rank i32[T] | count i32[4] | uconc f64[n_pad / DIV * A + A]
+static inline unsigned friq_start_tsize(long n) { unsigned t = 1024; while ((long)t < 2 * n) t <<= 1; return t; }
+unsigned long friqd_shared_start_scratch_bytes(long n_pad, int A)
+{
+    const unsigned long T = friq_start_tsize(n_pad);
+    return 8ul * T + 4ul * n_pad + 4ul * T + 4ul * T + 16ul + 8ul * ((unsigned long)(n_pad / FRIQ_START_DEDUPE_DIV + 1) * A + A);
+}
+int friqd_shared_start(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, const double *d_srb, int Rs, double *d_start, void *d_scratch, void *stream)
 {
     const dim3 g = grid_for(st.n); cudaStream_t s = (cudaStream_t)stream;
+    const int A = hp->A;
+    int *count = nullptr;
+    if (d_scratch && (FRIQ_SHAPE_MC(hp) || FRIQ_SHAPE_AC(hp)) && hp->U <= 65535) {
+        const unsigned T = friq_start_tsize(st.n_pad);
+        unsigned long long *table = (unsigned long long *)d_scratch;
+        int *slot_of_agent = (int *)(table + T), *rank_of_slot = slot_of_agent + st.n_pad, *slot_of_rank = rank_of_slot + T;
+        count = slot_of_rank + T;
+        double *uconc = (double *)(count + 4);
+        CK(cudaMemsetAsync(table, 0xff, 8ul * T, s));
+        CK(cudaMemsetAsync(count, 0, 16, s));
+        k_start_keys<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, table, T - 1, slot_of_agent);
+        k_start_compact<<<(T + 255) / 256, 256, 0, s>>>(table, T, rank_of_slot, slot_of_rank, count);
+        const long maxw = (long)(st.n / FRIQ_START_DEDUPE_DIV + 1) * A;
+        const unsigned gu = (unsigned)((maxw * 32 + 127) / 128);
+        if (FRIQ_SHAPE_MC(hp)) k_start_unique<2, 3><<<gu, 128, 0, s>>>(dprob, d_srb, Rs, table, slot_of_rank, count, st.n, uconc, A);
+        else k_start_unique<4, 5><<<gu, 128, 0, s>>>(dprob, d_srb, Rs, table, slot_of_rank, count, st.n, uconc, A);
+        k_start_scatter<<<g, FRIQ_BLOCK, 0, s>>>(st, slot_of_agent, rank_of_slot, count, uconc, d_start, A);
+    }
 #define FRIQ_LAUNCH_START(S_, P_, A_, UNR_)                                                                            \
     do {                                                                                                              \
-        if (hp->safe_range) k_shared_start<S_, P_, A_, UNR_, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, d_start); \
-        else k_shared_start<S_, P_, A_, UNR_, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, d_start);               \
+        if (hp->safe_range) k_shared_start<S_, P_, A_, UNR_, true><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, d_start, count); \
+        else k_shared_start<S_, P_, A_, UNR_, false><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_srb, Rs, d_start, count);               \
     } while (0)
     if (FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_START(2, 3, 3, 3);
     else if (FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_START(4, 5, 3, 2);

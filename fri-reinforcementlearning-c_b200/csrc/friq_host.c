@@ -14,6 +14,7 @@
 
 #include <fcntl.h>
 #include <math.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -22,6 +23,10 @@
 #define FRIQ_MAXGROUPS 8
 static __thread char g_err[512] = "";
 const char *friq_last_error(void) { return g_err; }
+void friq_set_error_(int code, const char *fmt, ...)      /* for the library's other translation units (friq_multi.c) */
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); (void)code;
+}
 #define FAIL(code, ...) do { snprintf(g_err, sizeof g_err, __VA_ARGS__); return (code); } while (0)
 #define DEV(call) do { int e_ = (call); if (e_) FAIL(e_, "%s failed: %s", #call, friqd_error_string(e_)); } while (0)
 
@@ -43,12 +48,14 @@ struct friq_batch {
     long retile_interval;     /* env steps between re-tilings inside one friq_batch_run (FRIQ_RUN_RETILE) */
     double *d_srb; int shared_R;   /* shared read-only rule base: rows of (K VE values, consequent) */
     double *d_memo; int memo_cells;   /* its memoised conclusions per (observation grid cell, action), or NULL */
+    void *d_start_scratch;    /* de-duplication of the start states (k_start_keys ...) */
     double *d_start; int start_dirty; /* its conclusions at every agent's episode start state [A][n_pad]; dirty = recompute before the next run */
     int groups;               /* independent agent groups pipelined on their own streams (hides launch tails) */
     void *gstream[FRIQ_MAXGROUPS], *gdone[FRIQ_MAXGROUPS], *gstart;
     int variant;              /* evaluation policy of the fused kernel (friq_batch_set_policy) */
     int *d_work;              /* re-tiling scratch */
     void *d_tmp8, *d_tmp4a, *d_tmp4b;   /* un-permuted result staging */
+    double *d_hyp;            /* agent-ordered staging of host hyper-parameter arrays (friq_batch_run_host on a re-tiled batch) */
     int device;
     uint64_t seed0; long first_agent;
     double *d_in0, *d_in1, *d_in2, *d_out0; int *d_iout; size_t cap_in, cap_out, cap_w; double *d_w;
@@ -491,6 +498,7 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
     { int rc2 = alloc_state(st, 1); if (rc2) return rc2; }
     const size_t slots = (size_t)st->n_pad * cap;
     DEV(friqd_malloc((void **)&st->sw, slots * 8)); DEV(friqd_memset(st->sw, 0, slots * 8));
+    DEV(friqd_malloc((void **)&st->ctr, 8 * FRIQ_NCTR)); DEV(friqd_memset(st->ctr, 0, 8 * FRIQ_NCTR));
     *out = b;
     return friq_batch_reset(b);
 }
@@ -536,13 +544,16 @@ void friq_batch_destroy(friq_batch *b)
     }
     if (b->gstart) friqd_event_destroy(b->gstart);
     friqd_free(b->st.sw);
+    friqd_free(b->st.ctr);
     if (b->d_srb) friqd_free(b->d_srb);
     if (b->d_memo) friqd_free(b->d_memo);
     if (b->d_start) friqd_free(b->d_start);
+    if (b->d_start_scratch) friqd_free(b->d_start_scratch);
     if (b->st.s0) friqd_free(b->st.s0);
     if (b->have_st2 && b->st2.s0) friqd_free(b->st2.s0);
     free_state(&b->st);
     if (b->have_st2) { free_state(&b->st2); friqd_free(b->d_work); }
+    if (b->d_hyp) friqd_free(b->d_hyp);
     if (b->d_tmp8) { friqd_free(b->d_tmp8); friqd_free(b->d_tmp4a); friqd_free(b->d_tmp4b); }
     void *tmp[6] = { b->d_in0, b->d_in1, b->d_in2, b->d_out0, b->d_iout, b->d_w };
     for (int i = 0; i < 6; i++) if (tmp[i]) friqd_free(tmp[i]);
@@ -741,7 +752,8 @@ int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream)
         IDENTITY(b);
         if (b->d_memo && b->variant != 0) {          /* memoised conclusions (default); policy 0 = one full pass per env step */
             if (!b->d_start) DEV(friqd_malloc((void **)&b->d_start, 8ul * (unsigned long)b->P->hp.A * (unsigned long)b->st.n_pad));
-            if (b->start_dirty) { DEV(friqd_shared_start(&b->P->hp, b->P->dp, b->st, b->d_srb, b->shared_R, b->d_start, stream)); b->start_dirty = 0; }
+            if (!b->d_start_scratch) DEV(friqd_malloc(&b->d_start_scratch, friqd_shared_start_scratch_bytes(b->st.n_pad, b->P->hp.A)));
+            if (b->start_dirty) { DEV(friqd_shared_start(&b->P->hp, b->P->dp, b->st, b->d_srb, b->shared_R, b->d_start, b->d_start_scratch, stream)); b->start_dirty = 0; }
             DEV(friqd_run_shared_memo(&b->P->hp, b->P->dp, b->st, b->d_memo, b->d_start, b->shared_R, n_steps, mode, stream));
             return 0;
         }
@@ -815,6 +827,35 @@ int friq_batch_gather(friq_batch *b, double *last_return, int *last_steps, int *
     return 0;
 }
 
+/* every agent starts a NEW episode at its next step (frirl_episode.c:46-82) whatever state its current one is in; rule bases,
+ * counters and random streams are untouched.  Asynchronous on `stream`. */
+int friq_batch_new_episodes(friq_batch *b, void *stream)
+{
+    DEV(friqd_set_device(b->device));
+    DEV(friqd_new_episodes(b->st, stream));
+    return 0;
+}
+/* statistics of a gathered per-agent result set of n agents (device arrays, e.g. what an all-gather produced): d_out3[0] = sum of
+ * rules, [1] = sum of returns, [2] = max rules - one small kernel, deterministic; asynchronous on `stream` */
+int friq_result_stats(int device, const void *d_ret_f64, const void *d_rules_i32, long n, void *d_out3_f64, void *stream)
+{
+    DEV(friqd_set_device(device));
+    DEV(friqd_result_stats((const double *)d_ret_f64, (const int *)d_rules_i32, n, (double *)d_out3_f64, stream));
+    return 0;
+}
+
+/* executed-work counters of the fused kernels since batch creation (or the last call with reset != 0): out[0..7] =
+ * pairs that needed Shepard sums, rules summed with looked-up weights, rules summed with computed chains, pairs answered by an
+ * exact-hit rule, rules appended, rules scanned by weighted updates, env steps, 0 */
+int friq_batch_work_counters(friq_batch *b, unsigned long long *out, int reset)
+{
+    DEV(friqd_set_device(b->device));
+    DEV(friqd_device_sync());
+    if (out) DEV(friqd_d2h(out, b->st.ctr, 8 * FRIQ_NCTR));
+    if (reset) DEV(friqd_memset(b->st.ctr, 0, 8 * FRIQ_NCTR));
+    return 0;
+}
+
 int friq_batch_gather_device(friq_batch *b, void *d_ret, void *d_steps, void *d_rules, void *stream)
 {
     const long n = b->st.n;
@@ -837,10 +878,19 @@ int friq_batch_run_host(friq_batch *b, const double *alpha, const double *gamma,
     const long n = b->st.n;
     DEV(friqd_set_device(b->device));
     if (alpha || gamma || epsilon) {                     /* host arrays are in agent order */
-        int rc0 = retile(b, 0, stream); if (rc0) return rc0;
-        if (alpha) DEV(friqd_h2d_async(b->st.alpha, alpha, 8 * n, stream));
-        if (gamma) DEV(friqd_h2d_async(b->st.gamma, gamma, 8 * n, stream));
-        if (epsilon) DEV(friqd_h2d_async(b->st.epsilon, epsilon, 8 * n, stream));
+        if (b->permuted) {                               /* agents live in re-tiled slots: stage in agent order, scatter through the placement */
+            const size_t np = (size_t)b->st.n_pad;
+            if (!b->d_hyp) DEV(friqd_malloc((void **)&b->d_hyp, 3 * 8 * np));
+            double *t0 = b->d_hyp, *t1 = b->d_hyp + np, *t2 = b->d_hyp + 2 * np;
+            if (alpha) DEV(friqd_h2d_async(t0, alpha, 8 * n, stream));
+            if (gamma) DEV(friqd_h2d_async(t1, gamma, 8 * n, stream));
+            if (epsilon) DEV(friqd_h2d_async(t2, epsilon, 8 * n, stream));
+            DEV(friqd_permute_in3(b->st, alpha ? t0 : NULL, b->st.alpha, gamma ? t1 : NULL, b->st.gamma, epsilon ? t2 : NULL, b->st.epsilon, stream));
+        } else {
+            if (alpha) DEV(friqd_h2d_async(b->st.alpha, alpha, 8 * n, stream));
+            if (gamma) DEV(friqd_h2d_async(b->st.gamma, gamma, 8 * n, stream));
+            if (epsilon) DEV(friqd_h2d_async(b->st.epsilon, epsilon, 8 * n, stream));
+        }
     }
     int rc = friq_batch_run(b, n_steps, mode, stream); if (rc) return rc;
     const void *s_ret = b->st.last_return, *s_steps = b->st.last_steps, *s_rules = b->st.R;

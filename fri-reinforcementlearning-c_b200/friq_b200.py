@@ -64,6 +64,9 @@ SYMBOLS = {
     "friq_batch_set_policy": (C.c_int, [C.c_void_p, C.c_int]),
     "friq_batch_set_groups": (C.c_int, [C.c_void_p, C.c_int]),
     "friq_batch_gather": (C.c_int, [C.c_void_p, dp, ip, ip, ip, ip, llp, llp]),
+    "friq_batch_new_episodes": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "friq_result_stats": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]),
+    "friq_batch_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "friq_batch_gather_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "friq_batch_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "friq_batch_vag_concl": (C.c_int, [C.c_void_p, dp, dp, ip]),
@@ -82,6 +85,18 @@ SYMBOLS = {
     "friq_batch_load_rb_file": (C.c_int, [C.c_void_p, C.c_long, C.c_char_p]),
     "friq_batch_save_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
     "friq_batch_load_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "friq_multi_create": (C.c_int, [C.POINTER(ProblemDesc), C.c_int, C.c_long, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "friq_multi_destroy": (None, [C.c_void_p]),
+    "friq_multi_devices": (C.c_int, [C.c_void_p]),
+    "friq_multi_batch": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "friq_multi_first_agent": (C.c_long, [C.c_void_p, C.c_int]),
+    "friq_multi_agents": (C.c_long, [C.c_void_p, C.c_int]),
+    "friq_multi_set_hyper": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "friq_multi_run": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
+    "friq_multi_sync": (C.c_int, [C.c_void_p]),
+    "friq_multi_gather": (C.c_int, [C.c_void_p, dp, ip, ip, dp]),
+    "friq_multi_gathered_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "friq_multi_merge_from": (C.c_int, [C.c_void_p, C.c_long, C.c_long]),
     "friq_reduce_rulebase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, ip, dp, dp, C.c_int, ip]),
     "friq_save_rb_to_text_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
     "friq_save_rb_to_bin_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, dp, dp]),
@@ -257,6 +272,14 @@ class Batch:
                                     _p(out["sum_rules"], llp)))
         return out
 
+    def new_episodes(self, stream=None):
+        _ck(lib().friq_batch_new_episodes(self.h, stream))
+
+    def work_counters(self, reset=False):
+        v = (C.c_ulonglong * 8)()
+        _ck(lib().friq_batch_work_counters(self.h, v, int(reset)))
+        return dict(zip(("pairs_summed", "table_rules", "chain_rules", "hit_pairs", "appended", "wupd_rules", "steps"), [int(x) for x in v][:7]))
+
     def gather_device(self, ret_ptr, steps_ptr, rules_ptr, stream=None):
         _ck(lib().friq_batch_gather_device(self.h, ret_ptr, steps_ptr, rules_ptr, stream))
 
@@ -298,6 +321,57 @@ class Batch:
         q_ant = _f64(q_ant).reshape(self.n, self.P.K); cur = _f64(cur_q_ant).reshape(self.n, self.P.K)
         reward = _f64(np.broadcast_to(reward, (self.n,)))
         _ck(lib().friq_batch_update_sarsa(self.h, _p(q_ant), _p(reward), _p(cur)))
+
+
+class Multi:
+    """Every GPU of the node behind one handle (friq_multi_*): contiguous agent blocks, NCCL all-gather of the results."""
+
+    def __init__(self, env, n_agents_total, capacity, n_devices=0, seed0=0x5EED0000, **overrides):
+        L = lib()
+        self.desc = ProblemDesc()
+        _ck(L.friq_problem_desc_builtin(ENV_ID[env] if isinstance(env, str) else env, C.byref(self.desc)))
+        for k, v in overrides.items():
+            setattr(self.desc, k, v)
+        self.h = C.c_void_p()
+        self.n = int(n_agents_total)
+        _ck(L.friq_multi_create(C.byref(self.desc), n_devices, self.n, capacity, seed0, C.byref(self.h)))
+        self.G = L.friq_multi_devices(self.h)
+
+    def batch(self, gpu, problem_like):
+        """A non-owning Batch view of GPU `gpu`'s batch (problem_like supplies S / K / A for array shapes)."""
+        b = Batch.__new__(Batch)
+        b.P, b.n, b.cap = problem_like, int(lib().friq_multi_agents(self.h, gpu)), None
+        b.h = C.c_void_p(lib().friq_multi_batch(self.h, gpu))
+        b.close = lambda: None
+        return b
+
+    def first_agent(self, gpu):
+        return int(lib().friq_multi_first_agent(self.h, gpu))
+
+    def set_hyper(self, alpha=None, gamma=None, epsilon=None):
+        a, g, e = [None if x is None else _f64(np.broadcast_to(x, (self.n,))) for x in (alpha, gamma, epsilon)]
+        _ck(lib().friq_multi_set_hyper(self.h, _p(a), _p(g), _p(e)))
+
+    def run(self, n_steps, mode=RUN_LEARN, sync=True):
+        _ck(lib().friq_multi_run(self.h, int(n_steps), int(mode)))
+        if sync:
+            _ck(lib().friq_multi_sync(self.h))
+
+    def gather(self):
+        ret = np.zeros(self.n); steps = np.zeros(self.n, np.int32); rules = np.zeros(self.n, np.int32); stats = np.zeros(3)
+        _ck(lib().friq_multi_gather(self.h, _p(ret), _p(steps, ip), _p(rules, ip), _p(stats)))
+        return dict(last_return=ret, last_steps=steps, rules=rules, stats=stats)
+
+    def merge_from(self, src_agent, dst_agent=-1):
+        _ck(lib().friq_multi_merge_from(self.h, int(src_agent), int(dst_agent)))
+
+    def close(self):
+        if self.h:
+            lib().friq_multi_destroy(self.h); self.h = None
+
+
+def result_stats(device, ret_ptr, rules_ptr, n, out_ptr, stream=None):
+    _ck(lib().friq_result_stats(int(device), ret_ptr, rules_ptr, int(n), out_ptr, stream))
 
 
 def device_trig(x):

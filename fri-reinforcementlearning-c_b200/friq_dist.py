@@ -64,31 +64,84 @@ def gather_rulebases(dist, rant, rconc, cap):
 
 
 class ResultExchange:
-    """The path's ONE exchange per step, as ONE collective: per-agent (return f64, steps i32, rules i32) live in a single
-    16 B/agent device buffer (three SoA segments; `ret`, `steps`, `rules` are views the engine writes into with
-    friq_batch_gather_device), which is all-gathered in one call; every rank then holds every agent's results, so the
-    rule-base statistics need no further all-reduce.  Outputs are in global agent order (contiguous shards)."""
+    """The path's ONE exchange per step: per-agent (return f64, steps i32, rules i32), gathered from every rank STRAIGHT into
+    agent-ordered arrays (contiguous shards: rank-major == agent-major, so `all_gather_into_tensor` needs no un-interleave
+    copy), on a SIDE stream so that the collective overlaps the next step's kernels instead of serialising behind them.
+    Two buffer sets alternate: the engine writes step i's results into set i % 2 while set (i - 1) % 2 is still in flight.
 
-    def __init__(self, dist, n, device):
-        self.dist, self.n = dist, n
+        buf = x.next_buffers()                  # (ret, steps, rules) views the engine writes into (friq_batch_gather_device)
+        ... engine call on `stream` ...
+        x.exchange_async(stream)                # side stream: wait for `stream`, 3 all-gathers (+ the statistics kernel)
+        ...
+        x.wait(stream)                          # `stream` waits for everything in flight; results() is then valid
+
+    CUDA tensors: torch.distributed NCCL; CPU tensors (gloo, tests): the same calls run synchronously.  `stats_fn(ret, rules, n,
+    out)` = optional device-side statistics kernel (friq_result_stats), else three torch reductions."""
+
+    def __init__(self, dist, n, device, stats_fn=None):
+        self.dist, self.n, self.device = dist, n, torch.device(device)
         self.world = dist.get_world_size() if dist is not None else 1
-        self.local = torch.empty(16 * n, dtype=torch.uint8, device=device)
-        self.ret = self.local[:8 * n].view(torch.float64)
-        self.steps = self.local[8 * n:12 * n].view(torch.int32)
-        self.rules = self.local[12 * n:].view(torch.int32)
-        self.all = torch.empty(self.world * 16 * n, dtype=torch.uint8, device=device) if self.world > 1 else self.local
-        self.g_ret = torch.empty(self.world * n, dtype=torch.float64, device=device)
-        self.g_steps = torch.empty(self.world * n, dtype=torch.int32, device=device)
-        self.g_rules = torch.empty(self.world * n, dtype=torch.int32, device=device)
-        self.stats = torch.zeros(3, dtype=torch.float64, device=device)
+        self.cuda = self.device.type == "cuda"
+        self.stats_fn = stats_fn
+        mk = lambda m, dt: torch.empty(m, dtype=dt, device=device)
+        self.sets = []
+        for _ in range(2):
+            loc = (mk(n, torch.float64), mk(n, torch.int32), mk(n, torch.int32))
+            glo = tuple(mk(self.world * n, t.dtype) for t in loc) if self.world > 1 else loc
+            self.sets.append(dict(local=loc, all=glo, stats=torch.zeros(3, dtype=torch.float64, device=device), done=None, used=False))
+        self.cur = -1
+        self.side = torch.cuda.Stream(device=self.device, priority=-1) if self.cuda else None
+        # legacy single-set views (first set)
+        self.ret, self.steps, self.rules = self.sets[0]["local"]
+
+    def next_buffers(self, stream=None):
+        """The buffer set of the coming step; `stream` (the engine's) first waits until the exchange that last used it is done."""
+        self.cur = (self.cur + 1) % 2
+        st = self.sets[self.cur]
+        if self.cuda and st["done"] is not None:
+            (stream or torch.cuda.current_stream(self.device)).wait_event(st["done"])
+        return st["local"]
+
+    def _run(self, st):
+        if self.world > 1:
+            for dst, src in zip(st["all"], st["local"]):
+                self.dist.all_gather_into_tensor(dst, src)
+        g_ret, _, g_rules = st["all"]
+        if self.stats_fn is not None:
+            self.stats_fn(g_ret, g_rules, g_ret.numel(), st["stats"])
+        else:
+            st["stats"][0] = g_rules.sum(); st["stats"][1] = g_ret.sum(); st["stats"][2] = g_rules.max()
+
+    def exchange_async(self, stream=None):
+        if self.cur < 0:
+            self.cur = 0
+        st = self.sets[self.cur]; st["used"] = True
+        if not self.cuda:
+            self._run(st)
+            return
+        stream = stream or torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event(); ready.record(stream)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            self._run(st)
+            st["done"] = torch.cuda.Event(); st["done"].record(self.side)
+
+    def wait(self, stream=None):
+        if not self.cuda:
+            return
+        stream = stream or torch.cuda.current_stream(self.device)
+        for st in self.sets:
+            if st["done"] is not None:
+                stream.wait_event(st["done"])
+
+    def results(self):
+        """(ret, steps, rules, stats) of the most recent exchange, in global agent order (call wait() first on CUDA)."""
+        st = self.sets[max(self.cur, 0)]
+        return st["all"] + (st["stats"],)
 
     def exchange(self):
-        n, w = self.n, self.world
-        if w > 1:
-            self.dist.all_gather_into_tensor(self.all, self.local)
-        blocks = self.all.view(w, 16 * n)
-        self.g_ret.view(w, n).copy_(blocks[:, :8 * n].contiguous().view(torch.float64).view(w, n))
-        self.g_steps.view(w, n).copy_(blocks[:, 8 * n:12 * n].contiguous().view(torch.int32).view(w, n))
-        self.g_rules.view(w, n).copy_(blocks[:, 12 * n:].contiguous().view(torch.int32).view(w, n))
-        self.stats[0] = self.g_rules.sum(); self.stats[1] = self.g_ret.sum(); self.stats[2] = self.g_rules.max()
-        return self.g_ret, self.g_steps, self.g_rules, self.stats
+        """Synchronous form: results written into `ret` / `steps` / `rules` (the first set) are exchanged and returned."""
+        self.cur = 0
+        self.exchange_async()
+        self.wait()
+        return self.results()

@@ -128,6 +128,16 @@ int friq_batch_set_retile_interval(friq_batch *b, long steps);
  * converged / overflow flags, env steps executed, and the sum over steps of the rule-base size */
 int friq_batch_gather(friq_batch *b, double *last_return, int *last_steps, int *rules, int *episodes, int *flags,
                       long long *total_steps, long long *sum_rules);
+/* every agent starts a NEW episode at its next step, whatever state its current one is in (a fresh batch of start states for
+ * inference; rule bases, counters and random streams untouched); asynchronous on `stream` */
+int friq_batch_new_episodes(friq_batch *b, void *stream);
+/* statistics of a gathered result set (device arrays of n agents): d_out3 = {sum of rules, sum of returns, max rules} (f64) */
+int friq_result_stats(int device, const void *d_ret_f64, const void *d_rules_i32, long n, void *d_out3_f64, void *stream);
+/* executed-work counters of the fused kernels, accumulated on the device since batch creation / the last reset: out[8] = (agent,
+ * channel) pairs that needed their Shepard sums, rules summed with looked-up weights (table mode), rules summed with computed
+ * sqrt / x87-power / reciprocal chains, pairs answered by an exact-hit rule, rules appended, rules scanned by weighted updates,
+ * env steps, 0.  What the path EXECUTES, beside the reference's nominal operation count (bench.py: roofline.executed) */
+int friq_batch_work_counters(friq_batch *b, unsigned long long *out, int reset);
 /* same results copied device -> device into caller-owned buffers (e.g. torch tensors fed to NCCL) */
 int friq_batch_gather_device(friq_batch *b, void *d_last_return_f64, void *d_last_steps_i32, void *d_rules_i32, void *stream);
 /* end-to-end convenience: hyper-parameters H2D, run, results D2H, all on `stream` and synchronised */
@@ -182,6 +192,31 @@ int friq_batch_keep_weights(friq_batch *b);
  * leader (member 0) finds its rule base complete.  log (optional, max_log rows of 4 doubles): (agent, steps, return, rules) of
  * every finished episode, agent by agent; *n_log = rows produced; *rounds_out = rounds run (<= max_rounds). */
 int friq_team_run(friq_batch *b, int team, int max_rounds, double *log, long max_log, long *n_log, int *rounds_out);
+
+/* ---- every GPU of the node behind one handle: agents in contiguous blocks, one batch per GPU, no data-path
+ * collective; the one exchange - per-agent results - is three grouped ncclAllGather calls over NVLink (NCCL is loaded at run time;
+ * one process, ncclCommInitAll).  Stands in for the reference's only distributed mode, frirl_mpi_run (frirl_agent.c:387-467:
+ * blocking MPI_Send / MPI_Recv between ranks).  Global agent i uses the Philox key seed0 + i whatever the number of GPUs. */
+typedef struct friq_multi friq_multi;
+/* n_devices <= 0: all GPUs of the node */
+int friq_multi_create(const friq_problem_desc *desc, int n_devices, long n_agents_total, int rule_capacity, uint64_t seed0, friq_multi **out);
+void friq_multi_destroy(friq_multi *m);
+int friq_multi_devices(const friq_multi *m);
+friq_batch *friq_multi_batch(friq_multi *m, int gpu);              /* GPU `gpu`'s batch, for every per-batch entry point above */
+long friq_multi_first_agent(const friq_multi *m, int gpu);
+long friq_multi_agents(const friq_multi *m, int gpu);              /* gpu < 0: n_agents_total */
+/* host arrays of n_agents_total in global agent order (NULL keeps the current values) */
+int friq_multi_set_hyper(friq_multi *m, const double *alpha, const double *gamma, const double *epsilon);
+/* every GPU advances its agents n_steps env steps (friq_batch_run on the GPU's own stream: the GPUs run side by side) */
+int friq_multi_run(friq_multi *m, long n_steps, int mode);
+int friq_multi_sync(friq_multi *m);
+/* all-gather of (return, steps, rules) into agent-ordered arrays on every GPU, {sum of rules, sum of returns, max rules} by one
+ * kernel, then to the host arrays of n_agents_total (any pointer may be NULL); synchronous */
+int friq_multi_gather(friq_multi *m, double *last_return, int *last_steps, int *rules, double *stats3);
+int friq_multi_gathered_device(friq_multi *m, int gpu, void **d_ret_f64, void **d_steps_i32, void **d_rules_i32);
+/* knowledge sharing across GPUs: the rule base of GLOBAL agent src_agent is merged (merge_rb, frirl_agent.c:58-117) into global
+ * agent dst_agent, or into every agent of every GPU when dst_agent < 0 */
+int friq_multi_merge_from(friq_multi *m, long src_agent, long dst_agent);
 
 /* ---- rule-base files, byte-compatible with frirl_utils.c:100-281 */
 int friq_save_rb_to_text_file(const char *file_name, int K, int R, const double *rant, const double *rconc);

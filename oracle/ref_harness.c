@@ -19,6 +19,10 @@
  *           the CUDA kernels.  Recording works by symbol interposition: this
  *           executable defines the four entry points, the shared library's
  *           internal calls bind to them, and they forward via RTLD_NEXT.
+ *   infer   CPU baseline of BASELINE config 4: REF_PROCS processes; each loads the rule base $REF_RBFILE (the reference's binary
+ *           format, frirl_load_rb_from_bin_file), switches updates off (reduction_state = 1, frirl_test_run.c:65-69) and runs
+ *           REF_REPS greedy episodes of REF_STEPS steps from random start states (theta1, theta2 ~ U(-pi/2, pi/2), the
+ *           example's values_def fields are overwritten per episode); prints the same REFBENCH line.
  *   bench   CPU baseline: REF_PROCS processes, each stepping an independent
  *           reference agent (no_random=1, the reference RNG is unseedable) for
  *           >= REF_STEPS env steps of frirl_episode(); prints one line
@@ -235,16 +239,45 @@ void ref_hook_frirl_run(struct frirl_desc *frirl, int verbose) {
          * fortified strcpy aborts on) */
         if (getenv("REF_RBFILE")) frirl->rbfile = strdup(getenv("REF_RBFILE"));
     }
+    if (!strcmp(g_mode, "infer")) {
+        const char *rb = getenv("REF_RBFILE");
+        if (!rb || frirl_load_rb_from_bin_file(frirl, rb) < 0) { fprintf(stderr, "ref_harness: cannot load REF_RBFILE\n"); exit(7); }
+        frirl->reduction_state = 1;                 /* no rule-base updates (frirl_episode.c:155) */
+        frirl->max_steps = (int)g_bench_steps_target;
+        int reps = atoi(getenv("REF_REPS") ? getenv("REF_REPS") : "1");
+        unsigned long long x = 88172645463325252ull + (unsigned long long)getpid();
+        long steps = 0; double rule_steps = 0;
+        double t0 = now_s();
+        for (int r = 0; r < reps; r++) {
+            for (int k = 0; k < 2 && k < (int)frirl->statedims_len; k++) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;                      /* xorshift64 */
+                frirl->statedims[k].values_def = ((double)(x >> 11) * 0x1p-53 - 0.5) * 3.14159265358979323846;
+            }
+            frirl_episode(frirl);
+            steps += frirl->reward.ep_total_steps;
+            rule_steps += (double)frirl->fiverb->numofrules * frirl->reward.ep_total_steps;
+            frirl->episode_num++;
+        }
+        double dt = now_s() - t0;
+        double msg[4] = { (double)steps, dt, (double)reps, rule_steps };
+        if (g_bench_pipe >= 0) { ssize_t w = write(g_bench_pipe, msg, sizeof msg); (void)w; }
+        return;
+    }
     if (!strcmp(g_mode, "bench")) {
         long steps = 0; int episodes = 0;
+        double rule_steps = 0;                     /* sum over episodes of (rules at episode end) x (steps of the episode) */
+        /* REF_EGREEDY=1: the example's own epsilon with the reference's libc rand() stream (unseedable, frirl_init.c:335-336) -
+         * the same exploration RATE as the GPU arm; default: no_random = 1 as the examples ship */
+        if (getenv("REF_EGREEDY") && atoi(getenv("REF_EGREEDY"))) frirl->no_random = 0;
         double t0 = now_s();
         while (steps < g_bench_steps_target) {
             frirl_episode(frirl);
             steps += frirl->reward.ep_total_steps;
+            rule_steps += (double)frirl->fiverb->numofrules * frirl->reward.ep_total_steps;
             frirl->episode_num++; episodes++;
         }
         double dt = now_s() - t0;
-        double msg[4] = { (double)steps, dt, (double)episodes, (double)frirl->fiverb->numofrules };
+        double msg[4] = { (double)steps, dt, (double)episodes, rule_steps };
         if (g_bench_pipe >= 0) { ssize_t w = write(g_bench_pipe, msg, sizeof msg); (void)w; }
         return;
     }
@@ -264,7 +297,8 @@ int main(int argc, char **argv) {
     if (getenv("REF_MODE")) g_mode = getenv("REF_MODE");
     char *one[2] = { argv[0], NULL };
     int quiet = !getenv("REF_VERBOSE");
-    if (!strcmp(g_mode, "bench")) {
+    if (!strcmp(g_mode, "bench") || !strcmp(g_mode, "infer")) {
+        const int infer = !strcmp(g_mode, "infer");
         int procs = atoi(getenv("REF_PROCS") ? getenv("REF_PROCS") : "1");
         g_bench_steps_target = atol(getenv("REF_STEPS") ? getenv("REF_STEPS") : "15000");
         int reps = atoi(getenv("REF_REPS") ? getenv("REF_REPS") : "1");
@@ -276,20 +310,19 @@ int main(int argc, char **argv) {
             if (pid == 0) {
                 close(fds[0]); g_bench_pipe = fds[1];
                 if (!freopen("/dev/null", "w", stdout)) return 6;
-                for (int r = 0; r < reps; r++) ref_example_main(1, one);
+                for (int r = 0; r < (infer ? 1 : reps); r++) ref_example_main(1, one);   /* infer: the episodes loop inside the hook */
                 _exit(0);
             }
         }
         close(fds[1]);
-        double steps = 0, busy = 0, maxbusy = 0, perproc[4096]; int nmsg = 0; double msg[4];
-        memset(perproc, 0, sizeof perproc);
-        while (read(fds[0], msg, sizeof msg) == (ssize_t)sizeof msg) { steps += msg[0]; busy += msg[1]; nmsg++; }
+        double steps = 0, busy = 0, maxbusy = 0, rule_steps = 0; int nmsg = 0; double msg[4];
+        while (read(fds[0], msg, sizeof msg) == (ssize_t)sizeof msg) { steps += msg[0]; busy += msg[1]; rule_steps += msg[3]; nmsg++; }
         while (wait(NULL) > 0) {}
         double wall = now_s() - t0;
         /* throughput = steps / (sum of in-frirl_episode time / procs): excludes init + file dump */
         double eff = busy / procs; if (eff > maxbusy) maxbusy = eff;
-        printf("REFBENCH env=%s procs=%d reps=%d steps=%.0f busy_s_per_proc=%.6f wall_s=%.6f steps_per_s=%.1f\n",
-               REF_ENV_NAME, procs, reps, steps, eff, wall, steps / eff);
+        printf("REFBENCH env=%s procs=%d reps=%d steps=%.0f busy_s_per_proc=%.6f wall_s=%.6f steps_per_s=%.1f mean_rules=%.2f agents_done=%d\n",
+               REF_ENV_NAME, procs, reps, steps, eff, wall, steps / eff, steps > 0 ? rule_steps / steps : 0.0, nmsg);
         char cmd[256]; snprintf(cmd, sizeof cmd, "rm -rf %s", dir); if (system(cmd)) {}
         return 0;
     }

@@ -454,7 +454,7 @@ def test_inference_mode_leaves_rule_base_untouched(fq):
 
 
 @pytest.mark.parametrize("policy", [0, 2])
-@pytest.mark.parametrize("name,R,n,steps", [("mountaincar", 0, 200, 400), ("acrobot", 700, 150, 120), ("acrobot", 513, 40, 30)])
+@pytest.mark.parametrize("name,R,n,steps", [("mountaincar", 0, 200, 400), ("acrobot", 700, 150, 120), ("acrobot", 513, 40, 30), ("acrobot", 300, 330, 25)])
 def test_shared_rule_base_inference_matches_oracle(fq, name, R, n, steps, policy):
     """BASELINE config 4 in miniature: many agents, ONE read-only rule base, randomised start states, greedy stepping.
     policy 0: one full pass over the rule base per env step (streamed through shared memory by TMA); policy 2 (default):
@@ -477,6 +477,8 @@ def test_shared_rule_base_inference_matches_oracle(fq, name, R, n, steps, policy
     lo = {"mountaincar": [-1.2, -0.05], "acrobot": [-np.pi / 2, -np.pi / 2, 0, 0]}[name]
     hi = {"mountaincar": [0.3, 0.05], "acrobot": [np.pi / 2, np.pi / 2, 0, 0]}[name]
     s0 = rng.uniform(lo, hi, size=(n, P.S))
+    if n == 330:                                        # few DISTINCT start states: the de-duplicated start pass (one warp per distinct
+        s0 = s0[rng.integers(0, 9, n)]                  # universe-index tuple) instead of one streaming pass per agent
     b = fq.Batch(P, n, max(len(rconc), P.ncorner))
     b.set_policy(policy)
     b.set_shared_rulebase(rant, rconc)
