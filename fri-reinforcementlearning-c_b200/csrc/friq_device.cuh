@@ -488,14 +488,38 @@ __device__ __forceinline__ void friq_cellvec_unpack(const friq_cellvec c, unsign
 { cc[0] = c.x & 0xffffu; cc[1] = c.x >> 16; cc[2] = c.y & 0xffffu; cc[3] = c.y >> 16; }
 #endif
 
+// the pair's row of the memoised weights: in global memory (read-only path), or wherever a generic pointer says - shared
+// memory when the row was staged by TMA
+struct friq_row_f64 {
+    const double *__restrict__ row;
+    __device__ __forceinline__ double operator()(unsigned c) const { return __ldg(row + c); }
+};
+struct friq_row_any {
+    const double *row;
+    __device__ __forceinline__ double operator()(unsigned c) const { return row[c]; }
+};
+// per-warp staging area for table rows: `slots` rows of FRIQ_ROW_MAXLEN doubles in shared memory, one mbarrier, its phase bit
+struct friq_rowstage { double *buf; uint64_t *bar; uint32_t phase; int slots; };
 // weights (looked up in the pair's table row through the block's cells) and consequents of one block of rules
-__device__ __forceinline__ void friq_tab_load(const double *__restrict__ rowd, const friq_cellvec c, const double *pq,
+template <class ROW>
+__device__ __forceinline__ void friq_tab_load(const ROW &row, const friq_cellvec c, const double *pq,
                                               double (&t)[FRIQ_CELL_VEC], double (&q)[FRIQ_CELL_VEC])
 {
     unsigned cc[FRIQ_CELL_VEC];
     friq_cellvec_unpack(c, cc);
 #pragma unroll
-    for (int u = 0; u < FRIQ_CELL_VEC; u++) { t[u] = __ldg(rowd + cc[u]); q[u] = pq[(size_t)u * FRIQ_TILE]; }
+    for (int u = 0; u < FRIQ_CELL_VEC; u++) {
+#ifdef FRIQ_EXP_NOTAB
+        t[u] = 1.0 + (double)cc[u];
+#else
+        t[u] = row(cc[u]);
+#endif
+#ifdef FRIQ_EXP_NOQ
+        q[u] = 1.0;
+#else
+        q[u] = pq[(size_t)u * FRIQ_TILE];
+#endif
+    }
 }
 // the block's terms added in rule order (BestAct.c:216-217 / FIVEVagConcl.c:234-235); cnt < block size only for a column's last block
 template <bool FULL>
@@ -511,8 +535,10 @@ __device__ __forceinline__ void friq_tab_acc(const double (&t)[FRIQ_CELL_VEC], c
         if (FULL || u < cnt) { vag = __dadd_rn(vag, __dmul_rn(t[u], q[u])); ws = __dadd_rn(ws, t[u]); }
 }
 // Shepard sums of one pair from the memoised weights: rules 0 .. Rt-1 of column j of the tile; block b+1's loads and block
-// b+2's cells are in flight while block b is added up
-__device__ __forceinline__ void friq_tab_sums(const double *__restrict__ rowd, const unsigned short *rbc_tile, const double *tq, double *tsw,
+// b+2's cells are in flight while block b is added up.  isq: the weights are also left in sw[] (knowledge-sharing runs keep
+// FIVERB.weights from them; the weighted update looks its few candidates up again instead)
+template <class ROW>
+__device__ __forceinline__ void friq_tab_sums(const ROW &row, const unsigned short *rbc_tile, const double *tq, double *tsw,
                                               int j, int Rt, bool isq, double &vag, double &ws)
 {
     constexpr int B = FRIQ_CELL_VEC;
@@ -521,16 +547,16 @@ __device__ __forceinline__ void friq_tab_sums(const double *__restrict__ rowd, c
     const int nb = (Rt + B - 1) / B;
     double tA[B], qA[B], tB[B], qB[B];
     friq_cellvec cn = friq_cellvec_zero();
-    if (nb > 0) friq_tab_load(rowd, pc[0], pq, tA, qA);
+    if (nb > 0) friq_tab_load(row, pc[0], pq, tA, qA);
     if (nb > 1) cn = pc[FRIQ_TILE];
 #pragma unroll 1
     for (int b = 0; b < nb; b += 2) {
         friq_cellvec cnn = friq_cellvec_zero();
-        if (b + 1 < nb) friq_tab_load(rowd, cn, pq + B * FRIQ_TILE, tB, qB);
+        if (b + 1 < nb) friq_tab_load(row, cn, pq + B * FRIQ_TILE, tB, qB);
         if (b + 2 < nb) cnn = pc[(size_t)(b + 2) * FRIQ_TILE];
         { const int cnt = Rt - B * b; if (cnt >= B) friq_tab_acc<true>(tA, qA, B, isq, psw, vag, ws); else friq_tab_acc<false>(tA, qA, cnt, isq, psw, vag, ws); }
         if (b + 1 < nb) {
-            if (b + 2 < nb) friq_tab_load(rowd, cnn, pq + 2 * B * FRIQ_TILE, tA, qA);
+            if (b + 2 < nb) friq_tab_load(row, cnn, pq + 2 * B * FRIQ_TILE, tA, qA);
             cn = friq_cellvec_zero();
             if (b + 3 < nb) cn = pc[(size_t)(b + 3) * FRIQ_TILE];
             const int cnt = Rt - B * (b + 1);
@@ -567,7 +593,8 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
                                                      const double *vo_obs, const double *vo_q, uint32_t ow, uint32_t qw,
                                                      unsigned wmask, const unsigned (&nm)[A], unsigned qm,
                                                      unsigned char *plist /* 32 bytes of shared memory per warp */,
-                                                     double (&conc)[A], double &vagq, double &wsq, unsigned &n_tab, unsigned &n_chain)
+                                                     double (&conc)[A], double &vagq, double &wsq, unsigned &n_tab, unsigned &n_chain, bool keep_sw,
+                                                     friq_rowstage &rs)
 {
     constexpr int K = S + 1, C = A + 1;
     const int lane = threadIdx.x & 31;
@@ -618,10 +645,31 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             const int ah = pb.act_hit[c < A ? c : 0];
             const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET);
             const bool tab = has && pw != FRIQ_NO_TARGET;
+            const double *rowd = pb.wtab + (size_t)(tab ? friq_cell<K>(pb, pw) : 0) * (size_t)pb.wstride;
+            // the first rs.slots pairs of the round get their whole table row into shared memory: one cp.async.bulk (TMA) per row,
+            // completion on the warp's mbarrier; the lookups of the walk are then shared-memory reads instead of L2 round trips
+            const bool stage = tab && rank < rs.slots;
+            const unsigned stm = rs.slots ? __ballot_sync(wmask, stage) : 0u;
+            if (stm) {                                   // warp-uniform
+                const uint32_t bytes = (uint32_t)pb.wstride * 8u, bar = (uint32_t)__cvta_generic_to_shared(rs.bar);
+                if (rank == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)__popc(stm)) : "memory");
+                __syncwarp(wmask);
+                if (stage) {
+                    double *dst = rs.buf + (size_t)rank * FRIQ_ROW_MAXLEN;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of this slot are done
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(rowd), "r"(bytes), "r"(bar) : "memory");
+                    rowd = dst;
+                }
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                                 : "=r"(ok) : "r"(bar), "r"(rs.phase) : "memory");
+                rs.phase ^= 1u;
+            }
             if (tab) {
-                const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wcells;
                 asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
-                friq_tab_sums(rowd, rbc, tq, tsw, j, Rj, isq, vag, ws);
+                friq_tab_sums(friq_row_any{rowd}, rbc, tq, tsw, j, Rj, isq && keep_sw, vag, ws);
                 n_tab += (unsigned)Rj;
             }
             const bool slow = has && !tab;
@@ -760,10 +808,12 @@ __device__ __forceinline__ int friq_snap_index(const friq_devprob &pb, int k, do
 #ifndef FRIQ_WUPD_VEC
 #define FRIQ_WUPD_VEC 4         /* rules per trip of the weighted-update loop (loads in flight per L2 round trip; 8 and 16 measured no better) */
 #endif
-template <int S, int P, bool COLD = false>
+struct friq_row_none { __device__ __forceinline__ double operator()(unsigned) const { return 0.0; } };
+template <int S, int P, bool COLD = false, class ROW = friq_row_none>
 __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_t *rbw, double *rbq, double *sw, int cap, int &R, int &flags,
                                                  const double *qs, const int *qi, double reward, double qp, int hitq, double qnow, double ws,
-                                                 double alpha, double gamma, double *wref = nullptr, unsigned *n_wupd = nullptr)
+                                                 double alpha, double gamma, double *wref = nullptr, unsigned *n_wupd = nullptr,
+                                                 const ROW *wrow = nullptr, const unsigned short *rbc_tile = nullptr)
 {   // qi[k] >= 0: qs[k] is known to BE the grid value dict_val[k][qi[k]] (snapping an on-grid value returns it)
     constexpr int K = S + 1;
     const double qdiff = __dmul_rn(alpha, __dsub_rn(__dadd_rn(reward, __dmul_rn(gamma, qp)), qnow));   // :358
@@ -806,6 +856,30 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
     // FRIQ_WUPD_VEC rules share it.  ncu, acrobot: this loop holds 24 % of the kernel's samples at 4; measured: 8 = no change, 16 = 19 % slower, profiles/README.md)
     const double pre = (pb.wsig >= 0.05) ? __dmul_rn(0.04, ws) : -1.0;
     if (n_wupd) *n_wupd += (unsigned)rules;
+    if (wrow) {
+        // table mode, FEW lanes of the warp updating (friq_pairs_compacted then does not store the weights it sums): the owner
+        // looks the weights up again - the pair's table row and its own cell blocks are in L1 from the sums - instead of reading
+        // what another lane would have had to store for it (mountaincar: +2.7 %; with MANY updating lanes, acrobot, the stored
+        // weights win because the owners' reads of one slot coalesce: -10 % when looked up, profiles/README.md)
+        const friq_cellvec *pc = reinterpret_cast<const friq_cellvec *>(rbc_tile) + (threadIdx.x & 31);
+#pragma unroll 1
+        for (int i = 0; i < rules; i += FRIQ_CELL_VEC) {
+            unsigned cc[FRIQ_CELL_VEC];
+            friq_cellvec_unpack(pc[(size_t)(i / FRIQ_CELL_VEC) * FRIQ_TILE], cc);
+            double wi[FRIQ_CELL_VEC]; bool any = false;
+#pragma unroll
+            for (int u = 0; u < FRIQ_CELL_VEC; u++) { wi[u] = (*wrow)(cc[u]); if (i + u >= rules) wi[u] = -2.0; any = any || (wi[u] > pre); }
+            if (!any) continue;
+#pragma unroll
+            for (int u = 0; u < FRIQ_CELL_VEC; u++) {
+                if (wi[u] > pre) {
+                    const double wgt = __ddiv_rn(wi[u], ws);                                                         // A6
+                    if (wgt > pb.wsig) rbq[(size_t)(i + u) * FRIQ_TILE] = __dadd_rn(qnow, __dmul_rn(qdiff, wgt));    // A7
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int i = 0; i < rules; i += FRIQ_WUPD_VEC) {
         double wi[FRIQ_WUPD_VEC]; bool any = false;
@@ -970,6 +1044,7 @@ template <> __device__ __forceinline__ void friq_env_reward<FRIQ_ENV_CARTPOLE>(c
     }
 }
 
+__device__ __noinline__ int friq_quantize_exact(double y, double div) { return (int)round(__ddiv_rn(y, div)); }   // mountaincar.c:107, acrobot.c:174
 // quantise_observations: writes the quantised state q[] and its VE values vo[]
 template <int ENV, int S>
 __device__ __forceinline__ void friq_env_quantize(const friq_devprob &pb, const double *s, double *q, double *vo, int *qidx)
@@ -991,7 +1066,14 @@ __device__ __forceinline__ void friq_env_quantize(const friq_devprob &pb, const 
     } else {                                             // mountaincar.c:98-125, acrobot.c:165-192
 #pragma unroll
         for (int k = 0; k < S; k++) {
-            int where = (int)round(__ddiv_rn(__dadd_rn(s[k], pb.q_abs0[k]), pb.q_div[k]));
+            // where = (int)round((s + |values[0]|) / div), without the division: ta = y * RN(1 / div) is within 1.5 * 2^-52 relative of
+            // RN(y / div), so both round to the same integer unless a half-integer boundary lies within 2^-49 |ta| of ta - only
+            // then (never in practice) the exact division decides.  Negative quotients all clamp to index 0 whatever their rounding.
+            const double y = __dadd_rn(s[k], pb.q_abs0[k]);
+            const double ta = __dmul_rn(y, pb.q_rdiv[k]);
+            const double fl = floor(ta), fr = __dsub_rn(ta, fl);
+            int where = (int)fl + (fr >= 0.5 ? 1 : 0);
+            if (fabs(__dsub_rn(fr, 0.5)) <= __dmul_rn(fabs(ta), 0x1p-49)) where = friq_quantize_exact(y, pb.q_div[k]);
             if (where < 0) where = 0; else if (where > pb.grid_len[k] - 1) where = pb.grid_len[k] - 1;
             q[k] = pb.dict_val[k][where];
             vo[k] = pb.dict_ve[k][where];                // = VE_k[nearest_index(values[where])]

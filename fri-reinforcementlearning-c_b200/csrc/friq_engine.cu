@@ -46,13 +46,19 @@
 #ifndef FRIQ_COOP_MAXPAIRS
 #define FRIQ_COOP_MAXPAIRS 64 /* at most this many (lane, action) pairs of a warp without an exact hit: compacted Shepard sums (<= 2 rounds) */
 #endif
+#ifndef FRIQ_WUPD_LOOKUP_MAX
+#define FRIQ_WUPD_LOOKUP_MAX 8 /* at most this many lanes of a warp with a weighted update pending: they look their weights up again instead of reading sw[] */
+#endif
+#ifndef FRIQ_ROW_SLOTS
+#define FRIQ_ROW_SLOTS 4     /* table rows staged into shared memory per warp and round (2 KB each) */
+#endif
 #ifndef FRIQ_QCOOP_MAX
 #define FRIQ_QCOOP_MAX 8     /* fewer lanes than this needing Q(s,a): friq_q_cooperative instead of the WITHQ pass */
 #endif
 
 #ifdef FRIQ_TIMELINE   /* experiments only (tools/timeline.py): one record per warp of k_run_steps */
 #define FRIQ_TL_MAX (1 << 18)
-__device__ unsigned long long friq_tl_buf[FRIQ_TL_MAX][4];
+__device__ unsigned long long friq_tl_buf[FRIQ_TL_MAX][6];
 __device__ unsigned int friq_tl_n;
 __device__ __forceinline__ unsigned long long friq_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned int friq_smid() { unsigned int v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
@@ -87,6 +93,12 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 {
     constexpr int K = S + 1;
     __shared__ unsigned char pair_list[FRIQ_BLOCK / 32][32];            // friq_pairs_compacted, per warp
+    // table mode, short rows (mountaincar: 231 cells = 1.8 KB): the table rows of the first ROWS pairs of a round are staged into
+    // shared memory by ONE cp.async.bulk (TMA) each, completion on the warp's mbarrier - the table (427 KB) does not fit L1, and
+    // looked up in global memory every block of 8 rules pays an L2 round trip (95 cycles per rule on an otherwise idle SM)
+    constexpr int ROWS = (COOP == 2 && ENV == FRIQ_ENV_MOUNTAINCAR) ? FRIQ_ROW_SLOTS : 0;
+    __shared__ __align__(16) double rowbuf[ROWS ? FRIQ_BLOCK / 32 : 1][ROWS ? ROWS : 1][ROWS ? FRIQ_ROW_MAXLEN : 2];
+    __shared__ uint64_t rowbar[FRIQ_BLOCK / 32];
 #ifdef FRIQ_TIMELINE
     const unsigned long long tl_t0 = friq_globaltimer();
 #endif
@@ -134,9 +146,21 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     // an episode spends one iteration on the initial action selection (frirl_episode.c:78) while its
     // neighbours step, and a lane that has finished idles until the slowest lane of the warp is done.
     const unsigned wmask = __activemask();
+    friq_rowstage rs; rs.buf = nullptr; rs.bar = &rowbar[threadIdx.x >> 5]; rs.phase = 0; rs.slots = 0;
+    if constexpr (ROWS > 0) {
+        if (pb.wstride <= FRIQ_ROW_MAXLEN) { rs.buf = &rowbuf[threadIdx.x >> 5][0][0]; rs.slots = ROWS; }
+        if ((int)(threadIdx.x & 31) == __ffs(wmask) - 1) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(rs.bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp(wmask);
+    }
     long done_steps = 0;
     bool running = true;
     unsigned c_pairs = 0, c_tab = 0, c_chain = 0, c_hit = 0, c_app = 0, c_wupd = 0;    // executed-work counters (friq_devstate.ctr)
+#ifdef FRIQ_TIMELINE
+    long long tl_cyc = 0; unsigned tl_rounds = 0, tl_pairs = 0, tl_walk = 0; const long long tl_k0 = clock64();
+#endif
     while (__any_sync(wmask, running && done_steps < n_steps)) {
         const bool act = running && done_steps < n_steps && !((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED));
         const bool initial = flags & FRIQ_F_NEED_RESET;
@@ -178,7 +202,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         const unsigned qm = __ballot_sync(wmask, needq);
         // exact hits first (BestAct.c:89-93): where distance 0 <=> equal dictionary indices, an integer sweep finds them, and only
         // the (lane, action) pairs without one need Shepard sums - cooperatively when few, else through the lock-step pass
-        bool lockstep = true;
+        bool lockstep = true, kept_sw = true;
         uint32_t ow = FRIQ_NO_TARGET;
         if constexpr (COOP || A == ACH) if (COOP || pb.hit_scan) {
             ow = friq_obs_word<S>(pb, vc, ci);
@@ -200,7 +224,17 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 #pragma unroll
                 for (int a = 0; a < A; a++) actconc[a] = (hidx[a] >= 0) ? rbq[(size_t)hidx[a] * FRIQ_TILE] : 0.0;
                 vagq = 0.0; wsq = 0.0;
-                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq, c_tab, c_chain);
+                // weighted updates read the weights of Q(s,a): handed over through sw[] when MANY lanes update (their reads of a slot
+                // coalesce), looked up again by the owner when few do (FRIQ_WUPD_LOOKUP_MAX); knowledge-sharing runs always keep them
+                kept_sw = !tabmode || wref != nullptr || __popc(qm) > FRIQ_WUPD_LOOKUP_MAX;
+#ifdef FRIQ_TIMELINE
+                const long long tl_c0 = clock64();
+                if (pairs | qm) { tl_rounds++; tl_pairs += pairs + __popc(qm); tl_walk += __reduce_max_sync(wmask, (act && (needq || hidx[0] < 0 || hidx[A - 1] < 0 || hidx[A / 2] < 0)) ? R : 0); }
+#endif
+                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq, c_tab, c_chain, kept_sw, rs);
+#ifdef FRIQ_TIMELINE
+                tl_cyc += clock64() - tl_c0;
+#endif
             }
         }
         if (!COOP && lockstep) {
@@ -215,6 +249,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         }
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
+        const uint32_t qw_upd = qw;                      // the pending update's point (its weights are looked up again by the weighted update)
         if (act) qw = (ow != FRIQ_NO_TARGET && pb.act_hit[a2] >= 0) ? (ow | ((uint32_t)pb.act_hit[a2] << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET;
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }
         if (act && !initial) {
@@ -232,7 +267,13 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 if (hitq >= 0) qnow = rbq[(size_t)hitq * FRIQ_TILE];
                 else { ws = wsq; qnow = __ddiv_rn(vagq, wsq); }                               // FIVEVagConcl.c:302
                 const int R0 = R;
-                friq_sarsa_apply<S, P, true>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref, &c_wupd);
+                if constexpr (tabmode) {
+                    const bool look = !kept_sw && qw_upd != FRIQ_NO_TARGET;
+                    const friq_row_f64 row{pb.wtab + (size_t)(look ? friq_cell<K>(pb, qw_upd) : 0) * (size_t)pb.wstride};
+                    friq_sarsa_apply<S, P, true, friq_row_f64>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref, &c_wupd,
+                                                               look ? &row : nullptr, rbc);
+                } else
+                    friq_sarsa_apply<S, P, true>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref, &c_wupd);
                 hitq = next_hit;
                 c_app += (unsigned)(R - R0);
                 if (R > R0 && tabmode) {                 // a rule was appended: keep the indexes current
@@ -304,10 +345,124 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 friq_tl_buf[i][0] = tl_t0; friq_tl_buf[i][1] = friq_globaltimer();
                 friq_tl_buf[i][2] = ((unsigned long long)friq_smid() << 32) | (unsigned long long)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
                 friq_tl_buf[i][3] = ((unsigned long long)rmax << 32) | (unsigned long long)rmin | ((unsigned long long)(st.n & 0xffff) << 48);
+                friq_tl_buf[i][4] = ((unsigned long long)(clock64() - tl_k0) << 32) | (unsigned long long)(tl_cyc & 0xffffffffll);     // kernel cycles | cycles inside friq_pairs_compacted
+                friq_tl_buf[i][5] = ((unsigned long long)tl_rounds << 48) | ((unsigned long long)(tl_pairs & 0xffffff) << 24) | (unsigned long long)(tl_walk & 0xffffff);
             }
         }
     }
 #endif
+}
+
+// ---------------------------------------------------------------------------------------
+// k_run_steps_anyA: the fused step loop for problems on a built-in environment that are NOT one of the three example shapes -
+// another action set (run-time A <= FRIQ_MAXA), other grids.  Same step semantics as k_run_steps (frirl_episode.c:86-186), plain
+// evaluation: the best-action pass walks the rule base once per action (friq_action_pass), Q(s,a) and Q(s',a') are
+// library-exact conclusions (FIVE_vag_concl), no exact-hit forwarding, no tables.  One thread per agent, lanes independent.
+// ---------------------------------------------------------------------------------------
+template <int S, int P, int ENV>
+__global__ void __launch_bounds__(FRIQ_BLOCK, 512 / FRIQ_BLOCK)
+k_run_steps_anyA(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
+{
+    constexpr int K = S + 1;
+    FRIQ_SMEM_PROLOGUE();
+    const int A = pb.A;
+    double *prevq = st.prevq ? st.prevq + tile_off : nullptr;
+    double *wref = ((mode & FRIQ_M_KEEP_WEIGHTS) && st.wref) ? st.wref + tile_off : nullptr;
+    double s[S], qs[K], vo[K];
+#pragma unroll
+    for (int k = 0; k < S; k++) s[k] = st.s[(size_t)k * st.n_pad + ag];
+#pragma unroll
+    for (int k = 0; k < K; k++) { qs[k] = st.qs[(size_t)k * st.n_pad + ag]; vo[k] = st.vo[(size_t)k * st.n_pad + ag]; }
+    int aidx = st.aidx[ag], flags = st.flags[ag], R = st.R[ag], step_in_ep = st.step_in_ep[ag];
+    uint32_t ep_num = st.ep_num[ag];
+    double ep_return = st.ep_return[ag];
+    double prev_reward = st.prev_reward[ag]; int prev_steps = st.prev_steps[ag], prev_numru = st.prev_numru[ag];
+    double last_return = st.last_return[ag]; int last_steps = st.last_steps[ag], last_rules = st.last_rules[ag];
+    unsigned long long total_steps = st.total_steps[ag], sum_rules = st.sum_rules[ag];
+    const unsigned long long seed = st.seed[ag];
+    const double alpha = st.alpha[ag], gamma = st.gamma[ag], epsilon = st.epsilon[ag];
+    const bool learn = mode & FRIQ_M_LEARN, track = (mode & FRIQ_M_TRACK) && prevq;
+    long done_steps = 0;
+    bool running = true;
+    while (running && done_steps < n_steps) {
+        if ((mode & FRIQ_M_STOP_ON_CONVERGE) && (flags & FRIQ_F_CONVERGED)) break;
+        const bool initial = flags & FRIQ_F_NEED_RESET;
+        double cur[S], cq[S], vc[K], reward = 0.0; int done = 0, ci[S];
+        if (initial) {                                   // frirl_episode.c:46-82
+#pragma unroll
+            for (int k = 0; k < S; k++) {
+                s[k] = qs[k] = st.s0 ? st.s0[(size_t)k * st.n_pad + ag] : pb.values_def[k];
+                vo[k] = vc[k] = st.s0 ? friq_obs_ve(pb, k, s[k]) : pb.ve_def[k];
+                cur[k] = cq[k] = s[k];
+            }
+            ep_return = 0.0; step_in_ep = 0; flags &= ~FRIQ_F_NEED_RESET;
+            prev_numru = R;
+            if (track) for (int i = 0; i < R; i++) prevq[(size_t)i * FRIQ_TILE] = rbq[(size_t)i * FRIQ_TILE];   // sequential_run.c:72
+        } else {                                         // frirl_episode.c:97-112
+            friq_env_step<ENV>(pb.act_val[aidx], s, cur);
+            friq_env_reward<ENV>(cur, reward, done);
+            ep_return = __dadd_rn(ep_return, reward);
+            friq_env_quantize<ENV, S>(pb, cur, cq, vc, ci);
+            step_in_ep++;
+        }
+        // frirl_get_best_action (frirl_get_best_action.c:31-341): first index of the maximum (max.inl:16-28)
+        int best = 0; double bv = 0.0;
+        for (int a = 0; a < A; a++) {
+            double conc; int hidx;
+            friq_action_pass<S, P, 1, false>(pb, rbw, rbq, R, vc, pb.act_ve[a], conc, hidx);
+            if (a == 0 || bv < conc) { bv = conc; best = a; }
+        }
+        int a2 = best;                                   // frirl_e_greedy_selection.c:21-37 with the Philox stream
+        if (pb.no_random != 1 && epsilon != 0.0) {
+            uint32_t r[4];
+            friq_philox4x32_10(ep_num, (uint32_t)step_in_ep, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+            const double u1 = (double)((((uint64_t)r[1] << 32) | r[0]) >> 11) * 0x1p-53;
+            const double u2 = (double)((((uint64_t)r[3] << 32) | r[2]) >> 11) * 0x1p-53;
+            if (!(u1 > epsilon)) { const int ra = (int)floor(__dmul_rn(u2, (double)A)); a2 = ra > A - 1 ? A - 1 : ra; }
+        }
+        if (initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; }
+        else {
+            sum_rules += (unsigned long long)R;
+            if (learn) {                                 // frirl_update_sarsa.c:348-385
+                double qp, qnow, wsp, ws;
+                vc[S] = pb.act_ve_eval[a2];
+                friq_vag_concl<K, P>(pb, rbw, rbq, nullptr, R, vc, qp, wsp);                    // :355
+                const int hitq = friq_vag_concl<K, P>(pb, rbw, rbq, sw, R, vo, qnow, ws);       // :356
+                int qi[K];
+#pragma unroll
+                for (int k = 0; k < K; k++) qi[k] = -1;
+                friq_sarsa_apply<S, P>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref);
+            }
+#pragma unroll
+            for (int k = 0; k < S; k++) { s[k] = cur[k]; qs[k] = cq[k]; vo[k] = vc[k]; }
+            aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2];
+            total_steps++; done_steps++;
+            if (done || step_in_ep >= pb.max_steps) {
+                if (learn && track && prev_numru == R && prev_steps == step_in_ep && ep_return > pb.reward_good_above && prev_reward == ep_return) {
+                    flags |= FRIQ_F_EPENDED;             // frirl_sequential_run.c:83-150
+                    bool ok = true;
+                    for (int i = 0; i < R && ok; i++)
+                        if (fabs(__dsub_rn(rbq[(size_t)i * FRIQ_TILE], prevq[(size_t)i * FRIQ_TILE])) >= pb.qdiff_final_tol) ok = false;
+                    if (ok) flags |= FRIQ_F_CONVERGED;
+                }
+                last_return = ep_return; last_steps = step_in_ep; last_rules = R;
+                prev_reward = ep_return; prev_steps = step_in_ep;
+                ep_num++;
+                flags |= FRIQ_F_NEED_RESET;
+                if (mode & FRIQ_M_STOP_AT_EPISODE_END) running = false;
+            }
+        }
+    }
+    if (st.ctr && done_steps) atomicAdd(st.ctr + FRIQ_CTR_STEPS, (unsigned long long)done_steps);
+#pragma unroll
+    for (int k = 0; k < S; k++) st.s[(size_t)k * st.n_pad + ag] = s[k];
+#pragma unroll
+    for (int k = 0; k < K; k++) { st.qs[(size_t)k * st.n_pad + ag] = qs[k]; st.vo[(size_t)k * st.n_pad + ag] = vo[k]; }
+    st.aidx[ag] = aidx; st.flags[ag] = flags; st.R[ag] = R; st.step_in_ep[ag] = step_in_ep; st.hitq[ag] = -2;
+    st.ep_num[ag] = ep_num; st.ep_return[ag] = ep_return;
+    st.prev_reward[ag] = prev_reward; st.prev_steps[ag] = prev_steps; st.prev_numru[ag] = prev_numru;
+    st.last_return[ag] = last_return; st.last_steps[ag] = last_steps; st.last_rules[ag] = last_rules;
+    st.total_steps[ag] = total_steps; st.sum_rules[ag] = sum_rules;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1197,11 +1352,12 @@ __global__ void k_team_ctl(friq_devstate st, int team, int op, int max_episodes,
 // memoised Shepard weights (friq_devprob.wtab): wtab[q * cells + r] = 1 / d(q, r)^p for every pair of dictionary cells, through the
 // same device functions as a computed chain (friq_dist2 left-to-right over the dimensions, sqrt, x87 power, reciprocal)
 template <int K, int P>
-__global__ void k_build_wtab(const friq_devprob *__restrict__ gprob, double *__restrict__ wtab, int cells)
+__global__ void k_build_wtab(const friq_devprob *__restrict__ gprob, double *__restrict__ wtab, int cells, int stride)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long)cells * cells) return;
-    int q = (int)(t / cells), r = (int)(t % cells);
+    const int q0 = (int)(t / cells), r0 = (int)(t % cells);
+    int q = q0, r = r0;
     double pt[K]; uint32_t w = 0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -1209,7 +1365,7 @@ __global__ void k_build_wtab(const friq_devprob *__restrict__ gprob, double *__r
         pt[k] = gprob->dict_ve[k][q % n]; q /= n;
         w |= (uint32_t)(r % n) << (FRIQ_IDX_BITS * k); r /= n;
     }
-    wtab[t] = friq_shepard_weight<P>(friq_dist2<K>(*gprob, w, pt));
+    wtab[(size_t)q0 * stride + r0] = friq_shepard_weight<P>(friq_dist2<K>(*gprob, w, pt));
 }
 
 __global__ void k_trig(const double *x, double *s, double *c, long n)
@@ -1344,7 +1500,7 @@ int friqd_timeline_fetch(unsigned long long *host, int max_entries, int reset)
     CK(cudaMemcpyFromSymbol(&n, friq_tl_n, sizeof n));
     if (n > FRIQ_TL_MAX) n = FRIQ_TL_MAX;
     if ((int)n > max_entries) n = max_entries;
-    if (host && n) CK(cudaMemcpyFromSymbol(host, friq_tl_buf, (size_t)n * 32));
+    if (host && n) CK(cudaMemcpyFromSymbol(host, friq_tl_buf, (size_t)n * 48));
     if (reset) { const unsigned int z = 0; CK(cudaMemcpyToSymbol(friq_tl_n, &z, sizeof z)); }
     return (int)n;
 }
@@ -1359,7 +1515,7 @@ int friqd_device_sync(void) { CK(cudaDeviceSynchronize()); return 0; }
 int friqd_sync(void *stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
 const char *friqd_error_string(int err)
 {
-    if (err == FRIQ_ERR_SHAPE) return "unsupported problem shape: per-call entry points need 1 <= S <= 4 state dimensions, p = S + 1 and A <= 32 actions; the fused kernels the shapes (S, p, A) of the three examples";
+    if (err == FRIQ_ERR_SHAPE) return "unsupported problem shape: per-call entry points need 1 <= S <= 4 state dimensions, p = S + 1 and A <= 32 actions; the fused kernels a built-in environment with its own number of state dimensions (any action set of <= 32 actions)";
     return cudaGetErrorString((cudaError_t)err);
 }
 
@@ -1371,16 +1527,6 @@ int friqd_init_agents(const friq_devprob *dprob, friq_devstate st, unsigned long
     return 0;
 }
 
-// the table-mode kernel lives off L1 (rule rows, cell maps, table rows) and needs 10 KB of shared memory per CTA: ask for the
-// smallest shared-memory carve-out once per kernel (a hint; FRIQ_CARVEOUT_PCT < 0 leaves the driver's default)
-#ifndef FRIQ_CARVEOUT_PCT
-#define FRIQ_CARVEOUT_PCT (-1)   /* measured: 0 % starves the CTAs of shared memory (3.7e9), 25 % == default (5.0e9) */
-#endif
-#define FRIQ_CARVEOUT(kernel)                                                                                          \
-    do {                                                                                                              \
-        static bool done_ = false;                                                                                    \
-        if (!done_ && FRIQ_CARVEOUT_PCT >= 0) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, FRIQ_CARVEOUT_PCT); done_ = true; } \
-    } while (0)
 int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devstate st, long n_steps, int mode, int variant, void *stream)
 {   // evaluation policy (friq_batch_set_policy): 0 lock-step pass over all actions (+ hit sweep / compacted sums when few pairs lack
     // a hit); 1 exact hits first + compacted Shepard chains only; 2 the same in table mode (memoised weights, per-agent indexes)
@@ -1398,13 +1544,8 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
         if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
         else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
     } while (0)
-    if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR) {
-        FRIQ_CARVEOUT((k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2>));
-        k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    } else if (tab && hp->env == FRIQ_ENV_ACROBOT) {
-        FRIQ_CARVEOUT((k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2>));
-        k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    }
+    if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR) k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (tab && hp->env == FRIQ_ENV_ACROBOT) k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else if (coop && hp->env == FRIQ_ENV_MOUNTAINCAR)
         k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else if (coop && hp->env == FRIQ_ENV_ACROBOT)
@@ -1412,6 +1553,13 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     else if (hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) FRIQ_LAUNCH_STEP(2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, FRIQ_UNR_MC);
     else if (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)) FRIQ_LAUNCH_STEP(4, 5, 3, 3, FRIQ_ENV_ACROBOT, 2);
     else if (hp->env == FRIQ_ENV_CARTPOLE && FRIQ_SHAPE_CP(hp)) FRIQ_LAUNCH_STEP(4, 5, 21, 3, FRIQ_ENV_CARTPOLE, 1);
+    // any other action set / grid on a built-in environment: the plain fused loop
+    else if (hp->env == FRIQ_ENV_MOUNTAINCAR && hp->S == 2 && hp->p == 3 && hp->A >= 1 && hp->A <= FRIQ_MAXA)
+        k_run_steps_anyA<2, 3, FRIQ_ENV_MOUNTAINCAR><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (hp->env == FRIQ_ENV_ACROBOT && hp->S == 4 && hp->p == 5 && hp->A >= 1 && hp->A <= FRIQ_MAXA)
+        k_run_steps_anyA<4, 5, FRIQ_ENV_ACROBOT><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    else if (hp->env == FRIQ_ENV_CARTPOLE && hp->S == 4 && hp->p == 5 && hp->A >= 1 && hp->A <= FRIQ_MAXA)
+        k_run_steps_anyA<4, 5, FRIQ_ENV_CARTPOLE><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1576,8 +1724,8 @@ int friqd_build_wtab(const friq_devprob *hp, const friq_devprob *dprob, double *
 {
     const long n = (long)hp->wcells * hp->wcells;
     const unsigned g = (unsigned)((n + 255) / 256);
-    if (hp->K == 3 && hp->p == 3) k_build_wtab<3, 3><<<g, 256>>>(dprob, d_wtab, hp->wcells);
-    else if (hp->K == 5 && hp->p == 5) k_build_wtab<5, 5><<<g, 256>>>(dprob, d_wtab, hp->wcells);
+    if (hp->K == 3 && hp->p == 3) k_build_wtab<3, 3><<<g, 256>>>(dprob, d_wtab, hp->wcells, hp->wstride);
+    else if (hp->K == 5 && hp->p == 5) k_build_wtab<5, 5><<<g, 256>>>(dprob, d_wtab, hp->wcells, hp->wstride);
     else return (int)cudaErrorInvalidValue;
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

@@ -224,7 +224,7 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
             hp->dict_ve[k][j] = ve[nearest_index(u, U, U, hp->udiv[k], hp->dict_val[k][j])];
         hp->values_def[k] = dim->values_def;
         hp->ve_def[k] = ve[nearest_index(u, U, U, hp->udiv[k], dim->values_def)];
-        hp->q_abs0[k] = fabs(hp->dict_val[k][0]); hp->q_div[k] = dim->values_div;
+        hp->q_abs0[k] = fabs(hp->dict_val[k][0]); hp->q_div[k] = dim->values_div; hp->q_rdiv[k] = 1.0 / dim->values_div;
         /* frirl_check_possible_states.c:68 would refine the grid when epsilon <= step/2; the device keeps grids fixed */
         for (int j = 1; j < dim->values_len; j++)
             if (dim->values_div <= fabs(hp->dict_val[k][j] - hp->dict_val[k][j - 1]) / 2) {
@@ -325,15 +325,17 @@ static int problem_publish(friq_problem *P)
 {
     friq_devprob *hp = &P->hp;
     if (P->d_wtab) { DEV(friqd_device_sync()); DEV(friqd_free(P->d_wtab)); P->d_wtab = NULL; }
-    hp->wtab = NULL; hp->wcells = 0;
+    hp->wtab = NULL; hp->wcells = 0; hp->wstride = 0;
     if ((hp->env == FRIQ_ENV_MOUNTAINCAR || hp->env == FRIQ_ENV_ACROBOT) && hp->hit_scan && hp->qp_reuse) {
         unsigned long cells = 1; int ok = 1;
         for (int k = 0; k < hp->K; k++) { hp->wlin[k] = (int)cells; cells *= (unsigned long)hp->dict_len[k]; if (cells > 65535ul) { ok = 0; break; } }
         for (int a = 0; a < hp->A; a++) if (hp->act_hit[a] < 0) ok = 0;
-        if (ok && cells * cells * 8ul <= FRIQ_WTAB_MAX_BYTES) {
+        const unsigned long stride = (cells + 1ul) & ~1ul;
+        if (ok && cells * stride * 8ul <= FRIQ_WTAB_MAX_BYTES) {
             DEV(friqd_h2d(P->dp, hp, sizeof(friq_devprob)));          /* the build kernel reads the dictionaries */
-            DEV(friqd_malloc((void **)&P->d_wtab, cells * cells * 8ul));
-            hp->wcells = (int)cells;
+            DEV(friqd_malloc((void **)&P->d_wtab, cells * stride * 8ul));
+            DEV(friqd_memset(P->d_wtab, 0, cells * stride * 8ul));
+            hp->wcells = (int)cells; hp->wstride = (int)stride;
             DEV(friqd_build_wtab(hp, P->dp, P->d_wtab));
             hp->wtab = P->d_wtab;
         }
@@ -362,7 +364,10 @@ static int problem_upload(friq_problem *P, int device)
 void friq_problem_destroy(friq_problem *P)
 {
     if (!P) return;
-    if (P->device != -1) { friqd_set_device(P->device); friqd_free(P->d_u); friqd_free(P->d_ve); friqd_free(P->dp); if (P->d_wtab) friqd_free(P->d_wtab); }
+    if (P->device != -1) {
+        friqd_set_device(P->device); friqd_free(P->d_u); friqd_free(P->d_ve); friqd_free(P->dp);
+        if (P->d_wtab) friqd_free(P->d_wtab);
+    }
     free(P->u); free(P->ve); free(P);
 }
 
@@ -504,8 +509,8 @@ int friq_batch_create(friq_problem *P, int device, long n, int cap, uint64_t see
 }
 
 /* evaluation policy of the fused kernel: 0 lock-step pass over all actions, 1 exact hits first + compacted Shepard chains,
- * 2 the same with memoised weights (table mode).  A policy the problem does not qualify for falls back to the next lower one;
- * results never depend on it (tests/test_gpu_parity.py compares all of them with the oracle). */
+ * 2 the same with memoised weights (table mode).  A policy the problem does not qualify for falls back to the next lower one; results never depend on it
+ * (tests/test_gpu_parity.py compares all of them with the oracle). */
 int friq_batch_set_policy(friq_batch *b, int policy)
 {
     if (policy < 0 || policy > 2) FAIL(4, "friq_batch_set_policy: policy %d (0, 1 or 2)", policy);
@@ -875,6 +880,17 @@ int friq_batch_gather_device(friq_batch *b, void *d_ret, void *d_steps, void *d_
 int friq_batch_run_host(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon, long n_steps, int mode,
                         double *last_return, int *last_steps, int *rules, void *stream)
 {
+    int rc = friq_batch_run_host_async(b, alpha, gamma, epsilon, n_steps, mode, last_return, last_steps, rules, stream);
+    if (rc) return rc;
+    DEV(friqd_sync(stream));
+    return 0;
+}
+/* the same without the final synchronisation: copies in, run, copies out are all enqueued on `stream`; the host buffers (pinned
+ * memory for real overlap) are valid once the stream has passed this point (an event recorded after the call) - a caller with two
+ * buffer sets reads step i's results while step i + 1 runs */
+int friq_batch_run_host_async(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon, long n_steps, int mode,
+                              double *last_return, int *last_steps, int *rules, void *stream)
+{
     const long n = b->st.n;
     DEV(friqd_set_device(b->device));
     if (alpha || gamma || epsilon) {                     /* host arrays are in agent order */
@@ -902,7 +918,6 @@ int friq_batch_run_host(friq_batch *b, const double *alpha, const double *gamma,
     if (last_return) DEV(friqd_d2h_async(last_return, s_ret, 8 * n, stream));
     if (last_steps) DEV(friqd_d2h_async(last_steps, s_steps, 4 * n, stream));
     if (rules) DEV(friqd_d2h_async(rules, s_rules, 4 * n, stream));
-    DEV(friqd_sync(stream));
     return 0;
 }
 

@@ -198,6 +198,44 @@ FRIQ_HD void friq_sincos_quick(double x, friq_dd *sn, friq_dd *cs) {
     *sn = (q == 0) ? sr : (q == 1) ? cr : (q == 2) ? nsr : ncr;
     *cs = (q == 0) ? cr : (q == 1) ? nsr : (q == 2) ? ncr : sr;
 }
+/* The quick phase for ONE of the two functions (want_cos = 0: sin x, 1: cos x).  With x = k pi/2 + r the answer is +-sin r or
+ * +-cos r depending on k mod 4, and both have the same shape
+ *     f = X + [Y.h th] + ((X.l + Y.l th) + (X.h dc + Y.h ds)),   (X, Y) = (sc, cc) for sin r,  (cc, -sc) for cos r:
+ * selecting the table operands first and evaluating once gives bit for bit what friq_sincos_quick returns for that function
+ * (negating an operand only flips signs of exact intermediate values) at about 60 % of its cost - the mountaincar dynamics need
+ * one cosine per env step (mountaincar.c:44). */
+FRIQ_HD friq_dd friq_sincos_quick_one(double x, int want_cos) {
+    double k = rint(x * FRIQ_TWO_OVER_PI);
+    double r0 = fma(-k, FRIQ_PIO2_1, x);
+    friq_dd a = friq_two_sum(r0, -k * FRIQ_PIO2_2);
+    friq_dd b = friq_two_sum(a.h, -k * FRIQ_PIO2_3);
+    friq_dd r = friq_fast_two_sum(b.h, (a.l + b.l) + (-k * FRIQ_PIO2_4));
+    double jf = rint(r.h * 32.0);
+    friq_dd t = friq_two_sum(r.h - jf * 0.03125, r.l);
+    int j = (int)jf, neg = j < 0;
+    if (neg) j = -j;
+    const double th = t.h, tl = t.l;
+    const double z = th * th, zl = fma(th, th, -z);
+    const double ps = FRIQ_S3_HI + z * (FRIQ_S5_HI + z * (FRIQ_S7 + z * FRIQ_S9));
+    const double ds = tl + th * (z * ps);
+    const double pc = FRIQ_C4_HI + z * (FRIQ_C6 + z * FRIQ_C8);
+    const double dc = -0.5 * z + ((z * z) * pc - (th * tl + 0.5 * zl));
+    double sch = FRIQ_SC_TAB[j][0], scl = FRIQ_SC_TAB[j][1];
+    const double cch = FRIQ_SC_TAB[j][2], ccl = FRIQ_SC_TAB[j][3];
+    if (neg) { sch = -sch; scl = -scl; }
+    const int q = ((int)k) & 3;
+    /* sin x = (sr, cr, -sr, -cr)[q],  cos x = (cr, -sr, -cr, sr)[q]: the cosine of r is needed when (q + want_cos) is odd */
+    const int use_cos = (q + want_cos) & 1;
+    const double Xh = use_cos ? cch : sch, Xl = use_cos ? ccl : scl;
+    const double Yh = use_cos ? -sch : cch, Yl = use_cos ? -scl : ccl;
+    friq_dd p = friq_two_prod(Yh, th);
+    friq_dd hs = friq_two_sum(Xh, p.h);
+    const double lo = ((Xl + Yl * th) + (Xh * dc + Yh * ds)) + (p.l + hs.l);
+    friq_dd f = friq_fast_two_sum(hs.h, lo);
+    const int negate = want_cos ? (q == 1 || q == 2) : (q >= 2);
+    if (negate) { f.h = -f.h; f.l = -f.l; }
+    return f;
+}
 /* 1 when RN(v.h + v.l + e) is the same double for every |e| <= FRIQ_QUICK_ERR * |v.h| */
 FRIQ_HD int friq_quick_ok(friq_dd v) {
     const double e = fabs(v.h) * FRIQ_QUICK_ERR;
@@ -205,12 +243,12 @@ FRIQ_HD int friq_quick_ok(friq_dd v) {
 }
 
 FRIQ_HD double friq_sin(double x) {
-    friq_dd s, c; friq_sincos_quick(x, &s, &c);
+    friq_dd s = friq_sincos_quick_one(x, 0), c;
     if (friq_quick_ok(s)) return s.h;
     friq_sincos_dd(x, &s, &c); return s.h + s.l;
 }
 FRIQ_HD double friq_cos(double x) {
-    friq_dd s, c; friq_sincos_quick(x, &s, &c);
+    friq_dd c = friq_sincos_quick_one(x, 1), s;
     if (friq_quick_ok(c)) return c.h;
     friq_sincos_dd(x, &s, &c); return c.h + c.l;
 }

@@ -127,8 +127,10 @@ static struct FIVERB *fiverb_alloc(double *u, double *ve, int p, int K, int U, i
     return frb;
 }
 
+static int g_device_override = -1;       /* frirl_mpi_run places its agents on the node's GPUs round-robin */
 static int device_index(void)
 {
+    if (g_device_override >= 0) return g_device_override;
     const char *d = getenv("FRIQ_DEVICE");
     return d ? atoi(d) : 0;
 }
@@ -818,7 +820,64 @@ void frirl_omp_run(struct frirl_desc *frirl)
     }
     free(agent);
 }
-void frirl_mpi_run(struct frirl_desc *frirl) { (void)frirl; printf("Built without MPI support!\n"); }        /* frirl_agent.c:387-391 */
+/* frirl_mpi_run (frirl_agent.c:387-467, the reference's BUILD_MPI mode: one MPI rank per agent).  There is no MPI here: the ranks
+ * are agents of THIS process, spread round-robin over the node's GPUs (rank r's one-agent device batch lives on GPU r mod #GPUs),
+ * and the rule bases that the reference ships with blocking MPI_Send / MPI_Recv (:427-461) are merged on the receiving agent's
+ * GPU (friq_batch_merge_rb).  World size: frirl->agent_world_size when the caller set it (> 1), else the launcher's
+ * OMPI_COMM_WORLD_SIZE / PMI_SIZE, else 3 or the number of GPUs, whichever is larger.  Rank 0 is the caller's own frirl_desc, so
+ * the merged rule base ends where an MPI rank 0 would hold it.  Exchange order as in the reference: after every chunk of
+ * episodes every member's rule base is merged into the leader in rank order (no "pended" test in this mode), then the leader's
+ * into every member; the run ends when the leader's rule base is complete (MPI_Bcast of is_running, :421-425). */
+void frirl_mpi_run(struct frirl_desc *frirl)
+{
+    int world = frirl->agent_world_size;
+    if (world < 2) { const char *e = getenv("OMPI_COMM_WORLD_SIZE"); if (!e) e = getenv("PMI_SIZE"); world = e ? atoi(e) : 0; }
+    int ndev = 1; friq_device_count(&ndev); if (ndev < 1) ndev = 1;
+    if (world < 2) world = ndev > 3 ? ndev : 3;
+    if (world == 2) { printf("frirl_mpi_run: FATAL ERROR: 2 agents divide by zero in gen_def_states (frirl_agent.c:132): use >= 3\n"); exit(1); }
+    const int S = frirl->statedims_len, K = frirl->numofantecedents;
+    struct frirl_desc **agent = (struct frirl_desc **)calloc(world, sizeof *agent);
+    frirl->agent_id = 0; frirl->agent_world_size = world;
+    agent[0] = frirl;
+    for (int i = 0; i < S; i++) printf("#%d sdim%d def:%f\n", 0, i, frirl->statedims[i].values_def);
+    ENGINE(friq_batch_keep_weights(ENG(frirl->fiverb)->B));
+    for (int id = 1; id < world; id++) {
+        struct frirl_desc *a = (struct frirl_desc *)malloc(sizeof *a);
+        memcpy(a, frirl, sizeof *a);
+        a->agent_id = id; a->agent_world_size = world; a->rbfile = NULL;
+        a->statedims = (struct frirl_dimension_desc *)malloc(sizeof(struct frirl_dimension_desc) * S);
+        memcpy(a->statedims, frirl->statedims, sizeof(struct frirl_dimension_desc) * S);
+        {                                                                                             /* gen_def_states, :118-138 */
+            const struct FIVERB *mf = frirl->fiverb;
+            const int gap = mf->numofrules / (world - 2);
+            for (int i = 0; i < S; i++) {
+                const size_t at = (size_t)(id - 1) * gap * K + i;
+                a->statedims[i].values_def = at < (size_t)mf->maxnumofrules * K ? mf->rant[at] : 0.0;
+            }
+        }
+        for (int i = 0; i < S; i++) printf("#%d sdim%d def:%f\n", id, i, a->statedims[i].values_def);
+        g_device_override = id % ndev;
+        if (frirl_init(a) != 0) { printf("frirl_mpi_run: FATAL ERROR: agent %d could not be initialised\n", id); exit(1); }
+        g_device_override = -1;
+        a->agent_id = id; a->agent_world_size = world; a->is_running = 1; a->reduction_state = 0; a->runmode = frirl->runmode;
+        a->episode_num = frirl->episode_num;
+        ENGINE(friq_batch_keep_weights(ENG(a->fiverb)->B));
+        agent[id] = a;
+    }
+    frirl->is_running = 1;
+    for (;;) {
+        for (int id = 0; id < world; id++) frirl_sequential_run(agent[id]);
+        if (frirl->is_running == 0) { printf("End\n"); break; }                                      /* :421-425 */
+        for (int id = 1; id < world; id++) merge_rule_base(frirl, id, agent[id]->fiverb);             /* :427-433 */
+        for (int id = 1; id < world; id++) merge_rule_base(agent[id], 0, frirl->fiverb);              /* :445-461 */
+    }
+    for (int id = 1; id < world; id++) {
+        struct frirl_dimension_desc *sd = agent[id]->statedims;
+        frirl_deinit(agent[id]);
+        free(sd); free(agent[id]);
+    }
+    free(agent);
+}
 
 void frirl_test_run(struct frirl_desc *frirl)                                    /* frirl_test_run.c:20-86 */
 {

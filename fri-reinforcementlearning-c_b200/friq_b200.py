@@ -69,6 +69,7 @@ SYMBOLS = {
     "friq_batch_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "friq_batch_gather_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "friq_batch_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "friq_batch_run_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "friq_batch_vag_concl": (C.c_int, [C.c_void_p, dp, dp, ip]),
     "friq_batch_vag_concl_weight": (C.c_int, [C.c_void_p, dp, ip, dp]),
     "friq_batch_get_best_action": (C.c_int, [C.c_void_p, dp, dp, ip]),
@@ -287,6 +288,10 @@ class Batch:
         """End-to-end call with HOST pointers (e.g. pinned torch tensors): H2D, run, D2H, sync."""
         _ck(lib().friq_batch_run_host(self.h, alpha_ptr, gamma_ptr, eps_ptr, int(n_steps), int(mode), ret_ptr, steps_ptr, rules_ptr, stream))
 
+    def run_host_async(self, n_steps, mode, alpha_ptr, gamma_ptr, eps_ptr, ret_ptr, steps_ptr, rules_ptr, stream=None):
+        """The same, enqueued only: the host buffers are valid once `stream` has passed this point (record an event after the call)."""
+        _ck(lib().friq_batch_run_host_async(self.h, alpha_ptr, gamma_ptr, eps_ptr, int(n_steps), int(mode), ret_ptr, steps_ptr, rules_ptr, stream))
+
     def merge_rb(self, rant, rconc, agent=-1):
         """merge_rb (frirl_agent.c:58-117): fold a sender's rule list into one agent's (agent < 0: every agent's) rule base"""
         rant, rconc = _f64(rant), _f64(rconc)
@@ -333,14 +338,14 @@ class Multi:
         for k, v in overrides.items():
             setattr(self.desc, k, v)
         self.h = C.c_void_p()
-        self.n = int(n_agents_total)
+        self.n, self.cap = int(n_agents_total), int(capacity)
         _ck(L.friq_multi_create(C.byref(self.desc), n_devices, self.n, capacity, seed0, C.byref(self.h)))
         self.G = L.friq_multi_devices(self.h)
 
     def batch(self, gpu, problem_like):
         """A non-owning Batch view of GPU `gpu`'s batch (problem_like supplies S / K / A for array shapes)."""
         b = Batch.__new__(Batch)
-        b.P, b.n, b.cap = problem_like, int(lib().friq_multi_agents(self.h, gpu)), None
+        b.P, b.n, b.cap = problem_like, int(lib().friq_multi_agents(self.h, gpu)), self.cap
         b.h = C.c_void_p(lib().friq_multi_batch(self.h, gpu))
         b.close = lambda: None
         return b

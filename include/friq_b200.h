@@ -116,8 +116,9 @@ int friq_batch_get_inserted(friq_batch *b, int *inserted);
 int friq_batch_run(friq_batch *b, long n_steps, int mode, void *stream);
 int friq_batch_sync(friq_batch *b, void *stream);
 /* evaluation policy of the fused kernel: 0 lock-step pass over all actions, 1 exact hits first + compacted Shepard chains,
- * 2 the same with memoised weights (table mode; the default where the problem qualifies).  Placement / evaluation strategy only:
- * results are bit-identical under every policy. */
+ * 2 the same with memoised weights (table mode; the default where the problem qualifies, else the next lower one).
+ * Evaluation strategy only: results are bit-identical under
+ * every policy.  With a shared rule base: 0 = one full pass per env step, else memoised conclusions. */
 int friq_batch_set_policy(friq_batch *b, int policy);
 /* agent groups of a re-tiled run (each sorted by rule count and launched on its own stream); 0 = default */
 int friq_batch_set_groups(friq_batch *b, int groups);
@@ -143,6 +144,9 @@ int friq_batch_gather_device(friq_batch *b, void *d_last_return_f64, void *d_las
 /* end-to-end convenience: hyper-parameters H2D, run, results D2H, all on `stream` and synchronised */
 int friq_batch_run_host(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon, long n_steps, int mode,
                         double *last_return, int *last_steps, int *rules, void *stream);
+/* the same, enqueued only (no synchronisation): the host buffers are valid once `stream` has passed this point */
+int friq_batch_run_host_async(friq_batch *b, const double *alpha, const double *gamma, const double *epsilon, long n_steps, int mode,
+                              double *last_return, int *last_steps, int *rules, void *stream);
 
 /* ---- per-call entry points: one call of the reference function per agent, host buffers in and out */
 /* FIVE_vag_concl (FIVE.h:102, FIVEVagConcl.c:64): ant [n][K] -> conc [n], hit [n] (rule index or -1) */

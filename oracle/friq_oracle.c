@@ -101,7 +101,10 @@ static const double CP_ACT[] = {-1.0, -0.9, -0.8, -0.7, -0.6, -0.5, -0.399999999
     -0.19999999999999995, -0.09999999999999998, 0.0, +0.09999999999999998, +0.19999999999999995,
     +0.29999999999999992, +0.3999999999999999, +0.5, +0.6, +0.7, +0.8, +0.9, +1.0};
 
-fo_problem *fo_problem_builtin(int env, int trig) {
+fo_problem *fo_problem_builtin(int env, int trig) { return fo_problem_builtin_actions(env, trig, 0, NULL, 0.0); }
+/* the example's problem with ANOTHER action dimension (A values: act_vals, or generated with step act_div when NULL - like
+ * FRIRL_GEN_FIXRES_VALUES); A = 0 keeps the example's own.  Same table builders, so everything downstream is the general code. */
+fo_problem *fo_problem_builtin_actions(int env, int trig, int A, const double *act_vals, double act_div) {
     fo_problem *P = calloc(1, sizeof *P);
     struct dim_spec sd[4], ad;
     P->env = env; P->trig = trig;
@@ -130,6 +133,7 @@ fo_problem *fo_problem_builtin(int env, int trig) {
         sd[3] = (struct dim_spec){2, NULL, 2.0, 1.0, 0.0, 0.016};
         ad = (struct dim_spec){21, CP_ACT, 0.1, 0, 0, 0.008};
     }
+    if (A > 0) { ad.len = A; ad.vals = act_vals; ad.div = act_div; }
     int S = P->S, K = S + 1, U = P->U;
     P->K = K; P->A = ad.len; P->p = K;                          /* FIVEInit.c:89-93 with p = 0 */
     P->u = malloc(sizeof(double) * K * U); P->ve = malloc(sizeof(double) * K * U);
@@ -508,7 +512,12 @@ void fo_merge_rb(fo_agent *r, int Rs, const double *srant, const double *srconc)
  * chunks of FRIRL_AGENT_EPCHUNK - 1 = 9 episodes (frirl_sequential_run.c:51-65,159-161), then agent 0's rules into every
  * other agent and every other agent's rules into agent 0, until agent 0 finds its rule base complete.
  * log rows: (agent, steps, return, rules) per finished episode in per-agent order; returns the number of rows. */
-int fo_team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log) {
+static int team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log, int mpi_order);
+int fo_team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log) { return team_run(ag, W, max_rounds, log, max_log, 0); }
+/* the same with the exchange of frirl_mpi_run (frirl_agent.c:387-467): after every chunk each member's rule base is merged into the
+ * leader in rank order (:427-441, no "pended" test), then the leader's - already merged - rule base into every member (:445-461) */
+int fo_team_run_mpi(fo_agent **ag, int W, int max_rounds, double *log, int max_log) { return team_run(ag, W, max_rounds, log, max_log, 1); }
+static int team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log, int mpi_order) {
     const fo_problem *P = ag[0]->P; const int K = P->K;
     int n = 0;
     if (W > 2) {
@@ -534,6 +543,11 @@ int fo_team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log) 
             if (id == 0 && !a->converged && !(a->episode_num < (uint32_t)P->max_episodes)) running0 = 0;
         }
         if (!running0) break;
+        if (mpi_order) {
+            for (int id = 1; id < W; id++) fo_merge_rb(ag[0], ag[id]->R, ag[id]->rant, ag[id]->rconc);
+            for (int id = 1; id < W; id++) fo_merge_rb(ag[id], ag[0]->R, ag[0]->rant, ag[0]->rconc);
+            continue;
+        }
         if (!ag[0]->epended)
             for (int id = 1; id < W; id++) fo_merge_rb(ag[id], ag[0]->R, ag[0]->rant, ag[0]->rconc);
         for (int id = 1; id < W; id++)

@@ -67,6 +67,7 @@ typedef struct fo_agent {
 } fo_agent;
 
 fo_problem *fo_problem_builtin(int env, int trig);
+fo_problem *fo_problem_builtin_actions(int env, int trig, int A, const double *act_vals, double act_div);
 void fo_problem_free(fo_problem *P);
 
 fo_agent *fo_agent_new(const fo_problem *P, int capacity, uint64_t seed);
@@ -85,6 +86,7 @@ void fo_agent_set_initial_state(fo_agent *a, const double *s0);
 /* knowledge sharing: frirl_agent.c merge_rb / frirl_omp_run */
 void fo_merge_rb(fo_agent *rcvr, int Rs, const double *srant, const double *srconc);
 int  fo_team_run(fo_agent **ag, int W, int max_rounds, double *log, int max_log);
+int  fo_team_run_mpi(fo_agent **ag, int W, int max_rounds, double *log, int max_log);   /* the exchange order of frirl_mpi_run (frirl_agent.c:427-461) */
 
 /* environment */
 void fo_env_step(const fo_problem *P, double action, const double *s, double *snew);

@@ -13,6 +13,7 @@ def lib():
     if _lib is None:
         L = C.CDLL(os.path.join(REPO, "oracle", "libfriq_oracle.so"))
         L.fo_problem_builtin.restype = C.c_void_p; L.fo_problem_builtin.argtypes = [C.c_int, C.c_int]
+        L.fo_problem_builtin_actions.restype = C.c_void_p; L.fo_problem_builtin_actions.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_double]
         L.fo_problem_free.argtypes = [C.c_void_p]
         for f in ["fo_problem_u", "fo_problem_ve", "fo_problem_udiv", "fo_problem_act_val", "fo_problem_act_ve"]:
             getattr(L, f).restype = dp; getattr(L, f).argtypes = [C.c_void_p]
@@ -49,6 +50,7 @@ def lib():
         L.fo_env_quantize.argtypes = [C.c_void_p, dp, dp]
         L.fo_merge_rb.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.fo_team_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_int]
+        L.fo_team_run_mpi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -58,8 +60,15 @@ def _p(a):
 
 
 class Problem:
-    def __init__(self, env, trig=1):
-        self.h = lib().fo_problem_builtin(env, trig)
+    def __init__(self, env, trig=1, actions=None, act_div=0.0):
+        """actions: None = the example's own action set; an int A = A generated values with step act_div; an array = those values"""
+        if actions is None:
+            self.h = lib().fo_problem_builtin(env, trig)
+        elif isinstance(actions, int):
+            self.h = lib().fo_problem_builtin_actions(env, trig, actions, None, act_div)
+        else:
+            self._av = np.ascontiguousarray(actions, dtype=np.float64)
+            self.h = lib().fo_problem_builtin_actions(env, trig, len(self._av), _p(self._av), act_div)
         info = (C.c_int * 8)(); lib().fo_problem_info(self.h, info)
         self.env, self.S, self.K, self.A, self.U, self.p, self.max_steps, self.max_episodes = list(info)
         hy = np.zeros(32); lib().fo_problem_hyper(self.h, _p(hy)); self.hyper = hy
@@ -153,9 +162,10 @@ class Agent:
                     s=o[16:16 + K - 1].copy(), qant=o[24:24 + K].copy())
 
 
-def team_run(agents, max_rounds=200, max_log=20000):
-    """frirl_omp_run (frirl_agent.c:294-385) over the given agents; rows (agent, steps, return, rules) per finished episode"""
+def team_run(agents, max_rounds=200, max_log=20000, mpi_order=False):
+    """frirl_omp_run (frirl_agent.c:294-385) over the given agents - or, mpi_order, the exchange order of frirl_mpi_run (:387-467);
+    rows (agent, steps, return, rules) per finished episode"""
     hs = (C.c_void_p * len(agents))(*[a.h for a in agents])
     log = np.zeros(4 * max_log)
-    n = lib().fo_team_run(hs, len(agents), max_rounds, _p(log), max_log)
+    n = (lib().fo_team_run_mpi if mpi_order else lib().fo_team_run)(hs, len(agents), max_rounds, _p(log), max_log)
     return log[:4 * n].reshape(n, 4)

@@ -74,6 +74,33 @@ def test_reference_example_driver_in_omp_mode_reproduces_reference_openmp_build(
     assert open(tmp_path / "mountaincar.frirlrb.txt", "rb").read() == open(os.path.join(_golden.GOLDEN, f"mountaincar_omp{W}.frirlrb.txt"), "rb").read()
 
 
+@pytest.mark.parametrize("W", [3, 5])
+def test_reference_example_driver_in_mpi_mode_matches_oracle(W, tmp_path):
+    """`mountaincar -m mpi` (frirl_run -> frirl_mpi_run, frirl_agent.c:387-467).  The reference needs BUILD_MPI and an MPI
+    launcher, neither of which exists in this image, so there is no recorded reference run: PARITY UNPINNED for this mode - the
+    checker is the oracle port with the MPI exchange order (members -> leader in rank order, then leader -> members, no "pended"
+    test), whose merge_rb itself IS pinned by the reference's OpenMP runs.  World size from the launcher's OMPI_COMM_WORLD_SIZE; the
+    ranks are agents of one process, spread over the box's GPUs."""
+    import re
+    r = subprocess.run([_exe("dropin_mountaincar_crtrig"), "-m", "mpi"], cwd=tmp_path, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, DROPIN_CONSTRUCT="1", OMPI_COMM_WORLD_SIZE=str(W)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    eps = {}
+    for l in r.stdout.splitlines():
+        m = re.match(r"#(\d+) Episode: (\d+)\tSteps: (\d+)\tReward: (?:\x1b\[[0-9;]*m)?(-?[0-9.]+)(?:\x1b\[[0-9;]*m)?\tRules: (\d+)", l)
+        if m:
+            eps.setdefault(int(m.group(1)), []).append((int(m.group(3)), float(m.group(4)), int(m.group(5))))
+    P = _oracle.Problem(0, trig=1)
+    agents = [_oracle.Agent(P, 4096) for _ in range(W)]
+    log = _oracle.team_run(agents, mpi_order=True)
+    for a in range(W):
+        want = [tuple(x) for x in log[log[:, 0] == a][:, 1:].tolist()]
+        assert [tuple(map(float, e)) for e in eps.get(a, [])] == want, a
+    R, rant, rconc = agents[0].rb()
+    assert open(tmp_path / "mountaincar.frirlrb.txt", "rb").read() == _golden.rb_text(rant, rconc)
+    assert "End" in r.stdout
+
+
 def test_test_mode_runs_one_greedy_episode(tmp_path):
     """-m test (frirl_test_run.c:20-86): one greedy episode without rule-base updates, exit code 0 on success."""
     rb = os.path.join(_golden.GOLDEN, "acrobot.frirlrb.bin")

@@ -178,8 +178,8 @@ def test_random_exploration_matches_oracle_port(fq, name):
     b.close(); P.close()
 
 
-@pytest.mark.parametrize("name,policy", [("mountaincar", 0), ("mountaincar", 1), ("mountaincar", 2), ("acrobot", 0), ("acrobot", 1),
-                                         ("acrobot", 2), ("cartpole", 0)])
+@pytest.mark.parametrize("name,policy", [("mountaincar", 0), ("mountaincar", 1), ("mountaincar", 2), ("acrobot", 0),
+                                         ("acrobot", 1), ("acrobot", 2), ("cartpole", 0)])
 def test_every_evaluation_policy_matches_oracle(fq, name, policy):
     """The fused kernel has three evaluation policies (friq_batch_set_policy): 0 lock-step pass over all actions (+ hit sweep /
     compacted sums when few pairs lack an exact hit; cartpole's A = 21 pass runs in 7 chunks of 3 actions with the Q(s,a) chain
@@ -205,6 +205,43 @@ def test_every_evaluation_policy_matches_oracle(fq, name, policy):
         b.run(chunk, mode)
     o = b.gather()
     OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
+    for i in range(n):
+        a = _oracle.Agent(OP, CAP[name], seed=0x5EED0000 + first + i)
+        a.set_hyper(alpha[i], gamma[i], eps[i]); a.set_initial_state(s0[i])
+        a.run_steps(steps)
+        sm = a.summary()
+        R, rant, rconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(rant, orant) and np.array_equal(rconc, orconc), i
+        assert (o["episodes"][i], o["last_steps"][i], o["last_return"][i], o["total_steps"][i], o["sum_rules"][i]) == \
+            (sm["episode_num"] - 1, sm["last_steps"], sm["last_return"], sm["total_steps"], sm["sum_rules"])
+    b.close(); P.close()
+
+
+@pytest.mark.parametrize("name,A,act_div", [("mountaincar", 5, 0.5), ("acrobot", 7, 1.0 / 3.0), ("cartpole", 5, 0.5)])
+def test_fused_kernel_for_other_action_sets_matches_oracle(fq, name, A, act_div):
+    """Problems on a built-in environment that are NOT one of the three example shapes - here another action set (the number of
+    actions is a run-time value) - run through the plain fused loop k_run_steps_anyA (frirl_types.h:62-100: any frirl_desc):
+    random exploration, per-agent hyper-parameters, off-grid start states, chunked launches; every agent equals the oracle."""
+    d = fq.ProblemDesc()
+    fq.lib().friq_problem_desc_builtin(fq.ENV_ID[name], d)
+    d.actiondim.values_len = A; d.actiondim.values = None; d.actiondim.values_div = act_div
+    d.no_random = 0
+    P = fq.Problem(desc=d)
+    assert P.A == A
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1, actions=A, act_div=act_div); OP.set_no_random(0)
+    n, first = 40, 3
+    rng = np.random.default_rng(77)
+    alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.02, 0.2], n)
+    lo = {"mountaincar": [-1.2, -0.05], "acrobot": [-1.0, -1.0, -0.5, -0.5], "cartpole": [-1.0, -0.6, -0.12, -0.6]}[name]
+    hi = {"mountaincar": [0.3, 0.05], "acrobot": [1.0, 1.0, 0.5, 0.5], "cartpole": [1.0, 0.6, 0.12, 0.6]}[name]
+    s0 = rng.uniform(lo, hi, size=(n, P.S))
+    b = fq.Batch(P, n, CAP[name], seed0=0x5EED0000, first_agent=first)
+    b.set_hyper(alpha, gamma, eps); b.set_initial_state(s0)
+    steps = {"mountaincar": 700, "acrobot": 300, "cartpole": 300}[name]
+    for chunk, mode in ((2, fq.RUN_LEARN), (steps - 102, fq.RUN_LEARN | fq.RUN_RETILE), (100, fq.RUN_LEARN)):
+        b.run(chunk, mode)
+    o = b.gather()
     for i in range(n):
         a = _oracle.Agent(OP, CAP[name], seed=0x5EED0000 + first + i)
         a.set_hyper(alpha[i], gamma[i], eps[i]); a.set_initial_state(s0[i])
@@ -281,8 +318,8 @@ def test_table_mode_survives_dictionary_growth_and_odd_capacity(fq):
 @pytest.mark.parametrize("name", ["mountaincar", "acrobot"])
 def test_table_mode_equals_computed_chains(fq, name):
     """The looked-up weights ARE the computed ones: a larger batch than the oracle comparisons afford, run once in table
-    mode (policy 2, the default) and once with policy 1 (integer hit sweep + computed sqrt / x87 power / reciprocal chains);
-    every rule base, return and step count must be identical."""
+    mode (policy 2, the default) and with policy 1 (integer hit sweep + computed sqrt / x87 power / reciprocal chains); every
+    rule base, return and step count must be identical."""
     n, steps = 4096 + 17, 1200 if name == "mountaincar" else 500
     rng = np.random.default_rng(8)
     alpha = rng.uniform(0.2, 0.8, n); gamma = rng.uniform(0.9, 1.0, n); eps = rng.choice([0.0, 0.01, 0.05, 0.2], n)
@@ -298,11 +335,11 @@ def test_table_mode_equals_computed_chains(fq, name):
         rbs = [b.get_rulebase(i) for i in range(0, n, 97)]
         res.append((o, rbs))
         b.close(); P.close()
-    (o0, r0), (o1, r1) = res
-    for k in ("last_return", "last_steps", "rules", "episodes", "flags", "total_steps", "sum_rules"):
-        assert np.array_equal(o0[k], o1[k]), k
-    for (Ra, ra, qa), (Rb, rb, qb) in zip(r0, r1):
-        assert Ra == Rb and np.array_equal(ra, rb) and np.array_equal(qa, qb)
+    for (o0, r0), (o1, r1) in zip(res[:-1], res[1:]):
+        for k in ("last_return", "last_steps", "rules", "episodes", "flags", "total_steps", "sum_rules"):
+            assert np.array_equal(o0[k], o1[k]), k
+        for (Ra, ra, qa), (Rb, rb, qb) in zip(r0, r1):
+            assert Ra == Rb and np.array_equal(ra, rb) and np.array_equal(qa, qb)
 
 
 @pytest.mark.parametrize("name,W", [("mountaincar", 3), ("mountaincar", 4), ("acrobot", 3), ("cartpole", 3)])

@@ -18,6 +18,7 @@ def test_trig_is_correctly_rounded(tmp_path):
     L = C.CDLL(so)
     dp = C.POINTER(C.c_double)
     L.shim_check.restype = C.c_long; L.shim_check.argtypes = [dp, C.c_long, dp]
+    L.shim_check_one.restype = C.c_long; L.shim_check_one.argtypes = [dp, C.c_long, dp]
     L.shim_dd_err.restype = C.c_double; L.shim_dd_err.argtypes = [dp, C.c_long]
     L.shim_quick_err.restype = C.c_double; L.shim_quick_err.argtypes = [dp, C.c_long, dp]
     rng = np.random.default_rng(2024)
@@ -28,6 +29,7 @@ def test_trig_is_correctly_rounded(tmp_path):
         x = np.ascontiguousarray(x)
         w = C.c_double()
         assert L.shim_check(x.ctypes.data_as(dp), x.size, C.byref(w)) == 0, w.value
+        assert L.shim_check_one(x.ctypes.data_as(dp), x.size, C.byref(w)) == 0, w.value      # friq_sin / friq_cos on their own
         assert L.shim_dd_err(x.ctypes.data_as(dp), min(x.size, 40000)) < 1.0
         # quick phase (Ziv): its error must stay well inside the bound the rounding test assumes (FRIQ_QUICK_ERR = 2^-61),
         # and the test must send only a small share of the calls to the accurate phase

@@ -13,6 +13,18 @@ long shim_check(const double *x, long n, double *worst_x) {
     }
     return bad;
 }
+/* friq_sin / friq_cos (the single-function quick phase): correctly rounded, and the quick values are bit for bit the ones
+ * friq_sincos_quick returns for that function; returns the number of violations */
+long shim_check_one(const double *x, long n, double *worst_x) {
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        friq_dd s, c; friq_sincos_quick(x[i], &s, &c);
+        const friq_dd s1 = friq_sincos_quick_one(x[i], 0), c1 = friq_sincos_quick_one(x[i], 1);
+        const int same = s1.h == s.h && s1.l == s.l && c1.h == c.h && c1.l == c.l;
+        if (!same || friq_sin(x[i]) != (double)sinq((__float128)x[i]) || friq_cos(x[i]) != (double)cosq((__float128)x[i])) { bad++; *worst_x = x[i]; }
+    }
+    return bad;
+}
 /* max relative error of the double-double result vs binary128, in units of 2^-90 */
 double shim_dd_err(const double *x, long n) {
     double worst = 0;

@@ -11,7 +11,7 @@ for cfg in "$@"; do
   (
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off -std=c++17 \
       "$@" -Xptxas -v -c csrc/friq_engine.cu -o build/variants/e_$tag.o 2> build/variants/ptxas_$tag.log &&
-    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/friq_$tag.so build/variants/e_$tag.o build/friq_host.o build/frirl_dropin.o
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/friq_$tag.so build/variants/e_$tag.o build/friq_host.o build/friq_multi.o build/frirl_dropin.o -ldl
     rm -f build/variants/e_$tag.o
   ) &
 done

@@ -27,7 +27,7 @@ def main():
         b.run(250, mode)
     L.friqd_timeline_fetch(None, 0, 1)
     b.run(250, mode)
-    buf = np.zeros((1 << 18, 4), dtype=np.uint64)
+    buf = np.zeros((1 << 18, 6), dtype=np.uint64)
     m = L.friqd_timeline_fetch(buf.ctypes.data_as(C.c_void_p), 1 << 18, 1)
     buf = buf[:m]
     t0 = buf[:, 0].astype(np.int64); t1 = buf[:, 1].astype(np.int64)
@@ -46,7 +46,13 @@ def main():
     for lo, hi in ((0, 20), (20, 30), (30, 40), (40, 50), (50, 60), (60, 80), (80, 100), (100, 200)):
         sel = (rmax >= lo) & (rmax < hi)
         if sel.any():
-            print("  rmax [%3d,%3d): %5d warps, mean %.1f us, max %.1f us per launch" % (lo, hi, sel.sum(), d[sel].mean(), d[sel].max()))
+            kc = (buf[:, 4] >> np.uint64(32)).astype(np.float64)[sel]; pc = (buf[:, 4] & np.uint64(0xffffffff)).astype(np.float64)[sel]
+            rounds = (buf[:, 5] >> np.uint64(48)).astype(np.float64)[sel]; pairs = ((buf[:, 5] >> np.uint64(24)) & np.uint64(0xffffff)).astype(np.float64)[sel]
+            walk = (buf[:, 5] & np.uint64(0xffffff)).astype(np.float64)[sel]
+            print("  rmax [%3d,%3d): %5d warps, mean %.1f us, max %.1f us per launch | kernel %.0f kcyc, in pair sums %.0f kcyc (%.0f %%), rounds %.0f, pairs %.0f, "
+                  "walked rules (max per round) %.0f -> %.1f cyc per walked rule, rest %.0f cyc per step"
+                  % (lo, hi, sel.sum(), d[sel].mean(), d[sel].max(), kc.mean() / 1e3, pc.mean() / 1e3, 100 * pc.mean() / kc.mean(), rounds.mean(), pairs.mean(),
+                     walk.mean(), pc.mean() / max(walk.mean(), 1), (kc.mean() - pc.mean()) / 125))
 
 
 if __name__ == "__main__":
