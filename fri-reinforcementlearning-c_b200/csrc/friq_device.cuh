@@ -488,18 +488,12 @@ __device__ __forceinline__ void friq_cellvec_unpack(const friq_cellvec c, unsign
 { cc[0] = c.x & 0xffffu; cc[1] = c.x >> 16; cc[2] = c.y & 0xffffu; cc[3] = c.y >> 16; }
 #endif
 
-// the pair's row of the memoised weights: in global memory (read-only path), or wherever a generic pointer says - shared
-// memory when the row was staged by TMA
+// the pair's row of the memoised weights (global memory, read-only path)
 struct friq_row_f64 {
     const double *__restrict__ row;
     __device__ __forceinline__ double operator()(unsigned c) const { return __ldg(row + c); }
 };
-struct friq_row_any {
-    const double *row;
-    __device__ __forceinline__ double operator()(unsigned c) const { return row[c]; }
-};
-// per-warp staging area for table rows: `slots` rows of FRIQ_ROW_MAXLEN doubles in shared memory, one mbarrier, its phase bit
-struct friq_rowstage { double *buf; uint64_t *bar; uint32_t phase; int slots; };
+
 // weights (looked up in the pair's table row through the block's cells) and consequents of one block of rules
 template <class ROW>
 __device__ __forceinline__ void friq_tab_load(const ROW &row, const friq_cellvec c, const double *pq,
@@ -508,18 +502,7 @@ __device__ __forceinline__ void friq_tab_load(const ROW &row, const friq_cellvec
     unsigned cc[FRIQ_CELL_VEC];
     friq_cellvec_unpack(c, cc);
 #pragma unroll
-    for (int u = 0; u < FRIQ_CELL_VEC; u++) {
-#ifdef FRIQ_EXP_NOTAB
-        t[u] = 1.0 + (double)cc[u];
-#else
-        t[u] = row(cc[u]);
-#endif
-#ifdef FRIQ_EXP_NOQ
-        q[u] = 1.0;
-#else
-        q[u] = pq[(size_t)u * FRIQ_TILE];
-#endif
-    }
+    for (int u = 0; u < FRIQ_CELL_VEC; u++) { t[u] = row(cc[u]); q[u] = pq[(size_t)u * FRIQ_TILE]; }
 }
 // the block's terms added in rule order (BestAct.c:216-217 / FIVEVagConcl.c:234-235); cnt < block size only for a column's last block
 template <bool FULL>
@@ -593,8 +576,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
                                                      const double *vo_obs, const double *vo_q, uint32_t ow, uint32_t qw,
                                                      unsigned wmask, const unsigned (&nm)[A], unsigned qm,
                                                      unsigned char *plist /* 32 bytes of shared memory per warp */,
-                                                     double (&conc)[A], double &vagq, double &wsq, unsigned &n_tab, unsigned &n_chain, bool keep_sw,
-                                                     friq_rowstage &rs)
+                                                     double (&conc)[A], double &vagq, double &wsq, unsigned &n_tab, unsigned &n_chain, bool keep_sw)
 {
     constexpr int K = S + 1, C = A + 1;
     const int lane = threadIdx.x & 31;
@@ -645,31 +627,10 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             const int ah = pb.act_hit[c < A ? c : 0];
             const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET);
             const bool tab = has && pw != FRIQ_NO_TARGET;
-            const double *rowd = pb.wtab + (size_t)(tab ? friq_cell<K>(pb, pw) : 0) * (size_t)pb.wstride;
-            // the first rs.slots pairs of the round get their whole table row into shared memory: one cp.async.bulk (TMA) per row,
-            // completion on the warp's mbarrier; the lookups of the walk are then shared-memory reads instead of L2 round trips
-            const bool stage = tab && rank < rs.slots;
-            const unsigned stm = rs.slots ? __ballot_sync(wmask, stage) : 0u;
-            if (stm) {                                   // warp-uniform
-                const uint32_t bytes = (uint32_t)pb.wstride * 8u, bar = (uint32_t)__cvta_generic_to_shared(rs.bar);
-                if (rank == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)__popc(stm)) : "memory");
-                __syncwarp(wmask);
-                if (stage) {
-                    double *dst = rs.buf + (size_t)rank * FRIQ_ROW_MAXLEN;
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of this slot are done
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(rowd), "r"(bytes), "r"(bar) : "memory");
-                    rowd = dst;
-                }
-                uint32_t ok = 0;
-                while (!ok)
-                    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                                 : "=r"(ok) : "r"(bar), "r"(rs.phase) : "memory");
-                rs.phase ^= 1u;
-            }
             if (tab) {
+                const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wstride;
                 asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
-                friq_tab_sums(friq_row_any{rowd}, rbc, tq, tsw, j, Rj, isq && keep_sw, vag, ws);
+                friq_tab_sums(friq_row_f64{rowd}, rbc, tq, tsw, j, Rj, isq && keep_sw, vag, ws);
                 n_tab += (unsigned)Rj;
             }
             const bool slow = has && !tab;

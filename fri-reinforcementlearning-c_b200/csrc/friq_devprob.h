@@ -24,7 +24,6 @@
 #define FRIQ_IDX_BITS 6
 #define FRIQ_MAXA 32
 #define FRIQ_TILE 32         /* agents per rule-base tile (= one warp) */
-#define FRIQ_ROW_MAXLEN 256  /* longest row of the memoised-weight table (f64 entries) the fused kernel stages into shared memory */
 
 #define FRIQ_ENV_NONE (-1)
 #ifndef FRIQ_ENV_MOUNTAINCAR            /* same values as include/friq_b200.h */
@@ -65,8 +64,7 @@ typedef struct friq_devprob {
     const double *wtab;                       /* device pointer or NULL: memoised Shepard weights 1/d^p between any two dictionary cells,
                                                * [wcells][wstride], cell = sum_k index_k * wlin[k] (built by k_build_wtab with the very device
                                                * functions the kernels use, so a looked-up weight IS the computed one) */
-    int wcells, wlin[FRIQ_MAXK], wstride;     /* wstride = wcells rounded up to an even count: every row is 16-byte aligned and a
-                                               * multiple of 16 bytes, i.e. a legal source of ONE cp.async.bulk (TMA) into shared memory */
+    int wcells, wlin[FRIQ_MAXK], wstride;     /* wstride = wcells rounded up to an even count (rows 16-byte aligned) */
     double q_rdiv[FRIQ_MAXK];                 /* 1 / q_div: the quantiser's quick path (exact result, division only when a rounding boundary is near) */
     /* ---- everything above is staged to shared memory; the tail stays in global ---- */
     unsigned int corner[256];                 /* packed 2^K corner rules, frirl_init_rb.c:99-126 */

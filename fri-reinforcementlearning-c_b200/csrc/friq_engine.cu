@@ -49,9 +49,6 @@
 #ifndef FRIQ_WUPD_LOOKUP_MAX
 #define FRIQ_WUPD_LOOKUP_MAX 8 /* at most this many lanes of a warp with a weighted update pending: they look their weights up again instead of reading sw[] */
 #endif
-#ifndef FRIQ_ROW_SLOTS
-#define FRIQ_ROW_SLOTS 4     /* table rows staged into shared memory per warp and round (2 KB each) */
-#endif
 #ifndef FRIQ_QCOOP_MAX
 #define FRIQ_QCOOP_MAX 8     /* fewer lanes than this needing Q(s,a): friq_q_cooperative instead of the WITHQ pass */
 #endif
@@ -93,12 +90,6 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 {
     constexpr int K = S + 1;
     __shared__ unsigned char pair_list[FRIQ_BLOCK / 32][32];            // friq_pairs_compacted, per warp
-    // table mode, short rows (mountaincar: 231 cells = 1.8 KB): the table rows of the first ROWS pairs of a round are staged into
-    // shared memory by ONE cp.async.bulk (TMA) each, completion on the warp's mbarrier - the table (427 KB) does not fit L1, and
-    // looked up in global memory every block of 8 rules pays an L2 round trip (95 cycles per rule on an otherwise idle SM)
-    constexpr int ROWS = (COOP == 2 && ENV == FRIQ_ENV_MOUNTAINCAR) ? FRIQ_ROW_SLOTS : 0;
-    __shared__ __align__(16) double rowbuf[ROWS ? FRIQ_BLOCK / 32 : 1][ROWS ? ROWS : 1][ROWS ? FRIQ_ROW_MAXLEN : 2];
-    __shared__ uint64_t rowbar[FRIQ_BLOCK / 32];
 #ifdef FRIQ_TIMELINE
     const unsigned long long tl_t0 = friq_globaltimer();
 #endif
@@ -146,15 +137,6 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     // an episode spends one iteration on the initial action selection (frirl_episode.c:78) while its
     // neighbours step, and a lane that has finished idles until the slowest lane of the warp is done.
     const unsigned wmask = __activemask();
-    friq_rowstage rs; rs.buf = nullptr; rs.bar = &rowbar[threadIdx.x >> 5]; rs.phase = 0; rs.slots = 0;
-    if constexpr (ROWS > 0) {
-        if (pb.wstride <= FRIQ_ROW_MAXLEN) { rs.buf = &rowbuf[threadIdx.x >> 5][0][0]; rs.slots = ROWS; }
-        if ((int)(threadIdx.x & 31) == __ffs(wmask) - 1) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(rs.bar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp(wmask);
-    }
     long done_steps = 0;
     bool running = true;
     unsigned c_pairs = 0, c_tab = 0, c_chain = 0, c_hit = 0, c_app = 0, c_wupd = 0;    // executed-work counters (friq_devstate.ctr)
@@ -231,7 +213,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 const long long tl_c0 = clock64();
                 if (pairs | qm) { tl_rounds++; tl_pairs += pairs + __popc(qm); tl_walk += __reduce_max_sync(wmask, (act && (needq || hidx[0] < 0 || hidx[A - 1] < 0 || hidx[A / 2] < 0)) ? R : 0); }
 #endif
-                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq, c_tab, c_chain, kept_sw, rs);
+                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq, c_tab, c_chain, kept_sw);
 #ifdef FRIQ_TIMELINE
                 tl_cyc += clock64() - tl_c0;
 #endif
