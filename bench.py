@@ -472,7 +472,11 @@ def main():
             b.run(chunk, mode, stream=sptr, sync=False)
             gather_results()
 
-    ms, tot, clocks = timed(step_device, b.reset)
+    def reset_batch():                           # friq_batch_reset restores the problem's own hyper-parameters: put the workload's back
+        b.reset()
+        b.set_hyper(h_alpha_np, h_gamma_np, h_eps_np)
+
+    ms, tot, clocks = timed(step_device, reset_batch)
     nsteps, sumR = tot[0], tot[1]
     expect = world * n * chunk * args.steps
     assert nsteps == expect, "work skipped inside the timed region"
@@ -510,7 +514,7 @@ def main():
             b.run_host_async(chunk, mode, vp(h_alpha), vp(h_gamma), vp(h_eps), vp(h_out[i][0]), vp(h_out[i][1]), vp(h_out[i][2]), sptr)
             pend[i] = torch.cuda.Event(); pend[i].record(stream)
         h2d, d2h = 3 * 8 * n, 16 * n
-    ms_e2e, tot_e2e, _ = timed(step_e2e, b.reset, after_fn=lambda: (e2e_collect(0), e2e_collect(1)))
+    ms_e2e, tot_e2e, _ = timed(step_e2e, reset_batch, after_fn=lambda: (e2e_collect(0), e2e_collect(1)))
     nsteps_e2e = tot_e2e[0]
 
     fp64_peak_g = fq.device_fp64_peak()          # measured DADD/DMUL lane-instr/s of this GPU (G/s)

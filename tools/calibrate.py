@@ -1,0 +1,88 @@
+#!/usr/bin/env python3
+"""tools/calibrate.py -- constants behind bench.py's `roofline.executed.frac_executed` and `roofline.traffic`.
+
+  python tools/calibrate.py run <workload>      (under ncu, see tools/calibrate.sh) warm a batch up, then ONE un-re-tiled launch of
+                                                125 env steps whose device-side work counters are printed as JSON
+  python tools/calibrate.py fit                 ncu CSVs + counters of gpurun_out/cal_* -> profiles/calibration.json
+
+Model: executed FP64 thread instructions of a launch = fp64_per_step * env steps + 3 * rules summed with looked-up weights (one
+DMUL + two DADD each, friq_tab_acc) + fp64_per_chain_rule * rules summed with computed chains.  ncu measures the left side
+(smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on), the counters the work; cartpole (no table) gives the chain
+constant with the per-step body taken from mountaincar's, the table kernels give their per-step constants.  The file records the
+sha1 of the kernel sources: bench.py ignores it when the sources have changed since."""
+import ctypes, glob, hashlib, json, os, re, sys
+import numpy as np
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "fri-reinforcementlearning-c_b200")
+sys.path.insert(0, PKG)
+WL = {"c3": ("mountaincar", 32768, 192, 0.01, 40), "acrobot": ("acrobot", 32768, 704, 0.001, 16), "cartpole": ("cartpole", 32768, 512, 0.001, 16)}
+
+
+def source_sha1():
+    h = hashlib.sha1()
+    for f in ("friq_engine.cu", "friq_device.cuh", "friq_math.cuh", "friq_trig.h", "friq_devprob.h"):
+        h.update(open(os.path.join(PKG, "csrc", f), "rb").read())
+    return h.hexdigest()[:12]
+
+
+def run(name):
+    import friq_b200 as fq
+    env, n, cap, eps, warm_launches = WL[name]
+    P = fq.Problem(env, no_random=0)
+    b = fq.Batch(P, n, cap, seed0=0x5EED0000)
+    b.set_groups(1)
+    b.set_hyper(np.full(n, P.desc.alpha), np.full(n, P.desc.gamma), np.full(n, eps))
+    for _ in range(warm_launches // 2):
+        b.run(250, fq.RUN_LEARN | fq.RUN_RETILE)          # 2 fused launches each
+    b.run(0, fq.RUN_LEARN | fq.RUN_RETILE)                # sort once more: the measured launch sees re-tiled agents (0 steps: no fused launch)
+    b.work_counters(reset=True)
+    b.run(125, fq.RUN_LEARN)                              # THE captured launch (launch number warm_launches + 1 of k_run_steps)
+    c = b.work_counters()
+    print("CALIB " + json.dumps(dict(workload=name, agents=n, **c)))
+
+
+def fit():
+    out = {}
+    res = {}
+    for name in WL:
+        log = os.path.join(REPO, "gpurun_out", f"cal_{name}.log"); csvf = os.path.join(REPO, "gpurun_out", f"cal_{name}.csv")
+        if not (os.path.exists(log) and os.path.exists(csvf)):
+            continue
+        m = re.search(r"CALIB (\{.*\})", open(log).read())
+        if not m:
+            continue
+        ctr = json.loads(m.group(1))
+        import csv
+        rows = [r for r in csv.reader(open(csvf)) if len(r) > 5]
+        hdr = rows[0]; vals = {}
+        for r in rows[1:]:
+            d = dict(zip(hdr, r))
+            try:
+                vals[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
+            except (KeyError, ValueError):
+                pass
+        fp64 = sum(v for k, v in vals.items() if re.search(r"op_d(add|mul|fma)_pred_on", k))
+        res[name] = dict(ctr=ctr, fp64=fp64, dram=vals.get("dram__bytes_read.sum", 0) + vals.get("dram__bytes_write.sum", 0),
+                         unit_note="dram bytes as ncu prints them", dur=vals.get("gpu__time_duration.sum"))
+    sha = source_sha1()
+    if "c3" in res:
+        r = res["c3"]; per_step = (r["fp64"] - 3.0 * r["ctr"]["table_rules"]) / r["ctr"]["steps"]
+    else:
+        per_step = 150.0
+    chain = None
+    if "cartpole" in res:
+        r = res["cartpole"]; chain = (r["fp64"] - per_step * r["ctr"]["steps"]) / max(r["ctr"]["chain_rules"], 1)
+    for name, r in res.items():
+        ps = per_step if name != "acrobot" else (r["fp64"] - 3.0 * r["ctr"]["table_rules"]) / r["ctr"]["steps"]
+        out[name] = dict(source_sha1=sha, fp64_per_step=ps, fp64_per_table_rule=3.0, fp64_per_chain_rule=chain if chain else 33.0,
+                         dram_bytes_per_launch=r["dram"], launch=dict(agents=r["ctr"]["agents"], env_steps=r["ctr"]["steps"], fp64_thread_instr=r["fp64"],
+                                                                   table_rules=r["ctr"]["table_rules"], chain_rules=r["ctr"]["chain_rules"]),
+                         source="ncu capture of one 125-step launch (tools/calibrate.sh): gpurun_out/cal_%s.csv -> profiles/r2_cal_%s.csv" % (name, name))
+    if "c3" in out:
+        out["c5"] = dict(out["c3"])
+    json.dump(out, open(os.path.join(REPO, "profiles", "calibration.json"), "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    run(sys.argv[2]) if sys.argv[1] == "run" else fit()
