@@ -524,28 +524,39 @@ template <class ROW>
 __device__ __forceinline__ void friq_tab_sums(const ROW &row, const unsigned short *rbc_tile, const double *tq, double *tsw,
                                               int j, int Rt, bool isq, double &vag, double &ws)
 {
+    // The steady-state loop body has NO branch: ptxas gives the loads of a loop body with control flow in it ONE scoreboard (every
+    // wait then drains the loads issued just before it and the double buffer overlaps nothing: measured 2 exposed load latencies
+    // per 16 rules); branch-free, the two halves get their own scoreboards.  So: the loop takes two FULL blocks per trip, block
+    // indexes beyond the column's last block are clamped (those loads are valid and never added), the tail is peeled.
     constexpr int B = FRIQ_CELL_VEC;
     const friq_cellvec *pc = reinterpret_cast<const friq_cellvec *>(rbc_tile) + j;        // block b of the column: pc[b * 32]
     const double *pq = tq + j; double *psw = tsw + j;
-    const int nb = (Rt + B - 1) / B;
+    if (Rt <= 0) return;
+    const int last = (Rt - 1) / B;                       // the column's last block
     double tA[B], qA[B], tB[B], qB[B];
-    friq_cellvec cn = friq_cellvec_zero();
-    if (nb > 0) friq_tab_load(row, pc[0], pq, tA, qA);
-    if (nb > 1) cn = pc[FRIQ_TILE];
+    friq_tab_load(row, pc[0], pq, tA, qA);
+    friq_cellvec cn = pc[(size_t)min(1, last) * FRIQ_TILE];
+    int b = 0;
+    // the cell vectors run one whole trip (two blocks) ahead of the loads they address: they are the first link of the
+    // dependent chain cells -> table entry, and a vector loaded half a trip ahead was still on the critical path
+    friq_cellvec cn2 = pc[(size_t)min(2, last) * FRIQ_TILE];
 #pragma unroll 1
-    for (int b = 0; b < nb; b += 2) {
-        friq_cellvec cnn = friq_cellvec_zero();
-        if (b + 1 < nb) friq_tab_load(row, cn, pq + B * FRIQ_TILE, tB, qB);
-        if (b + 2 < nb) cnn = pc[(size_t)(b + 2) * FRIQ_TILE];
-        { const int cnt = Rt - B * b; if (cnt >= B) friq_tab_acc<true>(tA, qA, B, isq, psw, vag, ws); else friq_tab_acc<false>(tA, qA, cnt, isq, psw, vag, ws); }
-        if (b + 1 < nb) {
-            if (b + 2 < nb) friq_tab_load(row, cnn, pq + 2 * B * FRIQ_TILE, tA, qA);
-            cn = friq_cellvec_zero();
-            if (b + 3 < nb) cn = pc[(size_t)(b + 3) * FRIQ_TILE];
-            const int cnt = Rt - B * (b + 1);
-            if (cnt >= B) friq_tab_acc<true>(tB, qB, B, isq, psw + B * FRIQ_TILE, vag, ws); else friq_tab_acc<false>(tB, qB, cnt, isq, psw + B * FRIQ_TILE, vag, ws);
-        }
-        pq += 2 * B * FRIQ_TILE; psw += 2 * B * FRIQ_TILE;
+    for (; Rt - B * b >= 2 * B; b += 2) {
+        friq_tab_load(row, cn, pq + (size_t)(b + 1) * (B * FRIQ_TILE), tB, qB);
+        const int b2 = min(b + 2, last), b3 = min(b + 3, last), b4 = min(b + 4, last);
+        const friq_cellvec c3 = pc[(size_t)b3 * FRIQ_TILE];
+        friq_tab_acc<true>(tA, qA, B, isq, psw + (size_t)b * (B * FRIQ_TILE), vag, ws);
+        friq_tab_load(row, cn2, pq + (size_t)b2 * (B * FRIQ_TILE), tA, qA);
+        const friq_cellvec c4 = pc[(size_t)b4 * FRIQ_TILE];
+        friq_tab_acc<true>(tB, qB, B, isq, psw + (size_t)(b + 1) * (B * FRIQ_TILE), vag, ws);
+        cn = c3; cn2 = c4;
+    }
+    const int rem = Rt - B * b;                          // 0 .. 15 rules left: block b is in tA / qA, the cells of block b + 1 in cn
+    if (rem > 0) {
+        if (rem > B) friq_tab_load(row, cn, pq + (size_t)(b + 1) * (B * FRIQ_TILE), tB, qB);
+        if (rem >= B) friq_tab_acc<true>(tA, qA, B, isq, psw + (size_t)b * (B * FRIQ_TILE), vag, ws);
+        else friq_tab_acc<false>(tA, qA, rem, isq, psw + (size_t)b * (B * FRIQ_TILE), vag, ws);
+        if (rem > B) friq_tab_acc<false>(tB, qB, rem - B, isq, psw + (size_t)(b + 1) * (B * FRIQ_TILE), vag, ws);
     }
 }
 // lane number of the n-th (0-based) set bit of mask: partial warps only (the last warp of a batch); __fns expands to ~220

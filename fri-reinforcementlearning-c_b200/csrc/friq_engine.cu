@@ -37,8 +37,11 @@
 #ifndef FRIQ_MINB_COOP
 #define FRIQ_MINB_COOP 2
 #endif
+#ifndef FRIQ_BLOCK_TAB
+#define FRIQ_BLOCK_TAB 256   /* table mode (COOP = 2): one 8-warp CTA per SM (measured +2 % over two 4-warp CTAs: one problem block per SM) */
+#endif
 #ifndef FRIQ_MINB_TAB
-#define FRIQ_MINB_TAB 2      /* table mode (COOP = 2); 3 and 4 CTAs per SM spill and measured 25-35 % slower */
+#define FRIQ_MINB_TAB 1      /* 8 warps per SM at 254 registers; 12 and 16 warps spill and measured 9-35 % slower (4-rule blocks: 8 % slower) */
 #endif
 #ifndef FRIQ_COMPACT_UNR
 #define FRIQ_COMPACT_UNR 6    /* rules per trip (= independent chains per lane) of friq_pairs_compacted */
@@ -85,11 +88,11 @@ struct __align__(16) friq_smem_t {
 // COOP = 2: the same in TABLE MODE - exact hits through the agent's cell-to-rule map, Shepard weights looked up in the problem's
 // memoised table (friq_devprob.wtab); the computed chain survives only as an out-of-line fall-back.
 template <int S, int P, int A, int ACH, int ENV, int UNR, bool SAFE, int COOP>
-__global__ void __launch_bounds__(FRIQ_BLOCK, COOP == 2 ? FRIQ_MINB_TAB : COOP ? FRIQ_MINB_COOP : FRIQ_MINB)
+__global__ void __launch_bounds__(COOP == 2 ? FRIQ_BLOCK_TAB : FRIQ_BLOCK, COOP == 2 ? FRIQ_MINB_TAB : COOP ? FRIQ_MINB_COOP : FRIQ_MINB)
 k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_steps, int mode)
 {
     constexpr int K = S + 1;
-    __shared__ unsigned char pair_list[FRIQ_BLOCK / 32][32];            // friq_pairs_compacted, per warp
+    __shared__ unsigned char pair_list[(COOP == 2 ? FRIQ_BLOCK_TAB : FRIQ_BLOCK) / 32][32];   // friq_pairs_compacted, per warp
 #ifdef FRIQ_TIMELINE
     const unsigned long long tl_t0 = friq_globaltimer();
 #endif
@@ -1526,8 +1529,9 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
         if (hp->safe_range) k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, true, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode); \
         else k_run_steps<S_, P_, A_, ACH_, ENV_, UNR_, false, 0><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);     \
     } while (0)
-    if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR) k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
-    else if (tab && hp->env == FRIQ_ENV_ACROBOT) k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
+    const dim3 gt((unsigned)((st.n + FRIQ_BLOCK_TAB - 1) / FRIQ_BLOCK_TAB));
+    if (tab && hp->env == FRIQ_ENV_MOUNTAINCAR) k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 2><<<gt, FRIQ_BLOCK_TAB, 0, s>>>(dprob, st, n_steps, mode);
+    else if (tab && hp->env == FRIQ_ENV_ACROBOT) k_run_steps<4, 5, 3, 3, FRIQ_ENV_ACROBOT, 1, true, 2><<<gt, FRIQ_BLOCK_TAB, 0, s>>>(dprob, st, n_steps, mode);
     else if (coop && hp->env == FRIQ_ENV_MOUNTAINCAR)
         k_run_steps<2, 3, 3, 3, FRIQ_ENV_MOUNTAINCAR, 1, true, 1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, n_steps, mode);
     else if (coop && hp->env == FRIQ_ENV_ACROBOT)

@@ -1,4 +1,8 @@
-python __graft_entry__.py smoke > gpurun_out/r2w_smoke.log 2>&1; tail -1 gpurun_out/r2w_smoke.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2w_ncu_launches.log 2>&1
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/r2w_sanitizer.log 2>&1; echo "sanitizer rc=$?" >> gpurun_out/r2w_sanitizer.log; tail -5 gpurun_out/r2w_sanitizer.log
-ncu --set full --import-source on --clock-control none -k regex:"k_infer_memo|k_shared_start|k_start_unique" --launch-skip 4 --launch-count 3 -f -o gpurun_out/r2w_c4 python bench.py --workload c4 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r2w_ncu_c4.log 2>&1; tail -2 gpurun_out/r2w_ncu_c4.log
+#!/bin/bash
+# scratch GPU job of the current experiment (edited per call)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+STEPS=20 BENCH_ARGS="--warmup 5" bash tools/run_variants.sh > gpurun_out/r2aa_variants_c3.log 2>&1
+cat gpurun_out/r2aa_variants_c3.log
+STEPS=6 BENCH_ARGS="--workload acrobot" bash tools/run_variants.sh > gpurun_out/r2aa_variants_acrobot.log 2>&1
+cat gpurun_out/r2aa_variants_acrobot.log
