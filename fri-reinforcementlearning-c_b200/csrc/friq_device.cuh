@@ -474,7 +474,12 @@ __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
 #define FRIQ_CELL_VEC 8         /* 8 (one 16-byte load per block) or 4 (8-byte loads, half the registers in flight) */
 #endif
 __host__ __device__ __forceinline__ size_t friq_cap8(int cap) { return (size_t)((cap + FRIQ_CELL_VEC - 1) & ~(FRIQ_CELL_VEC - 1)); }
+#define FRIQ_RBC_AHEAD 4        /* blocks of zero cells kept behind a column's last block (the walk requests cell vectors up to 4 blocks ahead, unclamped) */
+__host__ __device__ __forceinline__ size_t friq_rbc_slots(int cap) { return friq_cap8(cap) + (size_t)FRIQ_RBC_AHEAD * FRIQ_CELL_VEC; }   // rule slots per column of friq_devstate.rbc
 __device__ __forceinline__ size_t friq_rbc_index(int i, int lane) { return ((size_t)(i / FRIQ_CELL_VEC) * FRIQ_TILE + lane) * FRIQ_CELL_VEC + (i % FRIQ_CELL_VEC); }
+// The memoised table has one more column than cells, all +0.0 (friq_zero_cell): the cell of every slot between a column's last
+// rule and the end of its block, and of FRIQ_RBC_AHEAD whole blocks behind it, so that whole blocks can be summed without a tail.
+__device__ __forceinline__ unsigned friq_zero_cell(const friq_devprob &pb) { return (unsigned)pb.wcells; }
 #if FRIQ_CELL_VEC == 8
 typedef uint4 friq_cellvec;
 __device__ __forceinline__ friq_cellvec friq_cellvec_zero() { return make_uint4(0u, 0u, 0u, 0u); }
@@ -496,68 +501,66 @@ struct friq_row_f64 {
 
 // weights (looked up in the pair's table row through the block's cells) and consequents of one block of rules
 template <class ROW>
-__device__ __forceinline__ void friq_tab_load(const ROW &row, const friq_cellvec c, const double *pq,
-                                              double (&t)[FRIQ_CELL_VEC], double (&q)[FRIQ_CELL_VEC])
+__device__ __forceinline__ void friq_tab_load_t(const ROW &row, const friq_cellvec c, double (&t)[FRIQ_CELL_VEC])
 {
     unsigned cc[FRIQ_CELL_VEC];
     friq_cellvec_unpack(c, cc);
 #pragma unroll
-    for (int u = 0; u < FRIQ_CELL_VEC; u++) { t[u] = row(cc[u]); q[u] = pq[(size_t)u * FRIQ_TILE]; }
+    for (int u = 0; u < FRIQ_CELL_VEC; u++) t[u] = row(cc[u]);
 }
-// the block's terms added in rule order (BestAct.c:216-217 / FIVEVagConcl.c:234-235); cnt < block size only for a column's last block
-template <bool FULL>
-__device__ __forceinline__ void friq_tab_acc(const double (&t)[FRIQ_CELL_VEC], const double (&q)[FRIQ_CELL_VEC], int cnt, bool isq, double *psw,
-                                             double &vag, double &ws)
+__device__ __forceinline__ void friq_tab_load_q(const double *pq, double (&q)[FRIQ_CELL_VEC])
 {
-    if (isq) {
 #pragma unroll
-        for (int u = 0; u < FRIQ_CELL_VEC; u++) if (FULL || u < cnt) psw[(size_t)u * FRIQ_TILE] = t[u];
+    for (int u = 0; u < FRIQ_CELL_VEC; u++) q[u] = pq[(size_t)u * FRIQ_TILE];
+}
+// the block's terms added in rule order (BestAct.c:216-217 / FIVEVagConcl.c:234-235).  Every slot of the block is added: the
+// slots past the column's last rule carry the weight +0.0 (their cell is the table's ZERO column, friq_zero_cell) and a finite
+// consequent, and x + (+-0.0) == x bit for bit for every x a sum can hold (a sum that starts at +0.0 is never -0.0).
+// KEEP: the weights are also left in sw[], whole blocks, unconditionally (a round of Q(s,a) pairs; the rule capacity is a
+// multiple of the block size in table mode, so the zeros of a last block's tail stay inside the column)
+template <bool KEEP>
+__device__ __forceinline__ void friq_tab_acc(const double (&t)[FRIQ_CELL_VEC], const double (&q)[FRIQ_CELL_VEC], double *psw, double &vag, double &ws)
+{
+    if constexpr (KEEP) {
+#pragma unroll
+        for (int u = 0; u < FRIQ_CELL_VEC; u++) psw[(size_t)u * FRIQ_TILE] = t[u];
     }
 #pragma unroll
-    for (int u = 0; u < FRIQ_CELL_VEC; u++)
-        if (FULL || u < cnt) { vag = __dadd_rn(vag, __dmul_rn(t[u], q[u])); ws = __dadd_rn(ws, t[u]); }
+    for (int u = 0; u < FRIQ_CELL_VEC; u++) { vag = __dadd_rn(vag, __dmul_rn(t[u], q[u])); ws = __dadd_rn(ws, t[u]); }
 }
-// Shepard sums of one pair from the memoised weights: rules 0 .. Rt-1 of column j of the tile; block b+1's loads and block
-// b+2's cells are in flight while block b is added up.  isq: the weights are also left in sw[] (knowledge-sharing runs keep
-// FIVERB.weights from them; the weighted update looks its few candidates up again instead)
-template <class ROW>
-__device__ __forceinline__ void friq_tab_sums(const ROW &row, const unsigned short *rbc_tile, const double *tq, double *tsw,
-                                              int j, int Rt, bool isq, double &vag, double &ws)
+// Shepard sums of one pair from the memoised weights: rules 0 .. Rt-1 of column j of the tile (pc = the column's cell blocks,
+// pq = its consequents, psw = its weight scratch; c0 / qA = block 0's cells and consequents, already on their way).
+// The loop body has NO branch and no tail: ptxas gives the loads of a loop body with control flow in it ONE scoreboard (every
+// wait then drains the loads issued just before it and a double buffer overlaps nothing: measured, two exposed load latencies
+// per 16 rules); branch-free, the two halves of the trip get their own scoreboards.  A trip takes two blocks of 8 rules; the
+// blocks past the column's last one hold zero cells (FRIQ_RBC_AHEAD of them are kept there: k_refresh_index, the append in
+// k_run_steps), their consequents are the last block's again; the cell vectors run a whole trip ahead of the loads they
+// address (they are the first link of the chain cells -> table entry).
+template <bool KEEP, class ROW>
+__device__ __forceinline__ void friq_tab_sums(const ROW &row, const friq_cellvec *pc, const double *pq, double *psw,
+                                              const friq_cellvec c0, double (&qA)[FRIQ_CELL_VEC], int Rt, double &vag, double &ws)
 {
-    // The steady-state loop body has NO branch: ptxas gives the loads of a loop body with control flow in it ONE scoreboard (every
-    // wait then drains the loads issued just before it and the double buffer overlaps nothing: measured 2 exposed load latencies
-    // per 16 rules); branch-free, the two halves get their own scoreboards.  So: the loop takes two FULL blocks per trip, block
-    // indexes beyond the column's last block are clamped (those loads are valid and never added), the tail is peeled.
     constexpr int B = FRIQ_CELL_VEC;
-    const friq_cellvec *pc = reinterpret_cast<const friq_cellvec *>(rbc_tile) + j;        // block b of the column: pc[b * 32]
-    const double *pq = tq + j; double *psw = tsw + j;
+    constexpr size_t BS = (size_t)B * FRIQ_TILE;
     if (Rt <= 0) return;
     const int last = (Rt - 1) / B;                       // the column's last block
-    double tA[B], qA[B], tB[B], qB[B];
-    friq_tab_load(row, pc[0], pq, tA, qA);
-    friq_cellvec cn = pc[(size_t)min(1, last) * FRIQ_TILE];
+    double tA[B], tB[B], qB[B];
+    friq_tab_load_t(row, c0, tA);
+    friq_cellvec c1 = pc[FRIQ_TILE], c2 = pc[2 * FRIQ_TILE];
     int b = 0;
-    // the cell vectors run one whole trip (two blocks) ahead of the loads they address: they are the first link of the
-    // dependent chain cells -> table entry, and a vector loaded half a trip ahead was still on the critical path
-    friq_cellvec cn2 = pc[(size_t)min(2, last) * FRIQ_TILE];
 #pragma unroll 1
-    for (; Rt - B * b >= 2 * B; b += 2) {
-        friq_tab_load(row, cn, pq + (size_t)(b + 1) * (B * FRIQ_TILE), tB, qB);
-        const int b2 = min(b + 2, last), b3 = min(b + 3, last), b4 = min(b + 4, last);
-        const friq_cellvec c3 = pc[(size_t)b3 * FRIQ_TILE];
-        friq_tab_acc<true>(tA, qA, B, isq, psw + (size_t)b * (B * FRIQ_TILE), vag, ws);
-        friq_tab_load(row, cn2, pq + (size_t)b2 * (B * FRIQ_TILE), tA, qA);
-        const friq_cellvec c4 = pc[(size_t)b4 * FRIQ_TILE];
-        friq_tab_acc<true>(tB, qB, B, isq, psw + (size_t)(b + 1) * (B * FRIQ_TILE), vag, ws);
-        cn = c3; cn2 = c4;
+    for (; b < last; b += 2) {
+        friq_tab_load_t(row, c1, tB);
+        friq_tab_load_q(pq + (size_t)min(b + 1, last) * BS, qB);
+        const friq_cellvec c3 = pc[3 * FRIQ_TILE];
+        friq_tab_acc<KEEP>(tA, qA, psw, vag, ws);
+        friq_tab_load_t(row, c2, tA);
+        friq_tab_load_q(pq + (size_t)min(b + 2, last) * BS, qA);
+        const friq_cellvec c4 = pc[4 * FRIQ_TILE];
+        friq_tab_acc<KEEP>(tB, qB, psw + BS, vag, ws);
+        c1 = c3; c2 = c4; pc += 2 * FRIQ_TILE; psw += 2 * BS;
     }
-    const int rem = Rt - B * b;                          // 0 .. 15 rules left: block b is in tA / qA, the cells of block b + 1 in cn
-    if (rem > 0) {
-        if (rem > B) friq_tab_load(row, cn, pq + (size_t)(b + 1) * (B * FRIQ_TILE), tB, qB);
-        if (rem >= B) friq_tab_acc<true>(tA, qA, B, isq, psw + (size_t)b * (B * FRIQ_TILE), vag, ws);
-        else friq_tab_acc<false>(tA, qA, rem, isq, psw + (size_t)b * (B * FRIQ_TILE), vag, ws);
-        if (rem > B) friq_tab_acc<false>(tB, qB, rem - B, isq, psw + (size_t)(b + 1) * (B * FRIQ_TILE), vag, ws);
-    }
+    if (b == last) friq_tab_acc<KEEP>(tA, qA, psw, vag, ws);      // an odd number of blocks: the last one is already in tA / qA
 }
 // lane number of the n-th (0-based) set bit of mask: partial warps only (the last warp of a batch); __fns expands to ~220
 // instructions per use, so it lives out of line
@@ -599,12 +602,17 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
 #pragma unroll
     for (int a = 0; a < A; a++) chm[a] = nm[a];
     chm[A] = qm;
+    const int per_round = __popc(wmask), rank = __popc(wmask & lt);   // the last warp of a batch may be partial
     ofs[0] = 0;
 #pragma unroll
-    for (int c = 0; c < C; c++) ofs[c + 1] = ofs[c] + __popc(chm[c]);
+    for (int c = 0; c < A; c++) ofs[c + 1] = ofs[c] + __popc(chm[c]);
+    // table mode with kept weights: the Q(s,a) pairs get rounds of their own, so that a round either stores every weight it
+    // looks up or none (the walk's loop body must stay branch-free, friq_tab_sums)
+    const int end_act = ofs[A];
+    if (TAB && keep_sw) ofs[A] = ((ofs[A] + per_round - 1) / per_round) * per_round;
+    ofs[C] = ofs[A] + __popc(chm[A]);
     const int np = ofs[C];
     vagq = 0.0; wsq = 0.0;
-    const int per_round = __popc(wmask), rank = __popc(wmask & lt);   // the last warp of a batch may be partial
     for (int p0 = 0; p0 < np; p0 += per_round) {
         // ---- which pair is mine?  the owners post (lane, channel) of their pairs of this round, lane number `rank` reads entry `rank`
         __syncwarp(wmask);
@@ -614,7 +622,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             if (((chm[t] >> lane) & 1u) && e >= 0 && e < per_round) plist[e] = (unsigned char)(lane | (t << 5));
         }
         __syncwarp(wmask);
-        const bool has = p0 + rank < np;
+        const bool has = p0 + rank < np && !(p0 + rank >= end_act && p0 + rank < ofs[A]);
         const int ent = has ? plist[rank] : 0;
         const int c = ent >> 5, j = ent & 31;
         // ---- the owner's point (table mode needs it only for the rare computed fall-back) and rule count
@@ -629,6 +637,10 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             pt[S] = (c == A) ? y : pb.act_ve[c < A ? c : 0];
         };
         if constexpr (!TAB) fetch_point();
+        // table mode: block 0 of the owner's column (cells, consequents) is requested before anything else about the pair is known
+        const friq_cellvec *pc = reinterpret_cast<const friq_cellvec *>(rbc) + j;
+        friq_cellvec c0 = friq_cellvec_zero(); double q0[FRIQ_CELL_VEC];
+        if constexpr (TAB) { c0 = pc[0]; friq_tab_load_q(tq + j, q0); }
         const int Rj = __shfl_sync(wmask, R, j);
         const bool isq = has && c == A;
         double vag = 0.0, ws = 0.0;
@@ -641,7 +653,8 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
             if (tab) {
                 const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wstride;
                 asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
-                friq_tab_sums(friq_row_f64{rowd}, rbc, tq, tsw, j, Rj, isq && keep_sw, vag, ws);
+                if (keep_sw && p0 >= ofs[A]) friq_tab_sums<true>(friq_row_f64{rowd}, pc, tq + j, tsw + j, c0, q0, Rj, vag, ws);   // a round of Q(s,a) pairs
+                else friq_tab_sums<false>(friq_row_f64{rowd}, pc, tq + j, tsw + j, c0, q0, Rj, vag, ws);
                 n_tab += (unsigned)Rj;
             }
             const bool slow = has && !tab;

@@ -123,7 +123,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     }
     // table mode: memoised weights (pb.wtab) + this agent's rule-cell list and cell-to-rule map
     constexpr bool tabmode = COOP == 2;                  // the host launches this variant only with a table and sized indexes
-    unsigned short *rbc = tabmode ? st.rbc + (size_t)(ag >> 5) * friq_cap8(st.cap) * FRIQ_TILE : nullptr;      // the TILE's rule cells
+    unsigned short *rbc = tabmode ? st.rbc + (size_t)(ag >> 5) * friq_rbc_slots(st.cap) * FRIQ_TILE : nullptr;      // the TILE's rule cells
     unsigned short *cmap = tabmode ? st.cmap + (size_t)(ag >> 5) * st.idx_cells * FRIQ_TILE + (ag & 31) : nullptr;
     uint32_t qw = FRIQ_NO_TARGET;                        // packed dictionary indices of the pending update's point vo[], if it has them
     if (tabmode) {
@@ -264,8 +264,19 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 if (R > R0 && tabmode) {                 // a rule was appended: keep the indexes current
                     const int cn = friq_cell<K>(pb, rbw[(size_t)R0 * FRIQ_TILE]);
                     unsigned short *e = rbc + friq_rbc_index(R0, (int)(ag & 31));
-                    if ((R0 % FRIQ_CELL_VEC) == 0) { friq_cellvec v = friq_cellvec_zero(); v.x = (unsigned)cn; *reinterpret_cast<friq_cellvec *>(e) = v; }   // a new block: cell 0 in its unused tail
-                    else *e = (unsigned short)cn;
+                    if ((R0 % FRIQ_CELL_VEC) == 0) {     // a new block: the zero column's cell and a finite consequent in its unused tail (friq_tab_acc),
+                        const unsigned z = friq_zero_cell(pb), zz = z | (z << 16);     // and one more block of zero cells FRIQ_RBC_AHEAD blocks on
+#if FRIQ_CELL_VEC == 8
+                        const friq_cellvec vz = make_uint4(zz, zz, zz, zz);
+#else
+                        const friq_cellvec vz = make_uint2(zz, zz);
+#endif
+                        friq_cellvec v = vz; v.x = (unsigned)cn | (z << 16);
+                        *reinterpret_cast<friq_cellvec *>(e) = v;
+                        *reinterpret_cast<friq_cellvec *>(e + (size_t)FRIQ_RBC_AHEAD * FRIQ_TILE * FRIQ_CELL_VEC) = vz;
+#pragma unroll
+                        for (int u = 1; u < FRIQ_CELL_VEC; u++) if (R0 + u < st.cap) rbq[(size_t)(R0 + u) * FRIQ_TILE] = 0.0;
+                    } else *e = (unsigned short)cn;
                     if (!cmap[(size_t)cn * FRIQ_TILE]) cmap[(size_t)cn * FRIQ_TILE] = (unsigned short)(R0 + 1);
                 }
                 if (R > R0 && hitq == -1) {              // a rule was appended: is it at the next step's (s,a)?
@@ -1118,8 +1129,17 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
     for (int k = 0; k < FRIQ_MAXK; k++) wl[k] = k < K ? gprob->wlin[k] : 0;
     const uint32_t *rbw = st.rbw + (size_t)(ag >> 5) * st.cap * FRIQ_TILE + lane;
     unsigned short *cmap = st.cmap + (size_t)(ag >> 5) * cells * FRIQ_TILE + lane;
-    unsigned short *rbc = st.rbc + (size_t)(ag >> 5) * friq_cap8(st.cap) * FRIQ_TILE;
+    unsigned short *rbc = st.rbc + (size_t)(ag >> 5) * friq_rbc_slots(st.cap) * FRIQ_TILE;
     const int R = st.R[ag], Rb = (int)friq_cap8(R);
+    {   // FRIQ_RBC_AHEAD blocks of zero cells behind the column's last block
+        const unsigned zz = (unsigned)cells | ((unsigned)cells << 16);
+#if FRIQ_CELL_VEC == 8
+        const friq_cellvec vz = make_uint4(zz, zz, zz, zz);
+#else
+        const friq_cellvec vz = make_uint2(zz, zz);
+#endif
+        for (int k = 0; k < FRIQ_RBC_AHEAD; k++) *reinterpret_cast<friq_cellvec *>(rbc + friq_rbc_index(Rb + k * FRIQ_CELL_VEC, lane)) = vz;
+    }
     for (int i0 = Rb - FRIQ_CELL_VEC; i0 >= 0; i0 -= FRIQ_CELL_VEC) {
         uint32_t w[FRIQ_CELL_VEC];
 #pragma unroll
@@ -1130,7 +1150,7 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
             int cc = 0;
 #pragma unroll
             for (int k = 0; k < FRIQ_MAXK; k++) cc += (int)((w[u] >> ((FRIQ_IDX_BITS * k) & 31)) & (FRIQ_MAXDICT - 1)) * wl[k];
-            c[u] = (i0 + u < R && cc < cells) ? (unsigned)cc : 0u;      // unused tail of the last block: cell 0; never out of bounds
+            c[u] = (i0 + u < R && cc < cells) ? (unsigned)cc : (unsigned)cells;   // unused tail of the last block: the table's zero column (friq_zero_cell)
         }
         friq_cellvec v;
 #if FRIQ_CELL_VEC == 8
@@ -1140,8 +1160,10 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
 #endif
         *reinterpret_cast<friq_cellvec *>(rbc + friq_rbc_index(i0, lane)) = v;
 #pragma unroll
-        for (int u = FRIQ_CELL_VEC - 1; u >= 0; u--)
+        for (int u = FRIQ_CELL_VEC - 1; u >= 0; u--) {
             if (i0 + u < R) cmap[(size_t)c[u] * FRIQ_TILE] = (unsigned short)(i0 + u + 1);
+            else if (i0 + u < st.cap) st.rbq[((size_t)(ag >> 5) * st.cap + (size_t)(i0 + u)) * FRIQ_TILE + lane] = 0.0;   // a finite consequent under the zero weight
+        }
     }
 }
 
@@ -1519,7 +1541,7 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     // table mode (memoised weights + per-agent indexes) only where the COOP kernels run and the indexes are sized for this table
     const bool coop = variant >= 1 && hp->hit_scan && hp->safe_range &&
                       ((hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) || (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)));
-    const bool tab = coop && variant == 2 && hp->wtab && st.rbc && st.idx_cells == hp->wcells;
+    const bool tab = coop && variant == 2 && hp->wtab && st.rbc && st.idx_cells == hp->wcells && (st.cap % FRIQ_CELL_VEC) == 0;
     if (tab) {
         CK(cudaMemsetAsync(st.cmap, 0, (size_t)((st.n + FRIQ_TILE - 1) / FRIQ_TILE) * st.idx_cells * FRIQ_TILE * sizeof(unsigned short), s));
         k_refresh_index<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st);
@@ -1705,7 +1727,7 @@ int friqd_bestact_dists(const friq_devprob *hp, friq_devstate st, const double *
     return 0;
 }
 
-unsigned long friqd_rbc_tile_slots(int cap) { return (unsigned long)(friq_cap8(cap) * FRIQ_TILE); }
+unsigned long friqd_rbc_tile_slots(int cap) { return (unsigned long)(friq_rbc_slots(cap) * FRIQ_TILE); }
 int friqd_build_wtab(const friq_devprob *hp, const friq_devprob *dprob, double *d_wtab)
 {
     const long n = (long)hp->wcells * hp->wcells;

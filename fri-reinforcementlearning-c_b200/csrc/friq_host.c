@@ -330,8 +330,10 @@ static int problem_publish(friq_problem *P)
         unsigned long cells = 1; int ok = 1;
         for (int k = 0; k < hp->K; k++) { hp->wlin[k] = (int)cells; cells *= (unsigned long)hp->dict_len[k]; if (cells > 65535ul) { ok = 0; break; } }
         for (int a = 0; a < hp->A; a++) if (hp->act_hit[a] < 0) ok = 0;
-        const unsigned long stride = (cells + 1ul) & ~1ul;
-        if (ok && cells * stride * 8ul <= FRIQ_WTAB_MAX_BYTES) {
+        /* one column more than cells, +0.0 in every row: the "cell" of the slots between a rule base's last rule and the end of
+         * its block of 8 and of the blocks behind it (friq_device.cuh: friq_zero_cell) */
+        const unsigned long stride = (cells + 2ul) & ~1ul;
+        if (ok && cells < 65535ul && cells * stride * 8ul <= FRIQ_WTAB_MAX_BYTES) {
             DEV(friqd_h2d(P->dp, hp, sizeof(friq_devprob)));          /* the build kernel reads the dictionaries */
             DEV(friqd_malloc((void **)&P->d_wtab, cells * stride * 8ul));
             DEV(friqd_memset(P->d_wtab, 0, cells * stride * 8ul));
