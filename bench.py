@@ -451,6 +451,9 @@ def main():
         clocks = clk.stop() if clk else None
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if world > 1:
+            per_rank = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(per_rank, ms)                      # every rank's own time (diagnostic: the reported time is their MAX)
+            timed.ms_ranks = [float(t.item()) / args.steps for t in per_rank]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         o1 = b.gather(); ctr = b.work_counters()
         dsteps = int((o1["total_steps"] - o0["total_steps"]).sum()); drules = int((o1["sum_rules"] - o0["sum_rules"]).sum())
@@ -477,6 +480,7 @@ def main():
         b.set_hyper(h_alpha_np, h_gamma_np, h_eps_np)
 
     ms, tot, clocks = timed(step_device, reset_batch)
+    ms_ranks = getattr(timed, "ms_ranks", None)
     nsteps, sumR = tot[0], tot[1]
     expect = world * n * chunk * args.steps
     assert nsteps == expect, "work skipped inside the timed region"
@@ -571,6 +575,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": gpu_launches,
         "clocks": clocks,
+        **({"ms_per_step_by_rank": [round(x, 4) for x in ms_ranks]} if ms_ranks else {}),
         "roofline": {"bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",
                      "achieved": ach_tflops if frac_fp64 >= frac_hbm else ach_gbs,
                      "peak": fp64_peak_g / 1e3 if frac_fp64 >= frac_hbm else hbm_peak,

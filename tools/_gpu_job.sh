@@ -2,6 +2,9 @@
 # scratch GPU job of the current experiment (edited per call)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-V=$PWD/fri-reinforcementlearning-c_b200/build/variants
-for t in base q t qt; do echo "== loaded $t"; FRIQ_LIB=$V/tlx_$t.so python tools/timeline.py r2aj_$t 22 | grep -E "warp records|\[ 50, 60\)|\[ 80,100\)|\[100,200\)"; done > gpurun_out/r2aj_timeline.log 2>&1
-cat gpurun_out/r2aj_timeline.log
+( timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ) > gpurun_out/r2al_pytest.log 2>&1
+tail -3 gpurun_out/r2al_pytest.log
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('c3', '%.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'e2e %.4g'%d['e2e']['value'])"
+python bench.py --workload acrobot --steps 6 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('acrobot', '%.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'e2e %.4g'%d['e2e']['value'])"
