@@ -67,7 +67,10 @@ class ResultExchange:
     """The path's ONE exchange per step: per-agent (return f64, steps i32, rules i32), gathered from every rank STRAIGHT into
     agent-ordered arrays (contiguous shards: rank-major == agent-major, so `all_gather_into_tensor` needs no un-interleave
     copy), on a SIDE stream so that the collective overlaps the next step's kernels instead of serialising behind them.
-    Two buffer sets alternate: the engine writes step i's results into set i % 2 while set (i - 1) % 2 is still in flight.
+    `depth` buffer sets rotate (default 4): the engine writes step i's results into set i % depth while the sets of the steps
+    before it are still in flight.  The collective is the only thing that couples the ranks - a rank cannot run further ahead
+    of the slowest one than the sets allow - and every rank's step time varies (each learns different rule bases): with two sets
+    every step costs the slowest rank's time (8 GPUs: 0.968 of linear), with four the variations average out over the steps.
 
         buf = x.next_buffers()                  # (ret, steps, rules) views the engine writes into (friq_batch_gather_device)
         ... engine call on `stream` ...
@@ -78,14 +81,15 @@ class ResultExchange:
     CUDA tensors: torch.distributed NCCL; CPU tensors (gloo, tests): the same calls run synchronously.  `stats_fn(ret, rules, n,
     out)` = optional device-side statistics kernel (friq_result_stats), else three torch reductions."""
 
-    def __init__(self, dist, n, device, stats_fn=None):
+    def __init__(self, dist, n, device, stats_fn=None, depth=4):
         self.dist, self.n, self.device = dist, n, torch.device(device)
         self.world = dist.get_world_size() if dist is not None else 1
         self.cuda = self.device.type == "cuda"
         self.stats_fn = stats_fn
         mk = lambda m, dt: torch.empty(m, dtype=dt, device=device)
         self.sets = []
-        for _ in range(2):
+        self.depth = max(2, int(depth))
+        for _ in range(self.depth):
             loc = (mk(n, torch.float64), mk(n, torch.int32), mk(n, torch.int32))
             glo = tuple(mk(self.world * n, t.dtype) for t in loc) if self.world > 1 else loc
             self.sets.append(dict(local=loc, all=glo, stats=torch.zeros(3, dtype=torch.float64, device=device), done=None, used=False))
@@ -96,7 +100,7 @@ class ResultExchange:
 
     def next_buffers(self, stream=None):
         """The buffer set of the coming step; `stream` (the engine's) first waits until the exchange that last used it is done."""
-        self.cur = (self.cur + 1) % 2
+        self.cur = (self.cur + 1) % self.depth
         st = self.sets[self.cur]
         if self.cuda and st["done"] is not None:
             (stream or torch.cuda.current_stream(self.device)).wait_event(st["done"])
