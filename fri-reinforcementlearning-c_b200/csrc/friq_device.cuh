@@ -69,7 +69,7 @@ __device__ __forceinline__ double friq_dist2(const friq_devprob &pb, uint32_t w,
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < N; k++) {
-        const double v = pb.dict_ve[k][(w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+        const double v = pb.dict_ve[k][FRIQ_FIELD(w, k, N)];
         const double d = __dsub_rn(vo[k], v);
         const double d2 = __dmul_rn(d, d);
         s = (k == 0) ? d2 : __dadd_rn(s, d2);
@@ -198,7 +198,7 @@ __device__ __forceinline__ void friq_pass_trip(const friq_devprob &pb, const uin
         double ssum = 0.0, sq = 0.0;
 #pragma unroll
         for (int k = 0; k < S; k++) {
-            const double v = pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+            const double v = pb.dict_ve[k][FRIQ_FIELD(w[u], k, S + 1)];
             const double d = __dsub_rn(vo_obs[k], v);
             const double d2 = __dmul_rn(d, d);
             ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                              // A3/A4
@@ -208,7 +208,7 @@ __device__ __forceinline__ void friq_pass_trip(const friq_devprob &pb, const uin
                 sq = (k == 0) ? e2 : __dadd_rn(sq, e2);
             }
         }
-        const double va = pb.dict_ve[S][(w[u] >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)];
+        const double va = pb.dict_ve[S][FRIQ_FIELD(w[u], S, S + 1)];
 #pragma unroll
         for (int a = 0; a < ACH; a++) {
             const double da = __dsub_rn(ave[a], va);
@@ -317,11 +317,11 @@ __device__ __forceinline__ void friq_action_pass(const friq_devprob &pb, const u
             double ssum = 0.0;
 #pragma unroll
             for (int k = 0; k < S; k++) {
-                const double d = __dsub_rn(vo_obs[k], pb.dict_ve[k][(w[u] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)]);
+                const double d = __dsub_rn(vo_obs[k], pb.dict_ve[k][FRIQ_FIELD(w[u], k, S + 1)]);
                 const double d2 = __dmul_rn(d, d);
                 ssum = (k == 0) ? d2 : __dadd_rn(ssum, d2);                                  // A3/A4
             }
-            const double da = __dsub_rn(ave, pb.dict_ve[S][(w[u] >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)]);
+            const double da = __dsub_rn(ave, pb.dict_ve[S][FRIQ_FIELD(w[u], S, S + 1)]);
             sv[u] = __dadd_rn(__dmul_rn(da, da), ssum);                                      // A5
             z[u] = friq_is_zero(sv[u]);
             wv[u] = friq_shepard_weight_fast<P, SAFE>(sv[u], bad, !z[u]);                    // NaN when s == 0: discarded
@@ -421,7 +421,7 @@ __device__ __forceinline__ uint32_t friq_obs_word(const friq_devprob &pb, const 
         if (j == -2) j = pb.def_hit[k];
         else if (j < 0) j = friq_dict_find(pb.dict_ve[k], pb.dict_len[k], vo[k]);
         ok = ok && j >= 0;
-        word |= (uint32_t)(j & (FRIQ_MAXDICT - 1)) << (FRIQ_IDX_BITS * k);
+        word |= (uint32_t)(j & (FRIQ_DICT_MAX(S + 1) - 1)) << (FRIQ_BITS_OF(S + 1) * k);
     }
     return ok ? word : FRIQ_NO_TARGET;
 }
@@ -461,9 +461,9 @@ __device__ __forceinline__ void friq_hit_scan(const uint32_t *rbw, int R, const 
 template <int K>
 __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
 {
-    int c = (int)(w & (FRIQ_MAXDICT - 1));
+    int c = (int)FRIQ_FIELD(w, 0, K);
 #pragma unroll
-    for (int k = 1; k < K; k++) c += (int)((w >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)) * pb.wlin[k];
+    for (int k = 1; k < K; k++) c += (int)FRIQ_FIELD(w, k, K) * pb.wlin[k];
     return c;
 }
 
@@ -648,7 +648,7 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
         if constexpr (TAB) {
             const uint32_t x = __shfl_sync(wmask, ow, j), y = __shfl_sync(wmask, qw, j);
             const int ah = pb.act_hit[c < A ? c : 0];
-            const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET);
+            const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_BITS_OF(S + 1) * S))) : FRIQ_NO_TARGET);
             const bool tab = has && pw != FRIQ_NO_TARGET;
             if (tab) {
                 const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wstride;
@@ -808,7 +808,7 @@ __device__ __forceinline__ void friq_sarsa_apply(const friq_devprob &pb, uint32_
         for (int k = 0; k < K; k++) {
             if (qi[k] >= 0) gi[k] = qi[k];
             else { gi[k] = friq_snap_index(pb, k, qs[k]); same = same && (pb.dict_val[k][gi[k]] == qs[k]); }   // :146-170
-            packed |= (uint32_t)gi[k] << (FRIQ_IDX_BITS * k);
+            packed |= (uint32_t)gi[k] << (FRIQ_BITS_OF(K) * k);
         }
         int hitg = hitq; double qg = qnow;
         if (!same) {                                   // snapped point differs: evaluate Q there (:370)
@@ -898,7 +898,7 @@ __device__ __noinline__ void friq_merge_rb(const friq_devprob &pb, uint32_t *rbw
         double vo[K], ant[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            const int j = (word >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1);
+            const int j = (int)FRIQ_FIELD(word, k, K);
             vo[k] = pb.dict_ve[k][j]; ant[k] = pb.dict_val[k][j];
         }
         const int hit = friq_first_hit<K>(pb, rbw, R, vo);                       // FIVE_vag_concl_weight, :75-76
@@ -917,7 +917,7 @@ __device__ __noinline__ void friq_merge_rb(const friq_devprob &pb, uint32_t *rbw
             for (int k = 0; k < K; k++) {                                        // CHECK_STATES, :96-99 + :19-45
                 gi[k] = friq_snap_index(pb, k, ant[k]);
                 same = same && (pb.dict_val[k][gi[k]] == ant[k]);
-                packed |= (uint32_t)gi[k] << (FRIQ_IDX_BITS * k);
+                packed |= (uint32_t)gi[k] << (FRIQ_BITS_OF(K) * k);
             }
             int hitg = hit; double rcg = rc;
             if (!same) {

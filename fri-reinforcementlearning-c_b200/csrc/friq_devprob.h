@@ -7,21 +7,25 @@
  * path touches.  It is ~9.7 KB and is staged into shared memory with one TMA bulk
  * copy (cp.async.bulk + mbarrier) per CTA.
  *
- * Rule storage.  A rule's antecedent in dimension k is stored as a 6-bit index
+ * Rule storage.  A rule's antecedent in dimension k is stored as a 4- to 6-bit index
  * into a per-dimension *value dictionary* dict_val[k][] (the grid values of
  * frirl_init.c:55-102 first - every rule the learner inserts is grid-snapped,
  * frirl_update_sarsa.c:367-375 - then any extra value met in a loaded rule base).
  * dict_ve[k][j] = VE_k[nearest_index(dict_val[k][j])] is exactly what
- * five_add_rule.c:71-84 caches in rseqant_veval.  K*6 <= 32 bits => one u32 per
- * rule; the consequent is one f64.
+ * five_add_rule.c:71-84 caches in rseqant_veval.  One u32 per rule (FRIQ_BITS_OF(K)
+ * bits per index); the consequent is one f64.
  */
 #ifndef FRIQ_DEVPROB_H
 #define FRIQ_DEVPROB_H
 #include <stddef.h>
 
 #define FRIQ_MAXK 8          /* FIVE_MAX_NUM_OF_UNIVERSES, FIVE.h:19 */
-#define FRIQ_MAXDICT 64
-#define FRIQ_IDX_BITS 6
+#define FRIQ_MAXDICT 64          /* room per dimension in the dictionaries (the most a 6-bit index addresses) */
+/* K antecedent indexes share one 32-bit rule word: 6 bits each up to K = 5 (64 values per dimension), 5 bits for K = 6 (32),
+ * 4 bits for K = 7 and 8 = FIVE_MAX_NUM_OF_UNIVERSES (16) */
+#define FRIQ_BITS_OF(K) ((K) <= 5 ? 6 : (K) == 6 ? 5 : 4)
+#define FRIQ_DICT_MAX(K) (1 << FRIQ_BITS_OF(K))
+#define FRIQ_FIELD(w, k, K) (((w) >> (FRIQ_BITS_OF(K) * (k))) & ((1u << FRIQ_BITS_OF(K)) - 1u))
 #define FRIQ_MAXA 32
 #define FRIQ_TILE 32         /* agents per rule-base tile (= one warp) */
 

@@ -133,7 +133,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         const uint32_t w0 = friq_obs_word<S>(pb, vo, unk);
         int ah = -1;
         for (int j = 0; j < pb.dict_len[S]; j++) if (pb.dict_ve[S][j] == vo[S]) { ah = j; break; }
-        if (w0 != FRIQ_NO_TARGET && ah >= 0) qw = w0 | ((uint32_t)ah << (FRIQ_IDX_BITS * S));
+        if (w0 != FRIQ_NO_TARGET && ah >= 0) qw = w0 | ((uint32_t)ah << (FRIQ_BITS_OF(K) * S));
     }
 
     // All lanes of a warp iterate in lockstep (explicit reconvergence at the loop top): a lane that starts
@@ -193,7 +193,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
             ow = friq_obs_word<S>(pb, vc, ci);
             uint32_t tgt[A]; unsigned nm[A]; int pairs = 0;
 #pragma unroll
-            for (int a = 0; a < A; a++) tgt[a] = (ow != FRIQ_NO_TARGET && pb.act_hit[a] >= 0) ? (ow | ((uint32_t)pb.act_hit[a] << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET;
+            for (int a = 0; a < A; a++) tgt[a] = (ow != FRIQ_NO_TARGET && pb.act_hit[a] >= 0) ? (ow | ((uint32_t)pb.act_hit[a] << (FRIQ_BITS_OF(K) * S))) : FRIQ_NO_TARGET;
             if (tabmode) {                               // exact hits in O(1): the first rule of the target's dictionary cell
                 const int oc = (ow != FRIQ_NO_TARGET) ? friq_cell<S>(pb, ow) : 0;
 #pragma unroll
@@ -235,7 +235,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
         const uint32_t qw_upd = qw;                      // the pending update's point (its weights are looked up again by the weighted update)
-        if (act) qw = (ow != FRIQ_NO_TARGET && pb.act_hit[a2] >= 0) ? (ow | ((uint32_t)pb.act_hit[a2] << (FRIQ_IDX_BITS * S))) : FRIQ_NO_TARGET;
+        if (act) qw = (ow != FRIQ_NO_TARGET && pb.act_hit[a2] >= 0) ? (ow | ((uint32_t)pb.act_hit[a2] << (FRIQ_BITS_OF(K) * S))) : FRIQ_NO_TARGET;
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }
         if (act && !initial) {
             sum_rules += (unsigned long long)R;
@@ -281,9 +281,9 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 }
                 if (R > R0 && hitq == -1) {              // a rule was appended: is it at the next step's (s,a)?
                     const uint32_t wnew = rbw[(size_t)R0 * FRIQ_TILE];
-                    bool same = pb.dict_ve[S][(wnew >> (FRIQ_IDX_BITS * S)) & (FRIQ_MAXDICT - 1)] == pb.act_ve_eval[a2];
+                    bool same = pb.dict_ve[S][FRIQ_FIELD(wnew, S, K)] == pb.act_ve_eval[a2];
 #pragma unroll
-                    for (int k = 0; k < S; k++) same = same && (pb.dict_ve[k][(wnew >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)] == vc[k]);
+                    for (int k = 0; k < S; k++) same = same && (pb.dict_ve[k][FRIQ_FIELD(wnew, k, K)] == vc[k]);
                     if (same) hitq = R0;
                 }
             } else hitq = next_hit;
@@ -1124,7 +1124,7 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
 {
     const long ag = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ag >= st.n) return;
-    const int K = gprob->K, cells = st.idx_cells, lane = (int)(ag & 31);
+    const int K = gprob->K, cells = st.idx_cells, lane = (int)(ag & 31), bits = FRIQ_BITS_OF(K);
     int wl[FRIQ_MAXK];
     for (int k = 0; k < FRIQ_MAXK; k++) wl[k] = k < K ? gprob->wlin[k] : 0;
     const uint32_t *rbw = st.rbw + (size_t)(ag >> 5) * st.cap * FRIQ_TILE + lane;
@@ -1149,7 +1149,7 @@ __global__ void k_refresh_index(const friq_devprob *__restrict__ gprob, friq_dev
         for (int u = 0; u < FRIQ_CELL_VEC; u++) {
             int cc = 0;
 #pragma unroll
-            for (int k = 0; k < FRIQ_MAXK; k++) cc += (int)((w[u] >> ((FRIQ_IDX_BITS * k) & 31)) & (FRIQ_MAXDICT - 1)) * wl[k];
+            for (int k = 0; k < FRIQ_MAXK; k++) cc += (int)((w[u] >> ((bits * k) & 31)) & ((1u << bits) - 1u)) * wl[k];
             c[u] = (i0 + u < R && cc < cells) ? (unsigned)cc : (unsigned)cells;   // unused tail of the last block: the table's zero column (friq_zero_cell)
         }
         friq_cellvec v;
@@ -1370,7 +1370,7 @@ __global__ void k_build_wtab(const friq_devprob *__restrict__ gprob, double *__r
     for (int k = 0; k < K; k++) {
         const int n = gprob->dict_len[k];
         pt[k] = gprob->dict_ve[k][q % n]; q /= n;
-        w |= (uint32_t)(r % n) << (FRIQ_IDX_BITS * k); r /= n;
+        w |= (uint32_t)(r % n) << (FRIQ_BITS_OF(K) * k); r /= n;
     }
     wtab[(size_t)q0 * stride + r0] = friq_shepard_weight<P>(friq_dist2<K>(*gprob, w, pt));
 }
@@ -1522,7 +1522,7 @@ int friqd_device_sync(void) { CK(cudaDeviceSynchronize()); return 0; }
 int friqd_sync(void *stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
 const char *friqd_error_string(int err)
 {
-    if (err == FRIQ_ERR_SHAPE) return "unsupported problem shape: per-call entry points need 1 <= S <= 4 state dimensions, p = S + 1 and A <= 32 actions; the fused kernels a built-in environment with its own number of state dimensions (any action set of <= 32 actions)";
+    if (err == FRIQ_ERR_SHAPE) return "unsupported problem shape: per-call entry points need 1 <= S <= 7 state dimensions, p = S + 1 and A <= 32 actions; the fused kernels a built-in environment with its own number of state dimensions (any action set of <= 32 actions)";
     return cudaGetErrorString((cudaError_t)err);
 }
 
@@ -1657,6 +1657,9 @@ int friqd_vag_concl(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     else if (hp->S == 4 && hp->p == 5) k_vag_concl<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
     else if (hp->S == 1 && hp->p == 2) k_vag_concl<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
     else if (hp->S == 3 && hp->p == 4) k_vag_concl<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
+    else if (hp->S == 5 && hp->p == 6) k_vag_concl<5, 6><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
+    else if (hp->S == 6 && hp->p == 7) k_vag_concl<6, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
+    else if (hp->S == 7 && hp->p == 8) k_vag_concl<7, 8><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_conc, d_hit, d_weights);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1673,6 +1676,9 @@ int friqd_best_action(const friq_devprob *hp, const friq_devprob *dprob, friq_de
     else if (hp->S == 1 && hp->p == 2) k_best_action_anyA<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else if (hp->S == 2 && hp->p == 3) k_best_action_anyA<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else if (hp->S == 3 && hp->p == 4) k_best_action_anyA<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (hp->S == 5 && hp->p == 6) k_best_action_anyA<5, 6><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (hp->S == 6 && hp->p == 7) k_best_action_anyA<6, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
+    else if (hp->S == 7 && hp->p == 8) k_best_action_anyA<7, 8><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else if (hp->S == 4 && hp->p == 5) k_best_action_anyA<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_states, d_actconc, d_best);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
@@ -1687,6 +1693,9 @@ int friqd_update_sarsa(const friq_devprob *hp, const friq_devprob *dprob, friq_d
     else if (hp->S == 4 && hp->p == 5) k_update_sarsa<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
     else if (hp->S == 1 && hp->p == 2) k_update_sarsa<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
     else if (hp->S == 3 && hp->p == 4) k_update_sarsa<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
+    else if (hp->S == 5 && hp->p == 6) k_update_sarsa<5, 6><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
+    else if (hp->S == 6 && hp->p == 7) k_update_sarsa<6, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
+    else if (hp->S == 7 && hp->p == 8) k_update_sarsa<7, 8><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_qant, d_reward, d_curqant);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1702,6 +1711,9 @@ int friqd_classic_step(const friq_devprob *hp, const friq_devprob *dprob, friq_d
     else if (hp->S == 1 && hp->p == 2) k_classic_step_anyA<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
     else if (hp->S == 2 && hp->p == 3) k_classic_step_anyA<2, 3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
     else if (hp->S == 3 && hp->p == 4) k_classic_step_anyA<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (hp->S == 5 && hp->p == 6) k_classic_step_anyA<5, 6><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (hp->S == 6 && hp->p == 7) k_classic_step_anyA<6, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
+    else if (hp->S == 7 && hp->p == 8) k_classic_step_anyA<7, 8><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
     else if (hp->S == 4 && hp->p == 5) k_classic_step_anyA<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_in, d_out);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
@@ -1715,6 +1727,9 @@ int friqd_rule_distance(const friq_devprob *hp, const friq_devprob *dprob, friq_
     else if (hp->S == 4) k_rule_distance<4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
     else if (hp->S == 1) k_rule_distance<1><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
     else if (hp->S == 3) k_rule_distance<3><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
+    else if (hp->S == 5) k_rule_distance<5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
+    else if (hp->S == 6) k_rule_distance<6><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
+    else if (hp->S == 7) k_rule_distance<7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, d_ant, d_dists, d_hit);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1748,6 +1763,9 @@ int friqd_merge_rb(const friq_devprob *hp, const friq_devprob *dprob, friq_devst
     else if (hp->S == 4 && hp->p == 5) k_merge_list<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
     else if (hp->S == 1 && hp->p == 2) k_merge_list<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
     else if (hp->S == 3 && hp->p == 4) k_merge_list<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
+    else if (hp->S == 5 && hp->p == 6) k_merge_list<5, 6><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
+    else if (hp->S == 6 && hp->p == 7) k_merge_list<6, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
+    else if (hp->S == 7 && hp->p == 8) k_merge_list<7, 8><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, receiver, d_words, d_q, Rs);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;
@@ -1760,6 +1778,9 @@ int friqd_team_merge(const friq_devprob *hp, const friq_devprob *dprob, friq_dev
     else if (hp->S == 4 && hp->p == 5) k_team_merge<4, 5><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
     else if (hp->S == 1 && hp->p == 2) k_team_merge<1, 2><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
     else if (hp->S == 3 && hp->p == 4) k_team_merge<3, 4><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
+    else if (hp->S == 5 && hp->p == 6) k_team_merge<5, 6><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
+    else if (hp->S == 6 && hp->p == 7) k_team_merge<6, 7><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
+    else if (hp->S == 7 && hp->p == 8) k_team_merge<7, 8><<<g, FRIQ_BLOCK, 0, s>>>(dprob, st, team, phase);
     else return FRIQ_ERR_SHAPE;
     CK(cudaGetLastError());
     return 0;

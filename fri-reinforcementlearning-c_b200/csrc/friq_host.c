@@ -174,7 +174,7 @@ static int dict_find_or_add(friq_problem *P, int k, double v)
     friq_devprob *hp = &P->hp;
     for (int j = 0; j < hp->dict_len[k]; j++)
         if (memcmp(&hp->dict_val[k][j], &v, sizeof v) == 0) return j;
-    if (hp->dict_len[k] >= FRIQ_MAXDICT) return -1;
+    if (hp->dict_len[k] >= FRIQ_DICT_MAX(hp->K)) return -1;
     const int j = hp->dict_len[k]++;
     hp->dict_val[k][j] = v;
     hp->dict_ve[k][j] = P->ve[(size_t)k * hp->U + nearest_index(P->u + (size_t)k * hp->U, hp->U, hp->U, hp->udiv[k], v)];   /* five_add_rule.c:71-84 */
@@ -184,11 +184,11 @@ static int dict_find_or_add(friq_problem *P, int k, double v)
 int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
 {
     const int S = d->statedims_len, K = S + 1, A = d->actiondim.values_len, U = d->actiondim.universe_len;
-    if (S < 1 || K * FRIQ_IDX_BITS > 32) FAIL(2, "friq_problem_create: %d state dimensions unsupported (packed rule word holds %d)", S, 32 / FRIQ_IDX_BITS - 1);
+    if (S < 1 || K > FRIQ_MAXK) FAIL(2, "friq_problem_create: %d state dimensions unsupported (1..%d: FIVE_MAX_NUM_OF_UNIVERSES is %d)", S, FRIQ_MAXK - 1, FRIQ_MAXK);
     if (A < 2 || A > FRIQ_MAXA) FAIL(2, "friq_problem_create: %d actions unsupported (max %d)", A, FRIQ_MAXA);
     for (int k = 0; k < S; k++) {
         if (d->statedims[k].universe_len != U) FAIL(2, "friq_problem_create: all universes must have the same length (frirl_init.c:37)");
-        if (d->statedims[k].values_len < 2 || d->statedims[k].values_len > FRIQ_MAXDICT) FAIL(2, "friq_problem_create: state dim %d has %d values (2..%d supported)", k, d->statedims[k].values_len, FRIQ_MAXDICT);
+        if (d->statedims[k].values_len < 2 || d->statedims[k].values_len > FRIQ_DICT_MAX(K)) FAIL(2, "friq_problem_create: state dim %d has %d values (2..%d supported with %d antecedents)", k, d->statedims[k].values_len, FRIQ_DICT_MAX(K), K);
     }
     friq_problem *P = (friq_problem *)calloc(1, sizeof *P);
     friq_devprob *hp = &P->hp;
@@ -265,7 +265,7 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
         for (int k = 0; k < K; k++) {
             int lo = 0, hi = 0;
             for (int j = 1; j < hp->grid_len[k]; j++) { if (hp->dict_val[k][j] < hp->dict_val[k][lo]) lo = j; if (hp->dict_val[k][j] > hp->dict_val[k][hi]) hi = j; }
-            w |= (unsigned)(((r / (hp->ncorner >> (k + 1))) % 2 == 0) ? lo : hi) << (FRIQ_IDX_BITS * k);
+            w |= (unsigned)(((r / (hp->ncorner >> (k + 1))) % 2 == 0) ? lo : hi) << (FRIQ_BITS_OF(K) * k);
         }
         hp->corner[r] = w;
     }
@@ -275,7 +275,7 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
     if (hp->hit_scan) {
         int added = 0;
         for (int k = 0; k < S; k++)
-            if (hp->def_hit[k] < 0 && hp->dict_len[k] < FRIQ_MAXDICT) { dict_find_or_add(P, k, hp->values_def[k]); added = 1; }
+            if (hp->def_hit[k] < 0 && hp->dict_len[k] < FRIQ_DICT_MAX(K)) { dict_find_or_add(P, k, hp->values_def[k]); added = 1; }
         if (added) refresh_hit_scan(P);
     }
     *out = P;
@@ -286,7 +286,7 @@ int friq_problem_create(const friq_problem_desc *d, friq_problem **out)
  * actions, no environment - only the FIVE-level per-call entry points make sense on it. */
 int friq_problem_create_from_tables(int K, int U, int p, const double *u, const double *ve, friq_problem **out)
 {
-    if (K < 2 || K * FRIQ_IDX_BITS > 32) FAIL(2, "friq_problem_create_from_tables: %d antecedent dimensions unsupported (2..%d)", K, 32 / FRIQ_IDX_BITS);
+    if (K < 2 || K > FRIQ_MAXK) FAIL(2, "friq_problem_create_from_tables: %d antecedent dimensions unsupported (2..%d)", K, FRIQ_MAXK);
     friq_problem *P = (friq_problem *)calloc(1, sizeof *P);
     friq_devprob *hp = &P->hp;
     P->device = -1;
@@ -592,9 +592,9 @@ int friq_batch_set_rulebase(friq_batch *b, long agent, int R, const double *rant
         for (int k = 0; k < K; k++) {
             const int before = P->hp.dict_len[k];
             const int j = dict_find_or_add(P, k, rant[(size_t)i * K + k]);
-            if (j < 0) { free(w); FAIL(5, "friq_batch_set_rulebase: more than %d distinct antecedent values in dimension %d", FRIQ_MAXDICT, k); }
+            if (j < 0) { free(w); FAIL(5, "friq_batch_set_rulebase: more than %d distinct antecedent values in dimension %d", FRIQ_DICT_MAX(K), k); }
             grew |= (P->hp.dict_len[k] != before);
-            word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
+            word |= (unsigned int)j << (FRIQ_BITS_OF(K) * k);
         }
         w[i] = word;
     }
@@ -706,7 +706,7 @@ int friq_batch_get_rulebase(friq_batch *b, long agent, int *R_out, double *rant,
         int rc = friqd_d2h_2d(w, 4, b->st.rbw + off, FRIQ_TILE * 4, 4, R);
         if (rc) { free(w); FAIL(rc, "friq_batch_get_rulebase: %s", friqd_error_string(rc)); }
         for (int i = 0; i < R; i++)
-            for (int k = 0; k < K; k++) rant[(size_t)i * K + k] = hp->dict_val[k][(w[i] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+            for (int k = 0; k < K; k++) rant[(size_t)i * K + k] = hp->dict_val[k][FRIQ_FIELD(w[i], k, K)];
         free(w);
     }
     return 0;
@@ -1081,9 +1081,9 @@ int friq_batch_append_rule(friq_batch *b, long agent, const double *ant, double 
     for (int k = 0; k < K; k++) {
         const int before = P->hp.dict_len[k];
         const int j = dict_find_or_add(P, k, ant[k]);
-        if (j < 0) FAIL(5, "friq_batch_append_rule: more than %d distinct antecedent values in dimension %d", FRIQ_MAXDICT, k);
+        if (j < 0) FAIL(5, "friq_batch_append_rule: more than %d distinct antecedent values in dimension %d", FRIQ_DICT_MAX(K), k);
         grew |= (P->hp.dict_len[k] != before);
-        word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
+        word |= (unsigned int)j << (FRIQ_BITS_OF(K) * k);
     }
     if (grew) { refresh_hit_scan(P); int rcp_ = problem_publish(P); if (rcp_) return rcp_; }
     const size_t off = (size_t)(agent / FRIQ_TILE) * b->st.cap * FRIQ_TILE + (agent % FRIQ_TILE) + (size_t)R * FRIQ_TILE;
@@ -1120,9 +1120,9 @@ int friq_batch_merge_rb(friq_batch *b, long agent, int Rs, const double *rant, c
         for (int k = 0; k < K; k++) {
             const int before = P->hp.dict_len[k];
             const int j = dict_find_or_add(P, k, rant[(size_t)i * K + k]);
-            if (j < 0) { free(w); FAIL(5, "friq_batch_merge_rb: more than %d distinct antecedent values in dimension %d", FRIQ_MAXDICT, k); }
+            if (j < 0) { free(w); FAIL(5, "friq_batch_merge_rb: more than %d distinct antecedent values in dimension %d", FRIQ_DICT_MAX(K), k); }
             grew |= (P->hp.dict_len[k] != before);
-            word |= (unsigned int)j << (FRIQ_IDX_BITS * k);
+            word |= (unsigned int)j << (FRIQ_BITS_OF(K) * k);
         }
         w[i] = word;
     }
@@ -1172,7 +1172,7 @@ int friq_team_run(friq_batch *b, int team, int max_rounds, double *log, long max
                 double v = hp->values_def[k];
                 if (id >= 1) {
                     const int idx = (id - 1) * gap;
-                    v = idx < hp->ncorner ? hp->dict_val[k][(hp->corner[idx] >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)] : 0.0;
+                    v = idx < hp->ncorner ? hp->dict_val[k][FRIQ_FIELD(hp->corner[idx], k, hp->K)] : 0.0;
                 }
                 s0[(size_t)i * S + k] = v;
             }
@@ -1438,7 +1438,7 @@ static int fetch_rulebases(friq_batch *b, long first, long count, int *R, double
             const long o = ag - first;
             for (int i = 0; i < R[o]; i++) {
                 const unsigned int word = w[(size_t)i * FRIQ_TILE + l];
-                for (int k = 0; k < K; k++) rant[((size_t)o * cap + i) * K + k] = hp->dict_val[k][(word >> (FRIQ_IDX_BITS * k)) & (FRIQ_MAXDICT - 1)];
+                for (int k = 0; k < K; k++) rant[((size_t)o * cap + i) * K + k] = hp->dict_val[k][FRIQ_FIELD(word, k, K)];
                 rconc[(size_t)o * cap + i] = q[(size_t)i * FRIQ_TILE + l];
             }
         }

@@ -84,12 +84,14 @@ def main():
             print(f"knowledge sharing, {env}, {W} agents: {len(rows)} episodes, agent 0 ends with {len(txt.splitlines())} rules")
     # a problem that is none of the examples (3 state dimensions, 5 actions, skip_rules = 0): tests/dropin/custom_problem.c, our own
     # program on the reference's public API, built against the reference by oracle/Makefile
-    exe = os.path.join(HERE, "_ref", "custom_ref")
-    with tempfile.TemporaryDirectory() as tmp:
-        r = subprocess.run([exe], cwd=tmp, check=True, capture_output=True, text=True)
-        open(os.path.join(out, "custom_problem.out"), "w").write(r.stdout)
-        shutil.copy(os.path.join(tmp, "custom.frirlrb.txt"), os.path.join(out, "custom_problem.frirlrb.txt"))
-        print(f"custom problem: {len(r.stdout.splitlines())} output lines")
+    # custom6 / custom8: the same program with 5 / 7 state dimensions (K = 6 / 8 = FIVE_MAX_NUM_OF_UNIVERSES antecedents)
+    for tag in ("custom", "custom6", "custom8"):
+        exe = os.path.join(HERE, "_ref", tag + "_ref")
+        with tempfile.TemporaryDirectory() as tmp:
+            r = subprocess.run([exe], cwd=tmp, check=True, capture_output=True, text=True)
+            open(os.path.join(out, tag + "_problem.out"), "w").write(r.stdout)
+            shutil.copy(os.path.join(tmp, "custom.frirlrb.txt"), os.path.join(out, tag + "_problem.frirlrb.txt"))
+            print(f"{tag} problem: {len(r.stdout.splitlines())} output lines")
 
 
 if __name__ == "__main__":

@@ -4,7 +4,9 @@
  * It is compiled twice from this one source:
  *   oracle/_ref/custom_ref          against the reference's headers and library   -> tests/golden/custom_problem.out
  *   tests/dropin/_build/custom_dropin  against include/dropin and libfriq_b200.so -> must print the same, bit for bit
- * (all numbers are printed as hex floats).  Own code; nothing is taken from the reference's sources. */
+ * (all numbers are printed as hex floats).  Own code; nothing is taken from the reference's sources.
+ * -DNS=5 / -DNS=7 add two / four more state dimensions (K = 6 / 8 antecedents, the reference's FIVE_MAX_NUM_OF_UNIVERSES):
+ * custom6_* / custom8_* are the same program for those sizes. */
 #include "frirl.h"
 #include "frirl_types.h"
 #include "frirl_types_def.h"
@@ -12,6 +14,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifndef NS
+#define NS 3                      /* state dimensions */
+#endif
+#define NK (NS + 1)
 
 static void do_action(struct frirl_desc *f, fri_float action, fri_float *s, int n, fri_float *o)
 {   /* a damped point mass pushed by the action, with a slowly drifting third coordinate */
@@ -24,6 +30,7 @@ static void do_action(struct frirl_desc *f, fri_float action, fri_float *s, int 
     if (x < -2.0) { x = -2.0; v = 0.0; }
     double w = s[2] * 0.9 + (x > 0 ? 0.05 : -0.05);
     o[0] = x; o[1] = v; o[2] = w;
+    for (int k = 3; k < NS; k++) o[k] = s[k] * 0.8 + ((k & 1) ? 0.06 : -0.04) * (v > 0 ? 1.0 : -1.0) + 0.01 * s[k - 1];   /* more slow coordinates */
 }
 static void get_reward(struct frirl_desc *f, fri_float *s, int n, struct frirl_reward_desc *r)
 {
@@ -51,8 +58,14 @@ int main(void)
     FRIRL_ALLOC_DIM(d1); FRIRL_GEN_FIXRES_DIM(d1);
     struct frirl_dimension_desc d2 = { .values_len = 3, .values_div = 0.5, .values_steep = 1.0, .values_def = 0.0, .universe_len = 41, .universe_div = 0.025 };
     FRIRL_ALLOC_DIM(d2); FRIRL_GEN_FIXRES_DIM(d2);
-    frirl.statedims = (struct frirl_dimension_desc[]){d0, d1, d2};
-    frirl.statedims_len = 3;
+    struct frirl_dimension_desc dims[NS] = {d0, d1, d2};
+    for (int k = 3; k < NS; k++) {
+        struct frirl_dimension_desc dk = { .values_len = 3, .values_div = 0.5, .values_steep = 1.0, .values_def = 0.0, .universe_len = 41, .universe_div = 0.025 };
+        FRIRL_ALLOC_DIM(dk); FRIRL_GEN_FIXRES_DIM(dk);
+        dims[k] = dk;
+    }
+    frirl.statedims = dims;
+    frirl.statedims_len = NS;
     struct frirl_dimension_desc actiondim = { .values_len = 5, .values_div = 0.5, .universe_len = 41, .universe_div = 0.05 };
     FRIRL_ALLOC_DIM(actiondim); FRIRL_GEN_FIXRES_DIM(actiondim);
     frirl.actiondim = actiondim;
@@ -63,20 +76,20 @@ int main(void)
     frirl_sequential_run(&frirl);
     printf("final rules %d\n", frb->numofrules);
     for (int i = 0; i < frb->numofrules; i++) {
-        for (int k = 0; k < 4; k++) printf("%a ", frb->rant[i * 4 + k]);
+        for (int k = 0; k < NK; k++) printf("%a ", frb->rant[i * NK + k]);
         printf("%a\n", frb->rconc[i]);
     }
     /* per-call functions at a few points (pseudo-random, fixed) */
     unsigned long long lcg = 12345;
     for (int t = 0; t < 12; t++) {
-        double x[4];
-        for (int k = 0; k < 4; k++) {
+        double x[NK];
+        for (int k = 0; k < NK; k++) {
             lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
             const double u01 = (double)(lcg >> 11) * 0x1p-53;
             const double lo = frb->u[k * 41], hi = frb->u[k * 41 + 40];
             x[k] = lo + u01 * (hi - lo);
         }
-        if (t % 4 == 3) memcpy(x, frb->rant + (size_t)(t % frb->numofrules) * 4, sizeof x);     /* an exact hit */
+        if (t % 4 == 3) memcpy(x, frb->rant + (size_t)(t % frb->numofrules) * NK, sizeof x);     /* an exact hit */
         double conc = 0.0;
         const unsigned hit = FIVE_vag_concl(frb, x, &conc);
         const unsigned best = frirl_get_best_action(&frirl, x);

@@ -223,13 +223,16 @@ def test_reference_api_calls_match_oracle(env, tmp_path):
     assert int(f[1]) == hit and float.fromhex(f[2]) == conc
 
 
-def test_custom_problem_on_the_reference_api_matches_the_reference(tmp_path):
+@pytest.mark.parametrize("tag", ["custom", "custom6", "custom8"])
+def test_custom_problem_on_the_reference_api_matches_the_reference(tmp_path, tag):
     """tests/dropin/custom_problem.c - a program on the reference's public API for a problem that is none of the examples
     (3 state dimensions, 5 actions, skip_rules = 0, host-callback environment) - prints, built against the B200 engine, exactly
     what it prints built against the reference (golden recorded by oracle/make_golden.py from oracle/_ref/custom_ref): the
-    per-episode log, the learned rule base and per-call results, all as hex floats.  Exercises the generic-shape kernels."""
-    r = subprocess.run([_exe("custom_dropin")], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    per-episode log, the learned rule base and per-call results, all as hex floats.  Exercises the generic-shape kernels.
+    custom6 / custom8: the same program with 5 / 7 state dimensions = 6 / 8 antecedents (FIVE_MAX_NUM_OF_UNIVERSES, FIVE.h:19:
+    5- and 4-bit antecedent indexes in the packed rule word, 64 / 256 corner rules)."""
+    r = subprocess.run([_exe(tag + "_dropin")], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    want = open(os.path.join(_golden.GOLDEN, "custom_problem.out")).read()
+    want = open(os.path.join(_golden.GOLDEN, tag + "_problem.out")).read()
     assert r.stdout.splitlines() == want.splitlines()
-    assert open(tmp_path / "custom.frirlrb.txt", "rb").read() == open(os.path.join(_golden.GOLDEN, "custom_problem.frirlrb.txt"), "rb").read()
+    assert open(tmp_path / "custom.frirlrb.txt", "rb").read() == open(os.path.join(_golden.GOLDEN, tag + "_problem.frirlrb.txt"), "rb").read()

@@ -1,9 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2c_bench_c3_8gpu.json 2> gpurun_out/r2c_bench_c3_8gpu.err
-python - <<'PY'
-import json
-t=[l for l in open("gpurun_out/r2c_bench_c3_8gpu.json").read().split("\n") if l.startswith("{")]
-d=json.loads(t[-1]); print('c3 8 GPUs', '%.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'e2e ms %.3f'%d['e2e']['ms_per_step'], 'by rank', d.get('ms_per_step_by_rank'))
-PY
+( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/r2an_pytest.log 2>&1
+tail -15 gpurun_out/r2an_pytest.log
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('c3', '%.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'e2e %.4g'%d['e2e']['value'])"
