@@ -282,11 +282,13 @@ def test_hit_sweep_is_disabled_when_dictionary_ve_values_collide(fq):
     b.close(); P.close()
 
 
-def test_table_mode_survives_dictionary_growth_and_odd_capacity(fq):
+@pytest.mark.parametrize("cap", [184, 187])
+def test_table_mode_survives_dictionary_growth_and_odd_capacity(fq, cap):
     """Table mode of the fused kernel (memoised Shepard weights between dictionary cells, per-agent rule-cell lists and
     cell-to-rule maps).  A loaded rule base with an antecedent value OFF the grid whose universe point no grid value
     shares makes the dictionary - and with it the weight table and the per-agent indexes - grow after the batch
-    exists; the capacity is no multiple of the 8-rule blocks the cell lists are read in.  Results equal the oracle."""
+    exists.  Capacity 184: table mode (whole blocks of 8 rules are summed and stored); 187, no multiple of the block size:
+    the engine falls back to the computed chains.  Results equal the oracle either way."""
     name = "mountaincar"
     P = fq.Problem(name, no_random=0)
     g = _golden.load(name)
@@ -296,7 +298,7 @@ def test_table_mode_survives_dictionary_growth_and_odd_capacity(fq):
     used |= {int(np.argmin(np.abs(u - (-0.5))))}
     free = [i for i in range(3, len(u) - 3) if i not in used]
     rant[7, 0] = u[free[len(free) // 2]]                      # a new dictionary entry with its own VE value
-    n, cap = 45, 187
+    n = 45
     b = fq.Batch(P, n, cap, seed0=991, first_agent=5)
     b.run(40, fq.RUN_LEARN | fq.RUN_RETILE)                  # indexes sized for the original table ...
     b.reset()
@@ -541,6 +543,33 @@ def test_capacity_overflow_is_flagged(fq):
     o = b.gather()
     assert np.all(o["rules"] == 12) and np.all(o["flags"] & fq.F_OVERFLOW)
     b.close(); P.close()
+
+
+def test_full_rule_bases_in_table_mode_equal_computed_chains(fq):
+    """Rule bases that fill their capacity to the last slot (capacity 40 = five blocks of 8: the table-mode walk then sums a
+    last block without a zero-weight tail and reads the zero cells kept BEHIND the column), with exploration, re-tiling and
+    weighted updates going on after the overflow: table mode (policy 2) and the computed chains (policy 1) must agree bit for bit."""
+    n = 200
+    rng = np.random.default_rng(5)
+    alpha = rng.uniform(0.2, 0.8, n); eps = rng.choice([0.0, 0.05, 0.2], n)
+    res = []
+    for policy in (2, 1):
+        P = fq.Problem("mountaincar", no_random=0)
+        b = fq.Batch(P, n, 40, seed0=77)
+        b.set_policy(policy)
+        b.set_hyper(alpha, np.ones(n), eps)
+        for chunk in (700, 900):
+            b.run(chunk, fq.RUN_LEARN | fq.RUN_RETILE)
+        o = b.gather()
+        res.append((o, [b.get_rulebase(i) for i in range(0, n, 7)]))
+        b.close(); P.close()
+    (o0, r0), (o1, r1) = res
+    full = o0["rules"] == 40
+    assert full.sum() >= 10 and np.all(o0["flags"][full] & fq.F_OVERFLOW)
+    for k in ("last_return", "last_steps", "rules", "episodes", "flags", "total_steps", "sum_rules"):
+        assert np.array_equal(o0[k], o1[k]), k
+    for (Ra, ra, qa), (Rb, rb, qb) in zip(r0, r1):
+        assert Ra == Rb and np.array_equal(ra, rb) and np.array_equal(qa, qb)
 
 
 @pytest.mark.parametrize("width", [1, 7, 64])
