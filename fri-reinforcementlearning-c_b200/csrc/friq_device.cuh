@@ -584,10 +584,17 @@ __device__ __noinline__ void friq_pair_sums_slow(const friq_devprob *pbp, const 
     out[0] = vag; out[1] = ws;
 }
 
+// a warp's scratch for one round in table mode (shared memory): the owners post one descriptor per pair - x = offset of the
+// pair's row in the memoised table (FRIQ_NO_ROW: the point is no dictionary cell), y = owner lane | channel << 8 | rule count
+// << 16 - and the lanes that summed a pair post {conclusion (Q(s,a): the weighted sum), sum of the weights} for the owner
+#define FRIQ_NO_ROW 0xffffffffu
+struct __align__(16) friq_round_smem { uint2 desc[FRIQ_TILE]; double2 res[FRIQ_TILE]; };
 template <int S, int P, int A, int UNR, bool SAFE, bool TAB>
 __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, const uint32_t *rbw, const double *rbq, double *sw,
                                                      const unsigned short *rbc /* TAB: the TILE's rule cells (friq_devstate.rbc layout) */, int R,
-                                                     const double *vo_obs, const double *vo_q, uint32_t ow, uint32_t qw,
+                                                     const double *vo_obs, const double *vo_q,
+                                                     const unsigned (&arow)[A], unsigned qrow /* TAB: table rows of my action pairs / my Q(s,a) pair */,
+                                                     friq_round_smem *rs /* TAB: the warp's round scratch */,
                                                      unsigned wmask, const unsigned (&nm)[A], unsigned qm,
                                                      unsigned char *plist /* 32 bytes of shared memory per warp */,
                                                      double (&conc)[A], double &vagq, double &wsq, unsigned &n_tab, unsigned &n_chain, bool keep_sw)
@@ -619,11 +626,17 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
 #pragma unroll
         for (int t = 0; t < C; t++) {
             const int e = ofs[t] + __popc(chm[t] & lt) - p0;
-            if (((chm[t] >> lane) & 1u) && e >= 0 && e < per_round) plist[e] = (unsigned char)(lane | (t << 5));
+            if (((chm[t] >> lane) & 1u) && e >= 0 && e < per_round) {
+                if constexpr (TAB) rs->desc[e] = make_uint2(t < A ? arow[t < A ? t : 0] : qrow, (unsigned)lane | ((unsigned)t << 8) | ((unsigned)R << 16));
+                else plist[e] = (unsigned char)(lane | (t << 5));
+            }
         }
         __syncwarp(wmask);
         const bool has = p0 + rank < np && !(p0 + rank >= end_act && p0 + rank < ofs[A]);
-        const int ent = has ? plist[rank] : 0;
+        uint2 desc = make_uint2(FRIQ_NO_ROW, 0u);
+        int ent = 0;
+        if constexpr (TAB) { if (has) desc = rs->desc[rank]; ent = (int)(desc.y & 31u) | (int)(((desc.y >> 8) & 0xffu) << 5); }
+        else ent = has ? plist[rank] : 0;
         const int c = ent >> 5, j = ent & 31;
         // ---- the owner's point (table mode needs it only for the rare computed fall-back) and rule count
         double pt[K];
@@ -641,17 +654,15 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
         const friq_cellvec *pc = reinterpret_cast<const friq_cellvec *>(rbc) + j;
         friq_cellvec c0 = friq_cellvec_zero(); double q0[FRIQ_CELL_VEC];
         if constexpr (TAB) { c0 = pc[0]; friq_tab_load_q(tq + j, q0); }
-        const int Rj = __shfl_sync(wmask, R, j);
+        int Rj;
+        if constexpr (TAB) Rj = (int)(desc.y >> 16); else Rj = __shfl_sync(wmask, R, j);
         const bool isq = has && c == A;
         double vag = 0.0, ws = 0.0;
         // ---- table mode: a pair whose point is a dictionary cell looks the weight of every rule up (pb.wtab)
         if constexpr (TAB) {
-            const uint32_t x = __shfl_sync(wmask, ow, j), y = __shfl_sync(wmask, qw, j);
-            const int ah = pb.act_hit[c < A ? c : 0];
-            const uint32_t pw = (c == A) ? y : ((x != FRIQ_NO_TARGET && ah >= 0) ? (x | ((uint32_t)ah << (FRIQ_BITS_OF(S + 1) * S))) : FRIQ_NO_TARGET);
-            const bool tab = has && pw != FRIQ_NO_TARGET;
+            const bool tab = has && desc.x != FRIQ_NO_ROW;
             if (tab) {
-                const double *rowd = pb.wtab + (size_t)friq_cell<K>(pb, pw) * (size_t)pb.wstride;
+                const double *rowd = pb.wtab + desc.x;
                 asm volatile("" : "+l"(rowd));           // one base register for the row (lookups stay base + cell * 8)
                 if (keep_sw && p0 >= ofs[A]) friq_tab_sums<true>(friq_row_f64{rowd}, pc, tq + j, tsw + j, c0, q0, Rj, vag, ws);   // a round of Q(s,a) pairs
                 else friq_tab_sums<false>(friq_row_f64{rowd}, pc, tq + j, tsw + j, c0, q0, Rj, vag, ws);
@@ -710,6 +721,19 @@ __device__ __forceinline__ void friq_pairs_compacted(const friq_devprob &pb, con
         }   // !TAB
         const double res = __ddiv_rn(vag, ws);                                               // BestAct.c:265
         // ---- hand the results back to the owners
+        if constexpr (TAB) {                             // through the warp's scratch: entry e was summed by the lane of rank e
+            rs->res[rank] = make_double2(c == A ? vag : res, ws);
+            __syncwarp(wmask);
+#pragma unroll
+            for (int t = 0; t < C; t++) {
+                const int e = ofs[t] + __popc(chm[t] & lt) - p0;
+                if (((chm[t] >> lane) & 1u) && e >= 0 && e < per_round) {
+                    const double2 v = rs->res[e];
+                    if (t < A) conc[t < A ? t : 0] = v.x; else { vagq = v.x; wsq = v.y; }
+                }
+            }
+            continue;
+        }
         __syncwarp(wmask);
 #pragma unroll
         for (int t = 0; t < C; t++) {

@@ -93,6 +93,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
 {
     constexpr int K = S + 1;
     __shared__ unsigned char pair_list[(COOP == 2 ? FRIQ_BLOCK_TAB : FRIQ_BLOCK) / 32][32];   // friq_pairs_compacted, per warp
+    __shared__ friq_round_smem round_smem[COOP == 2 ? FRIQ_BLOCK_TAB / 32 : 1];                // the same in table mode
 #ifdef FRIQ_TIMELINE
     const unsigned long long tl_t0 = friq_globaltimer();
 #endif
@@ -125,7 +126,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
     constexpr bool tabmode = COOP == 2;                  // the host launches this variant only with a table and sized indexes
     unsigned short *rbc = tabmode ? st.rbc + (size_t)(ag >> 5) * friq_rbc_slots(st.cap) * FRIQ_TILE : nullptr;      // the TILE's rule cells
     unsigned short *cmap = tabmode ? st.cmap + (size_t)(ag >> 5) * st.idx_cells * FRIQ_TILE + (ag & 31) : nullptr;
-    uint32_t qw = FRIQ_NO_TARGET;                        // packed dictionary indices of the pending update's point vo[], if it has them
+    unsigned qrow = FRIQ_NO_ROW;                         // offset of the row of the pending update's point vo[] in the memoised table, if it is a dictionary cell
     if (tabmode) {
         int unk[S];
 #pragma unroll
@@ -133,7 +134,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         const uint32_t w0 = friq_obs_word<S>(pb, vo, unk);
         int ah = -1;
         for (int j = 0; j < pb.dict_len[S]; j++) if (pb.dict_ve[S][j] == vo[S]) { ah = j; break; }
-        if (w0 != FRIQ_NO_TARGET && ah >= 0) qw = w0 | ((uint32_t)ah << (FRIQ_BITS_OF(K) * S));
+        if (w0 != FRIQ_NO_TARGET && ah >= 0) qrow = (unsigned)friq_cell<K>(pb, w0 | ((uint32_t)ah << (FRIQ_BITS_OF(K) * S))) * (unsigned)pb.wstride;
     }
 
     // All lanes of a warp iterate in lockstep (explicit reconvergence at the loop top): a lane that starts
@@ -189,6 +190,9 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         // the (lane, action) pairs without one need Shepard sums - cooperatively when few, else through the lock-step pass
         bool lockstep = true, kept_sw = true;
         uint32_t ow = FRIQ_NO_TARGET;
+        unsigned arow[A];                                // table mode: offset of the row of (observation, action a) in the memoised table
+#pragma unroll
+        for (int a = 0; a < A; a++) arow[a] = FRIQ_NO_ROW;
         if constexpr (COOP || A == ACH) if (COOP || pb.hit_scan) {
             ow = friq_obs_word<S>(pb, vc, ci);
             uint32_t tgt[A]; unsigned nm[A]; int pairs = 0;
@@ -198,7 +202,11 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 const int oc = (ow != FRIQ_NO_TARGET) ? friq_cell<S>(pb, ow) : 0;
 #pragma unroll
                 for (int a = 0; a < A; a++)
-                    hidx[a] = (act && tgt[a] != FRIQ_NO_TARGET) ? (int)cmap[(size_t)(oc + pb.act_hit[a] * pb.wlin[S]) * FRIQ_TILE] - 1 : -1;
+                {
+                    const int ca = oc + pb.act_hit[a] * pb.wlin[S];
+                    hidx[a] = (act && tgt[a] != FRIQ_NO_TARGET) ? (int)cmap[(size_t)ca * FRIQ_TILE] - 1 : -1;
+                    if (tgt[a] != FRIQ_NO_TARGET) arow[a] = (unsigned)ca * (unsigned)pb.wstride;
+                }
             } else
                 friq_hit_scan<A>(rbw, act ? R : 0, tgt, hidx);
 #pragma unroll
@@ -216,7 +224,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 const long long tl_c0 = clock64();
                 if (pairs | qm) { tl_rounds++; tl_pairs += pairs + __popc(qm); tl_walk += __reduce_max_sync(wmask, (act && (needq || hidx[0] < 0 || hidx[A - 1] < 0 || hidx[A / 2] < 0)) ? R : 0); }
 #endif
-                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, ow, qw, wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq, c_tab, c_chain, kept_sw);
+                if (pairs | qm) friq_pairs_compacted<S, P, A, FRIQ_COMPACT_UNR, SAFE, tabmode>(pb, rbw, rbq, sw, rbc, R, vc, vo, arow, qrow, &round_smem[tabmode ? threadIdx.x >> 5 : 0], wmask, nm, qm, pair_list[threadIdx.x >> 5], actconc, vagq, wsq, c_tab, c_chain, kept_sw);
 #ifdef FRIQ_TIMELINE
                 tl_cyc += clock64() - tl_c0;
 #endif
@@ -234,8 +242,8 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
         }
         const int a2 = friq_select_action<A>(pb, actconc, epsilon, seed, ep_num, (uint32_t)step_in_ep);
         const int next_hit = qp_reuse ? friq_pick_int<A>(hidx, a2) : -2;
-        const uint32_t qw_upd = qw;                      // the pending update's point (its weights are looked up again by the weighted update)
-        if (act) qw = (ow != FRIQ_NO_TARGET && pb.act_hit[a2] >= 0) ? (ow | ((uint32_t)pb.act_hit[a2] << (FRIQ_BITS_OF(K) * S))) : FRIQ_NO_TARGET;
+        const unsigned qrow_upd = qrow;                  // the pending update's point (its weights are looked up again by the weighted update)
+        if (act) qrow = (unsigned)friq_pick_int<A>(reinterpret_cast<const int *>(arow), a2);
         if (act && initial) { aidx = a2; qs[S] = pb.act_val[a2]; vo[S] = pb.act_ve_eval[a2]; qi[S] = a2; hitq = next_hit; }
         if (act && !initial) {
             sum_rules += (unsigned long long)R;
@@ -253,8 +261,8 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 else { ws = wsq; qnow = __ddiv_rn(vagq, wsq); }                               // FIVEVagConcl.c:302
                 const int R0 = R;
                 if constexpr (tabmode) {
-                    const bool look = !kept_sw && qw_upd != FRIQ_NO_TARGET;
-                    const friq_row_f64 row{pb.wtab + (size_t)(look ? friq_cell<K>(pb, qw_upd) : 0) * (size_t)pb.wstride};
+                    const bool look = !kept_sw && qrow_upd != FRIQ_NO_ROW;
+                    const friq_row_f64 row{pb.wtab + (look ? qrow_upd : 0u)};
                     friq_sarsa_apply<S, P, true, friq_row_f64>(pb, rbw, rbq, sw, st.cap, R, flags, qs, qi, reward, qp, hitq, qnow, ws, alpha, gamma, wref, &c_wupd,
                                                                look ? &row : nullptr, rbc);
                 } else
