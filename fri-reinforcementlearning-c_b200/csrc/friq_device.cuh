@@ -456,7 +456,8 @@ __device__ __forceinline__ void friq_hit_scan(const uint32_t *rbw, int R, const 
 // owner's point (shuffles), walks the OWNER's rule-base column - the 32 columns of a tile share their cache lines row by
 // row, so these reads stay coalesced - and accumulates the sums sequentially in its own registers exactly like the
 // lock-step pass does (UNR rules = UNR independent chains per trip, friq_shepard_weights_n).  One round serves as many
-// pairs as the warp has lanes for the price of ONE chain per rule; the owners then pick their results up with a shuffle.  Bit-identical sums.
+// pairs as the warp has lanes for the price of ONE chain per rule; the owners then pick their results up - with shuffles in the
+// computed mode, through the warp's scratch in shared memory in table mode (friq_round_smem).  Bit-identical sums.
 // dictionary cell of a packed word (row / column of the memoised weights pb.wtab)
 template <int K>
 __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
@@ -469,7 +470,9 @@ __device__ __forceinline__ int friq_cell(const friq_devprob &pb, uint32_t w)
 
 // ---- table mode: the per-agent list of rule cells (friq_devstate.rbc) is stored in blocks of FRIQ_CELL_VEC rules per lane,
 // [tile][slot / 8][lane][8] u16, so that a lane fetches the cells of 8 consecutive rules of a column with ONE 16-byte load;
-// the unused tail of the last block holds cell 0 (any valid column: those weights are loaded but never added).
+// the unused tail of the last block and FRIQ_RBC_AHEAD whole blocks behind it hold the table's zero column (friq_zero_cell).
+// Lane-minor on purpose: the lanes of a warp walk columns of the SAME tile, so their loads of a slot share cache lines; three
+// agent-major variants of these arrays measured 4-38 % slower (profiles/README.md).
 #ifndef FRIQ_CELL_VEC
 #define FRIQ_CELL_VEC 8         /* 8 (one 16-byte load per block) or 4 (8-byte loads, half the registers in flight) */
 #endif
