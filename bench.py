@@ -259,9 +259,13 @@ class ClockSampler:
 
 
 def kernel_source_hash():
+    """sha1 of the kernel sources with comments and white space removed: what the calibration is tied to is the CODE"""
     h = hashlib.sha1()
     for f in ("friq_engine.cu", "friq_device.cuh", "friq_math.cuh", "friq_trig.h", "friq_devprob.h"):
-        h.update(open(os.path.join(PKG, "csrc", f), "rb").read())
+        t = open(os.path.join(PKG, "csrc", f), "r", errors="replace").read()
+        t = re.sub(r"/\*.*?\*/", " ", t, flags=re.S)
+        t = re.sub(r"//[^\n]*", " ", t)
+        h.update(" ".join(t.split()).encode())
     return h.hexdigest()[:12]
 
 
