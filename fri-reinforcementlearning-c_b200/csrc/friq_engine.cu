@@ -1549,7 +1549,7 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     // table mode (memoised weights + per-agent indexes) only where the COOP kernels run and the indexes are sized for this table
     const bool coop = variant >= 1 && hp->hit_scan && hp->safe_range &&
                       ((hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) || (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)));
-    const bool tab = coop && variant == 2 && hp->wtab && st.rbc && st.idx_cells == hp->wcells && (st.cap % FRIQ_CELL_VEC) == 0;
+    const bool tab = coop && variant == 2 && hp->wtab && st.rbc && st.idx_cells == hp->wcells && (st.cap % FRIQ_CELL_VEC) == 0 && st.cap <= 65535;   /* whole blocks; the rule count rides in 16 bits of a round descriptor */
     if (tab) {
         CK(cudaMemsetAsync(st.cmap, 0, (size_t)((st.n + FRIQ_TILE - 1) / FRIQ_TILE) * st.idx_cells * FRIQ_TILE * sizeof(unsigned short), s));
         k_refresh_index<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st);
