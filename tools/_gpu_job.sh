@@ -1,5 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 ) > gpurun_out/r2c_multi_gpu_tests.log 2>&1
-cat gpurun_out/r2c_multi_gpu_tests.log
+STEPS=20 BENCH_ARGS="--warmup 5 --policy 3 --groups 1" bash tools/run_variants.sh 2>&1 | tee gpurun_out/r2av_sliced.log
+STEPS=6 BENCH_ARGS="--workload c5 --policy 3 --groups 1" bash tools/run_variants.sh 2>&1 | tee -a gpurun_out/r2av_sliced.log
