@@ -219,7 +219,7 @@ k_run_steps(const friq_devprob *__restrict__ gprob, friq_devstate st, long n_ste
                 vagq = 0.0; wsq = 0.0;
                 // weighted updates read the weights of Q(s,a): handed over through sw[] when MANY lanes update (their reads of a slot
                 // coalesce), looked up again by the owner when few do (FRIQ_WUPD_LOOKUP_MAX); knowledge-sharing runs always keep them
-                kept_sw = !tabmode || wref != nullptr || __popc(qm) > FRIQ_WUPD_LOOKUP_MAX;
+                kept_sw = !tabmode || wref != nullptr || (__popc(qm) > FRIQ_WUPD_LOOKUP_MAX && (st.cap % FRIQ_CELL_VEC) == 0);   // kept weights are stored in whole blocks: a capacity that is no multiple of the block size looks them up again
 #ifdef FRIQ_TIMELINE
                 const long long tl_c0 = clock64();
                 if (pairs | qm) { tl_rounds++; tl_pairs += pairs + __popc(qm); tl_walk += __reduce_max_sync(wmask, (act && (needq || hidx[0] < 0 || hidx[A - 1] < 0 || hidx[A / 2] < 0)) ? R : 0); }
@@ -1549,7 +1549,8 @@ int friqd_run_steps(const friq_devprob *hp, const friq_devprob *dprob, friq_devs
     // table mode (memoised weights + per-agent indexes) only where the COOP kernels run and the indexes are sized for this table
     const bool coop = variant >= 1 && hp->hit_scan && hp->safe_range &&
                       ((hp->env == FRIQ_ENV_MOUNTAINCAR && FRIQ_SHAPE_MC(hp)) || (hp->env == FRIQ_ENV_ACROBOT && FRIQ_SHAPE_AC(hp)));
-    const bool tab = coop && variant == 2 && hp->wtab && st.rbc && st.idx_cells == hp->wcells && (st.cap % FRIQ_CELL_VEC) == 0 && st.cap <= 65535;   /* whole blocks; the rule count rides in 16 bits of a round descriptor */
+    const bool tab = coop && variant == 2 && hp->wtab && st.rbc && st.idx_cells == hp->wcells && st.cap <= 65535 &&                             /* the rule count rides in 16 bits of a round descriptor */
+                     ((st.cap % FRIQ_CELL_VEC) == 0 || !((mode & FRIQ_M_KEEP_WEIGHTS) && st.wref));   /* kept weights (knowledge sharing) are stored in whole blocks of rules */
     if (tab) {
         CK(cudaMemsetAsync(st.cmap, 0, (size_t)((st.n + FRIQ_TILE - 1) / FRIQ_TILE) * st.idx_cells * FRIQ_TILE * sizeof(unsigned short), s));
         k_refresh_index<<<g, FRIQ_BLOCK, 0, s>>>(dprob, st);

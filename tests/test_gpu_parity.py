@@ -287,8 +287,8 @@ def test_table_mode_survives_dictionary_growth_and_odd_capacity(fq, cap):
     """Table mode of the fused kernel (memoised Shepard weights between dictionary cells, per-agent rule-cell lists and
     cell-to-rule maps).  A loaded rule base with an antecedent value OFF the grid whose universe point no grid value
     shares makes the dictionary - and with it the weight table and the per-agent indexes - grow after the batch
-    exists.  Capacity 184: table mode (whole blocks of 8 rules are summed and stored); 187, no multiple of the block size:
-    the engine falls back to the computed chains.  Results equal the oracle either way."""
+    exists.  Capacity 184: whole blocks of 8 rules are summed and, for Q(s,a), stored; 187, no multiple of the block size: table
+    mode still, but the weights of Q(s,a) are looked up again instead of stored.  Results equal the oracle either way."""
     name = "mountaincar"
     P = fq.Problem(name, no_random=0)
     g = _golden.load(name)
@@ -542,6 +542,28 @@ def test_capacity_overflow_is_flagged(fq):
     b.run(400, fq.RUN_LEARN)
     o = b.gather()
     assert np.all(o["rules"] == 12) and np.all(o["flags"] & fq.F_OVERFLOW)
+    b.close(); P.close()
+
+
+def test_acrobot_table_mode_with_a_capacity_off_the_block_size_matches_oracle(fq):
+    """Acrobot in table mode with a rule capacity (701) that is no multiple of the walk's block of 8 rules: many lanes of a warp
+    update with weights at every step, and with such a capacity those weights are looked up again instead of being stored in
+    whole blocks.  Sampled agents equal the oracle."""
+    name, n, cap, steps = "acrobot", 96, 701, 350
+    P = fq.Problem(name, no_random=0)
+    rng = np.random.default_rng(12)
+    alpha = rng.uniform(0.2, 0.8, n); eps = rng.choice([0.0, 0.02, 0.1], n)
+    b = fq.Batch(P, n, cap, seed0=31337)
+    b.set_hyper(alpha, np.ones(n), eps)
+    for chunk in (100, steps - 100):
+        b.run(chunk, fq.RUN_LEARN | fq.RUN_RETILE)
+    OP = _oracle.Problem(_golden.ENV_ID[name], trig=1); OP.set_no_random(0)
+    for i in (0, 17, 40, 95):
+        a = _oracle.Agent(OP, cap, seed=31337 + i)
+        a.set_hyper(alpha[i], 1.0, eps[i]); a.run_steps(steps)
+        R, rant, rconc = b.get_rulebase(i)
+        oR, orant, orconc = a.rb()
+        assert R == oR and np.array_equal(rant, orant) and np.array_equal(rconc, orconc), i
     b.close(); P.close()
 
 

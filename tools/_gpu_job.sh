@@ -1,5 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-STEPS=20 BENCH_ARGS="--warmup 5 --policy 3 --groups 1" bash tools/run_variants.sh 2>&1 | tee gpurun_out/r2av_sliced.log
-STEPS=6 BENCH_ARGS="--workload c5 --policy 3 --groups 1" bash tools/run_variants.sh 2>&1 | tee -a gpurun_out/r2av_sliced.log
+( timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -6 ) > gpurun_out/r2aw_pytest.log 2>&1
+tail -6 gpurun_out/r2aw_pytest.log
