@@ -383,13 +383,20 @@ def main():
         # the exchange moves 16 B per agent: one NCCL channel is plenty, and NCCL's persistent CTAs - which sit on SM slots while
         # they wait for the slowest rank - stay out of the step kernels' way (measured at 2 GPUs: 3.91 -> 3.82 ms per step)
         os.environ.setdefault("NCCL_MAX_CTAS", "1")
-        try:                                     # the collective runs on NCCL's own stream: make it a high-priority one (it is tiny and must not queue behind the step kernels)
-            if not args.nccl_high_priority:
-                raise AttributeError
-            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
-        except (AttributeError, TypeError):
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout is the ONE JSON line: whatever NCCL prints while the communicator comes up (its version line under NCCL_DEBUG=VERSION)
+        # goes to stderr - file descriptor 1 points there until the first collective has run
+        sys.stdout.flush(); saved_stdout = os.dup(1); os.dup2(2, 1)
+        try:
+            try:                                 # the collective runs on NCCL's own stream: make it a high-priority one (it is tiny and must not queue behind the step kernels)
+                if not args.nccl_high_priority:
+                    raise AttributeError
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
+            except (AttributeError, TypeError):
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved_stdout, 1); os.close(saved_stdout)
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
