@@ -74,7 +74,7 @@ class ResultExchange:
 
         buf = x.next_buffers()                  # (ret, steps, rules) views the engine writes into (friq_batch_gather_device)
         ... engine call on `stream` ...
-        x.exchange_async(stream)                # side stream: wait for `stream`, 3 all-gathers (+ the statistics kernel)
+        x.exchange_async(stream)                # side stream: wait for `stream`, 3 all-gathers as one grouped call (+ the statistics kernel)
         ...
         x.wait(stream)                          # `stream` waits for everything in flight; results() is then valid
 
@@ -94,6 +94,7 @@ class ResultExchange:
             glo = tuple(mk(self.world * n, t.dtype) for t in loc) if self.world > 1 else loc
             self.sets.append(dict(local=loc, all=glo, stats=torch.zeros(3, dtype=torch.float64, device=device), done=None, used=False))
         self.cur = -1
+        self._no_coalescing = False
         self.side = torch.cuda.Stream(device=self.device, priority=-1) if self.cuda else None
         # legacy single-set views (first set)
         self.ret, self.steps, self.rules = self.sets[0]["local"]
@@ -108,8 +109,21 @@ class ResultExchange:
 
     def _run(self, st):
         if self.world > 1:
-            for dst, src in zip(st["all"], st["local"]):
-                self.dist.all_gather_into_tensor(dst, src)
+            # the three all-gathers as ONE grouped NCCL call (one kernel instead of three: each of them has to find a free SM next to
+            # step kernels that fill the GPU, and holds it while it waits for the slowest rank); gloo and older torch: one by one
+            cm = getattr(self.dist, "_coalescing_manager", None) if self.cuda else None
+            done = False
+            if cm is not None and not self._no_coalescing:
+                try:
+                    with cm(device=self.device):
+                        for dst, src in zip(st["all"], st["local"]):
+                            self.dist.all_gather_into_tensor(dst, src)
+                    done = True
+                except (RuntimeError, ValueError, TypeError):
+                    self._no_coalescing = True
+            if not done:
+                for dst, src in zip(st["all"], st["local"]):
+                    self.dist.all_gather_into_tensor(dst, src)
         g_ret, _, g_rules = st["all"]
         if self.stats_fn is not None:
             self.stats_fn(g_ret, g_rules, g_ret.numel(), st["stats"])

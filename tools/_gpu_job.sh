@@ -1,6 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2d_bench_c3_2gpu.json 2> gpurun_out/r2d_bench_c3_2gpu.err
-echo "stdout lines: $(wc -l < gpurun_out/r2d_bench_c3_2gpu.json)"; head -c 150 gpurun_out/r2d_bench_c3_2gpu.json; echo; grep -c "NCCL version" gpurun_out/r2d_bench_c3_2gpu.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r2d_ref_2gpu.json 2> gpurun_out/r2d_ref_2gpu.err; echo "reference arm stdout lines: $(wc -l < gpurun_out/r2d_ref_2gpu.json)"; head -c 200 gpurun_out/r2d_ref_2gpu.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2e_bench_c3_8gpu.json 2> gpurun_out/r2e_bench_c3_8gpu.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2e_bench_c3_8gpu.json").read().strip().split("\n")[-1]); print('c3 8 GPUs', '%.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'e2e ms %.3f'%d['e2e']['ms_per_step'], d.get('ms_per_step_by_rank'))
+PY
+echo "stdout lines $(wc -l < gpurun_out/r2e_bench_c3_8gpu.json)"
